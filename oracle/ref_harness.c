@@ -1,0 +1,130 @@
+/* oracle/ref_harness.c -- TEST INFRASTRUCTURE ONLY (never linked into libeigb200.so).
+ *
+ * Thin ctypes-callable wrappers around the UNMODIFIED reference functions on the smartpca hot
+ * path.  The reference translation unit is compiled from where it lies under /root/reference
+ * (textual #include below, `main` renamed) so that its file-static thread table
+ * (smartpca.c:526-534) is reachable; nothing from the reference is copied into this repository.
+ * Built by oracle/Makefile into oracle/_ref/libeigref.so (git-ignored, travels with gpurun).
+ *
+ * Each wrapper only marshals flat arrays into the reference's SNP / Indiv structs and then runs
+ * the reference's own calls in the order smartpca.c:main makes them:
+ *   refh_grm        -> smartpca.c:1088-1236  (getcolxz_binary1/2, domult_increment_lookup, symit2)
+ *   refh_eigvecs    -> eigsubs.c:39 (dspev_ via eigx.c:97)
+ *   refh_ridoutlier -> smartsubs.c:18
+ *   refh_fpca       -> gval.c:31 setgval + kjg_fpca.c:24 kjg_fpca
+ *   refh_gauss      -> kjg_gsl.c:96,166 (seeded Gaussian matrix)
+ */
+#define main smartpca_reference_main
+#include "eigensrc/smartpca.c"
+#undef main
+#include <time.h>
+#include <gsl/gsl_matrix.h>
+#include <gsl/gsl_rng.h>
+#include "kjg_gsl.h"
+
+static double now_s (void) { struct timespec t; clock_gettime (CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+static int dummy_gtypes[1];
+static SNP *hsnps; static SNP **hsnpp; static Indiv *hind; static Indiv **hindp;
+static void hfree (void) { free (hsnps); free (hsnpp); free (hind); free (hindp); hsnps = NULL; hsnpp = NULL; hind = NULL; hindp = NULL; }
+static void hbuild (const unsigned char *packed, long nsnp, long rl, int nind)
+{
+  long i;
+  hfree ();
+  hsnps = (SNP *) calloc (nsnp, sizeof (SNP)); hsnpp = (SNP **) calloc (nsnp, sizeof (SNP *));
+  hind = (Indiv *) calloc (nind, sizeof (Indiv)); hindp = (Indiv **) calloc (nind, sizeof (Indiv *));
+  for (i = 0; i < nsnp; i++) {
+    snprintf (hsnps[i].ID, IDSIZE, "s%ld", i);
+    hsnps[i].pbuff = (char *) packed + i * rl; hsnps[i].ngtypes = nind; hsnps[i].gtypes = dummy_gtypes;
+    hsnps[i].chrom = 1; hsnps[i].weight = 1.0; hsnpp[i] = hsnps + i;
+  }
+  for (i = 0; i < nind; i++) { snprintf (hind[i].ID, IDSIZE, "i%ld", i); hind[i].affstatus = YES; hind[i].egroup = "P"; hindp[i] = hind + i; }
+  packmode = YES;
+}
+
+/* One pass of the GRM region. Outputs are per input SNP (length nsnp):
+ * c0,c1 (=n0,n1; -1 if all missing), nmiss (-1 if all missing), used (1 if it entered XTX), xmean,xfancy.
+ * XTX_out: nrows*nrows row-major after symit2, NOT yet divided by y; *y_out = trace/(nrows-1).
+ * secs[0] = wall seconds of the per-SNP loop (stats+pack+lookup), secs[1] = seconds inside domult_increment_lookup. */
+int refh_grm (const unsigned char *packed, long nsnp, long rl, int nind, const int *xindex_in, int nrows,
+              int fancy, int altnorm, int minac, int maxmiss, const double *weights, int nthreads,
+              int *c0, int *c1, int *nmiss, unsigned char *used, double *xmean_o, double *xfancy_o,
+              double *XTX_out, double *y_out, double *secs)
+{
+  long i; int n0, n1, t, tt, xblock = 0, blocksize = 20; uint32_t thread_ct; double y, t0, t1, tl = 0;
+  pthread_t threads[MAX_THREADS];
+  int *rawcol, *xidx; uintptr_t *bc, *bm; double *tblock, *lut, cc[3];
+  hbuild (packed, nsnp, rl, nind);
+  fancynorm = fancy; altnormstyle = altnorm;
+  thread_ct = nthreads < 1 ? 1 : nthreads; if (thread_ct > MAX_THREADS) thread_ct = MAX_THREADS;
+  if (thread_ct > (uint32_t) nrows * 2) { thread_ct = nrows / 2; if (!thread_ct) thread_ct = 1; }
+  triangle_fill (g_thread_start, nrows, thread_ct, 0, 1, 0, 1);
+  ZALLOC (rawcol, nrows, int); ZALLOC (bc, nrows, uintptr_t); ZALLOC (bm, nrows, uintptr_t);
+  ZALLOC (tblock, 3 * blocksize, double); ZALLOC (lut, 131072, double); ZALLOC (xidx, nrows, int);
+  memcpy (xidx, xindex_in, sizeof (int) * nrows);
+  vzero (XTX_out, ((long) nrows * (nrows + 1)) / 2);
+  t0 = now_s ();
+  for (i = 0; i < nsnp; i++) {
+    tt = getcolxz_binary1 (rawcol, cc, hsnpp[i], xidx, nrows, (int) i, xmean_o, xfancy_o, &n0, &n1);
+    c0[i] = n0; c1[i] = n1; nmiss[i] = tt; used[i] = 0;
+    t = MIN (n0, n1);
+    if ((t < minac) || (tt > maxmiss) || (tt < 0) || (t == 0)) continue;
+    getcolxz_binary2 (rawcol, bc, bm, xblock, nrows);
+    if (weights) vst (cc, cc, weights[i], 3);
+    copyarr (cc, &(tblock[xblock * 3]), 3);
+    used[i] = 1; ++xblock;
+    if (xblock == blocksize) {
+      t1 = now_s ();
+      domult_increment_lookup (threads, thread_ct, XTX_out, tblock, bc, bm, xblock, nrows, lut);
+      tl += now_s () - t1;
+      memset (bc, 0, sizeof (uintptr_t) * nrows); memset (bm, 0, sizeof (uintptr_t) * nrows);
+      vzero (tblock, 3 * blocksize); xblock = 0;
+    }
+  }
+  if (xblock > 0) { t1 = now_s (); domult_increment_lookup (threads, thread_ct, XTX_out, tblock, bc, bm, xblock, nrows, lut); tl += now_s () - t1; }
+  if (secs) { secs[0] = now_s () - t0; secs[1] = tl; }
+  symit2 (XTX_out, nrows);
+  y = trace (XTX_out, nrows) / (double) (nrows - 1);
+  *y_out = y;
+  free (rawcol); free (bc); free (bm); free (tblock); free (lut); free (xidx); hfree ();
+  return 0;
+}
+
+void refh_eigvecs (double *mat, double *evals, double *evecs, int n) { eigvecs (mat, evals, evecs, n); }
+
+int refh_ridoutlier (double *evecs, int n, int neigs, double thresh, int mode, int *badlist, int *vecno, double *score)
+{
+  OUTLINFO **oi; int k, nbad;
+  oi = (OUTLINFO **) calloc (n, sizeof (OUTLINFO *));
+  for (k = 0; k < n; k++) oi[k] = (OUTLINFO *) calloc (1, sizeof (OUTLINFO));
+  setoutliermode (mode);
+  nbad = ridoutlier (evecs, n, neigs, thresh, badlist, oi);
+  for (k = 0; k < n; k++) { vecno[k] = oi[k]->vecno; score[k] = oi[k]->score; free (oi[k]); }
+  free (oi);
+  return nbad;
+}
+
+/* fastmode: evec is n*K row-major exactly as kjg_fpca leaves it (before smartpca.c:971 transposes). */
+int refh_fpca (const unsigned char *packed, long nsnp, long rl, int nind, const int *xindex_in, int nrows,
+               int fancy, int altnorm, long K, long L, long I, long seed_in, double *eval, double *evec, double *secs)
+{
+  int *xidx, *xt; double t0;
+  hbuild (packed, nsnp, rl, nind);
+  fancynorm = fancy; altnormstyle = altnorm; usepopsformissing = NO; seed = seed_in;
+  ZALLOC (xidx, nrows, int); ZALLOC (xt, nrows, int); memcpy (xidx, xindex_in, sizeof (int) * nrows);
+  setgval (hsnpp, nrows, hindp, nind, xidx, xt, (int) nsnp);
+  t0 = now_s ();
+  kjg_fpca (K, L, I, eval, evec);
+  if (secs) secs[0] = now_s () - t0;
+  unsetgval (); free (xidx); free (xt); hfree ();
+  return 0;
+}
+
+void refh_gauss (long seed_in, long n, long L, double *out)
+{
+  gsl_matrix_view v = gsl_matrix_view_array (out, n, L); gsl_rng *r;
+  seed = seed_in; r = kjg_gsl_rng_init (); kjg_gsl_ran_ugaussian_matrix (r, &v.matrix); gsl_rng_free (r);
+}
+
+unsigned long refh_mt_first (unsigned long s) { gsl_rng *r; unsigned long v; gsl_rng_default_seed = s; r = gsl_rng_alloc (gsl_rng_default); v = gsl_rng_get (r); gsl_rng_free (r); return v; }
+void refh_openblas_threads (int n) { extern void openblas_set_num_threads (int); openblas_set_num_threads (n); }
