@@ -1,0 +1,208 @@
+"""ctypes bindings for the CHECKERS (test infrastructure only).
+
+`port()`  -> oracle/liboracle.so   (plain-C restatement, eig_oracle.c)
+`ref()`   -> oracle/_ref/libeigref.so (the unmodified reference behind ref_harness.c)
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) import this module.
+The product package eig_b200 never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def build(ref=True):
+    """(Re)build the checkers; the reference part is skipped when /root/reference is absent."""
+    subprocess.run(["make", "-s", "-C", HERE, "port"] + (["ref"] if ref else []), check=True)
+
+
+_port = None
+_ref = None
+
+
+def port():
+    global _port
+    if _port is None:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        _port = C.CDLL(path)
+        _port.orc_mt_first.restype = C.c_uint32
+        _port.orc_mt_first.argtypes = [C.c_ulong]
+    return _port
+
+
+def ref():
+    """The compiled reference; None when it was never built (no /root/reference and no prebuilt copy)."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(HERE, "_ref", "libeigref.so")
+        if not os.path.exists(path):
+            if os.path.exists("/root/reference/src/eigensrc/smartpca.c"):
+                build(ref=True)
+            else:
+                return None
+        _ref = C.CDLL(path)
+        _ref.refh_mt_first.restype = C.c_ulong
+        _ref.refh_mt_first.argtypes = [C.c_ulong]
+    return _ref
+
+
+def ref_smartpca_binary():
+    p = os.path.join(HERE, "_ref", "smartpca")
+    return p if os.path.exists(p) else None
+
+
+def _xi(xindex, nind):
+    return np.ascontiguousarray(np.arange(nind) if xindex is None else xindex, dtype=np.int32)
+
+
+# ----------------------------------------------------------------------------- port
+def port_snp_counts(packed, xindex=None, numindivs=None):
+    nsnp, rlen = packed.shape
+    xi = _xi(xindex, numindivs)
+    c0 = np.empty(nsnp, np.int32); c1 = np.empty(nsnp, np.int32); nm = np.empty(nsnp, np.int32)
+    port().orc_snp_counts(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen),
+                          xi.ctypes.data_as(C.c_void_p), C.c_int(len(xi)),
+                          c0.ctypes.data_as(C.c_void_p), c1.ctypes.data_as(C.c_void_p), nm.ctypes.data_as(C.c_void_p))
+    return c0, c1, nm
+
+
+def port_indiv_valid_counts(packed, numindivs, snp_keep=None):
+    nsnp, rlen = packed.shape
+    out = np.empty(numindivs, np.int32)
+    keep = None if snp_keep is None else np.ascontiguousarray(snp_keep, np.uint8)
+    port().orc_indiv_valid_counts(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen), C.c_int(numindivs),
+                                  keep.ctypes.data_as(C.c_void_p) if keep is not None else None,
+                                  out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def _grm_call(fn, packed, numindivs, xindex, fancynorm, altnormstyle, minallelecnt, maxmissing, weights, extra):
+    nsnp, rlen = packed.shape
+    xi = _xi(xindex, numindivs)
+    n = len(xi)
+    r = dict(c0=np.empty(nsnp, np.int32), c1=np.empty(nsnp, np.int32), nmiss=np.empty(nsnp, np.int32),
+             used=np.empty(nsnp, np.uint8), xmean=np.zeros(nsnp), xfancy=np.zeros(nsnp),
+             XTX=np.zeros((n, n)), y=np.zeros(1))
+    w = None if weights is None else np.ascontiguousarray(weights, np.float64)
+    fn(packed, xi, n, fancynorm, altnormstyle, minallelecnt, maxmissing, w, r, extra)
+    r["y"] = float(r["y"][0])
+    return r
+
+
+def port_grm(packed, numindivs, xindex=None, fancynorm=1, altnormstyle=1, minallelecnt=1, maxmissing=9999999, weights=None):
+    def fn(packed, xi, n, fn_, an, mac, mm, w, r, _):
+        nsnp, rlen = packed.shape
+        port().orc_grm(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen), xi.ctypes.data_as(C.c_void_p), C.c_int(n),
+                       C.c_int(fn_), C.c_int(an), C.c_int(mac), C.c_int(mm), w.ctypes.data_as(C.c_void_p) if w is not None else None,
+                       *[r[k].ctypes.data_as(C.c_void_p) for k in ("c0", "c1", "nmiss", "used", "xmean", "xfancy", "XTX", "y")])
+    return _grm_call(fn, packed, numindivs, xindex, fancynorm, altnormstyle, minallelecnt, maxmissing, weights, None)
+
+
+def port_eigvecs(mat, want_vectors=True):
+    mat = np.ascontiguousarray(mat, np.float64); n = mat.shape[0]
+    ev = np.empty(n); vec = np.empty((n, n)) if want_vectors else None
+    rc = port().orc_eigvecs(mat.ctypes.data_as(C.c_void_p), ev.ctypes.data_as(C.c_void_p),
+                            vec.ctypes.data_as(C.c_void_p) if want_vectors else None, C.c_int(n))
+    assert rc == 0
+    return ev, vec
+
+
+def port_ridoutlier(evecs, neigs, thresh=6.0, mode=0):
+    evecs = np.ascontiguousarray(evecs, np.float64); n = evecs.shape[1]
+    bad = np.empty(n, np.int32); vecno = np.empty(n, np.int32); score = np.zeros(n)
+    nb = port().orc_ridoutlier(evecs.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(neigs), C.c_double(thresh), C.c_int(mode),
+                               bad.ctypes.data_as(C.c_void_p), vecno.ctypes.data_as(C.c_void_p), score.ctypes.data_as(C.c_void_p))
+    return bad[:nb].copy(), vecno, score
+
+
+def port_gauss(seed, n, L):
+    out = np.empty((n, L))
+    port().orc_gauss_matrix(C.c_long(seed), C.c_long(n), C.c_long(L), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def port_gtable(packed, numindivs, xindex=None, fancynorm=1, altnormstyle=1):
+    nsnp, rlen = packed.shape; xi = _xi(xindex, numindivs)
+    gt = np.empty((nsnp, 4)); mono = np.empty(nsnp, np.uint8)
+    port().orc_gtable(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen), xi.ctypes.data_as(C.c_void_p), C.c_int(len(xi)),
+                      C.c_int(fancynorm), C.c_int(altnormstyle), gt.ctypes.data_as(C.c_void_p), mono.ctypes.data_as(C.c_void_p))
+    return gt, mono
+
+
+def port_fpca(packed, numindivs, K, L, I, seed, xindex=None, fancynorm=1, altnormstyle=1):
+    nsnp, rlen = packed.shape; xi = _xi(xindex, numindivs); n = len(xi)
+    ev = np.empty(K); vec = np.empty((n, K))
+    rc = port().orc_fpca(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen), xi.ctypes.data_as(C.c_void_p), C.c_long(n),
+                         C.c_int(fancynorm), C.c_int(altnormstyle), C.c_long(K), C.c_long(L), C.c_long(I), C.c_long(seed),
+                         ev.ctypes.data_as(C.c_void_p), vec.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return ev, vec
+
+
+def port_project(packed, numindivs, used, xmean, xfancy, evecs, xindex=None):
+    nsnp, rlen = packed.shape; xi = _xi(xindex, numindivs); n = len(xi)
+    evecs = np.ascontiguousarray(evecs, np.float64); k = evecs.shape[0]
+    ff = np.empty((k, nsnp)); fx = np.empty((k, n)); sc = np.empty(k)
+    port().orc_project(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen), xi.ctypes.data_as(C.c_void_p), C.c_int(n),
+                       np.ascontiguousarray(used, np.uint8).ctypes.data_as(C.c_void_p),
+                       np.ascontiguousarray(xmean).ctypes.data_as(C.c_void_p), np.ascontiguousarray(xfancy).ctypes.data_as(C.c_void_p),
+                       evecs.ctypes.data_as(C.c_void_p), C.c_int(k),
+                       ff.ctypes.data_as(C.c_void_p), fx.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p))
+    return ff, fx, sc
+
+
+# ----------------------------------------------------------------------------- reference (oracle/_ref)
+def ref_grm(packed, numindivs, xindex=None, fancynorm=1, altnormstyle=1, minallelecnt=1, maxmissing=9999999,
+            weights=None, nthreads=None):
+    secs = np.zeros(2)
+
+    def fn(packed, xi, n, fn_, an, mac, mm, w, r, nthr):
+        nsnp, rlen = packed.shape
+        ref().refh_grm(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen), C.c_int(numindivs),
+                       xi.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(fn_), C.c_int(an), C.c_int(mac), C.c_int(mm),
+                       w.ctypes.data_as(C.c_void_p) if w is not None else None, C.c_int(nthr),
+                       *[r[k].ctypes.data_as(C.c_void_p) for k in ("c0", "c1", "nmiss", "used", "xmean", "xfancy", "XTX", "y")],
+                       secs.ctypes.data_as(C.c_void_p))
+    r = _grm_call(fn, packed, numindivs, xindex, fancynorm, altnormstyle, minallelecnt, maxmissing, weights,
+                  nthreads or os.cpu_count())
+    r["secs_loop"], r["secs_lookup"] = float(secs[0]), float(secs[1])
+    return r
+
+
+def ref_eigvecs(mat):
+    mat = np.ascontiguousarray(mat, np.float64).copy(); n = mat.shape[0]
+    ev = np.empty(n); vec = np.empty((n, n))
+    ref().refh_eigvecs(mat.ctypes.data_as(C.c_void_p), ev.ctypes.data_as(C.c_void_p), vec.ctypes.data_as(C.c_void_p), C.c_int(n))
+    return ev, vec
+
+
+def ref_ridoutlier(evecs, neigs, thresh=6.0, mode=0):
+    evecs = np.ascontiguousarray(evecs, np.float64).copy(); n = evecs.shape[1]
+    bad = np.empty(n, np.int32); vecno = np.empty(n, np.int32); score = np.zeros(n)
+    nb = ref().refh_ridoutlier(evecs.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(neigs), C.c_double(thresh), C.c_int(mode),
+                               bad.ctypes.data_as(C.c_void_p), vecno.ctypes.data_as(C.c_void_p), score.ctypes.data_as(C.c_void_p))
+    return bad[:nb].copy(), vecno, score
+
+
+def ref_gauss(seed, n, L):
+    out = np.empty((n, L))
+    ref().refh_gauss(C.c_long(seed), C.c_long(n), C.c_long(L), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def ref_fpca(packed, numindivs, K, L, I, seed, xindex=None, fancynorm=1, altnormstyle=1):
+    nsnp, rlen = packed.shape; xi = _xi(xindex, numindivs); n = len(xi)
+    ev = np.empty(K); vec = np.empty((n, K)); secs = np.zeros(1)
+    ref().refh_fpca(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen), C.c_int(numindivs),
+                    xi.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(fancynorm), C.c_int(altnormstyle),
+                    C.c_long(K), C.c_long(L), C.c_long(I), C.c_long(seed),
+                    ev.ctypes.data_as(C.c_void_p), vec.ctypes.data_as(C.c_void_p), secs.ctypes.data_as(C.c_void_p))
+    return ev, vec, float(secs[0])
