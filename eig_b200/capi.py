@@ -1,0 +1,259 @@
+"""ctypes mirror of include/eigb200.h (the C-ABI of libeigb200.so).  No compute happens in Python.
+
+The library is loaded lazily; if it is missing it is built with nvcc (eig_b200/build.py).  Every entry point
+raises EigB200Error when the library reports an error -- in particular when no B200 is visible: there is no
+CPU fallback.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from . import build as _build
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libeigb200.so")
+
+
+class EigB200Error(RuntimeError):
+    pass
+
+
+class GrmOpts(C.Structure):
+    _fields_ = [("fancynorm", C.c_int), ("altnormstyle", C.c_int), ("minallelecnt", C.c_int), ("maxmissing", C.c_int),
+                ("snp_ignore", C.c_void_p), ("snp_weight", C.c_void_p)]
+
+
+class PcaOpts(C.Structure):
+    _fields_ = [("grm", GrmOpts), ("numeigs", C.c_int), ("numoutliter", C.c_int), ("numoutleigs", C.c_int),
+                ("outlthresh", C.c_double), ("outliermode", C.c_int)]
+
+
+class PcaResult(C.Structure):
+    _fields_ = [("nrows_final", C.c_int), ("niter", C.c_int), ("nremoved", C.c_int), ("nused", C.c_int64), ("y", C.c_double),
+                ("secs_grm", C.c_double), ("secs_eig", C.c_double), ("secs_total", C.c_double)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("gather_ms", C.c_float), ("stats_ms", C.c_float), ("grm_ms", C.c_float), ("finalize_ms", C.c_float),
+                ("tridiag_ms", C.c_float), ("bisect_ms", C.c_float), ("vectors_ms", C.c_float),
+                ("grm_launches", C.c_int), ("nsplit", C.c_int)]
+
+
+EXPORTS = [
+    "eb_last_error", "eb_version", "eb_create", "eb_destroy", "eb_device_count", "eb_stream", "eb_sync", "eb_launch_count",
+    "eb_reset_launch_count", "eb_upload_packed", "eb_upload_packed_rows", "eb_adopt_packed_device", "eb_synth_packed_device",
+    "eb_set_rows", "eb_snp_counts", "eb_indiv_valid_counts", "eb_grm", "eb_grm_partial", "eb_grm_device_ptr", "eb_grm_finish",
+    "eb_eig", "eb_eigvecs", "eb_ridoutlier", "eb_pca_full", "eb_fpca", "eb_gauss_matrix", "eb_project", "eb_get_timings",
+    "eb_microbench_fp64",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH) or (os.path.exists("/usr/local/cuda/bin/nvcc") and _build.needs_build()):
+            _build.build()
+        L = C.CDLL(LIB_PATH)
+        L.eb_last_error.restype = C.c_char_p
+        L.eb_create.restype = C.c_void_p
+        L.eb_create.argtypes = [C.c_int]
+        L.eb_destroy.argtypes = [C.c_void_p]
+        L.eb_stream.restype = C.c_void_p
+        L.eb_stream.argtypes = [C.c_void_p]
+        L.eb_launch_count.restype = C.c_int64
+        L.eb_launch_count.argtypes = [C.c_void_p]
+        L.eb_grm_device_ptr.restype = C.c_void_p
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _chk(rc):
+    if rc != 0:
+        raise EigB200Error("libeigb200: %s (code %d)" % (lib().eb_last_error().decode(), rc))
+
+
+def gauss_matrix(seed, n, L):
+    out = np.empty((n, L))
+    lib().eb_gauss_matrix(C.c_long(seed), C.c_size_t(n), C.c_size_t(L), _p(out))
+    return out
+
+
+def ridoutlier(evecs, neigs, thresh=6.0, outliermode=0):
+    evecs = np.ascontiguousarray(evecs, np.float64); n = evecs.shape[1]
+    bad = np.empty(n, np.int32); vecno = np.empty(n, np.int32); score = np.zeros(n)
+    nb = lib().eb_ridoutlier(_p(evecs), C.c_int(n), C.c_int(neigs), C.c_double(thresh), C.c_int(outliermode), _p(bad), _p(vecno), _p(score))
+    return bad[:nb].copy(), vecno, score
+
+
+class Context:
+    """One eb_ctx = one GPU."""
+
+    def __init__(self, device=-1):
+        self.h = lib().eb_create(device)
+        if not self.h:
+            raise EigB200Error("libeigb200: %s" % lib().eb_last_error().decode())
+        self.h = C.c_void_p(self.h)
+        self.nsnp = self.numindivs = self.nrows = 0
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            lib().eb_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- store
+    def upload_packed(self, packed, numindivs):
+        packed = np.ascontiguousarray(packed, np.uint8)
+        self.nsnp, rlen = packed.shape
+        self.numindivs = numindivs
+        _chk(lib().eb_upload_packed(self.h, _p(packed), C.c_int64(self.nsnp), C.c_int64(rlen), C.c_int(numindivs)))
+        _chk(lib().eb_sync(self.h))
+
+    def adopt_packed_device(self, dev_ptr, nsnp, pitch, numindivs):
+        self.nsnp, self.numindivs = nsnp, numindivs
+        _chk(lib().eb_adopt_packed_device(self.h, C.c_void_p(dev_ptr), C.c_int64(nsnp), C.c_int64(pitch), C.c_int(numindivs)))
+
+    def synth_packed_device(self, dev_ptr, nsnp, pitch, numindivs, seed, s0=0, missing=0.0, npops=1, delta=0.0):
+        _chk(lib().eb_synth_packed_device(self.h, C.c_void_p(dev_ptr), C.c_int64(nsnp), C.c_int64(pitch), C.c_int(numindivs),
+                                          C.c_uint64(seed), C.c_int64(s0), C.c_double(missing), C.c_int(npops), C.c_double(delta)))
+
+    def set_rows(self, xindex=None):
+        if xindex is None:
+            self.nrows = self.numindivs
+            _chk(lib().eb_set_rows(self.h, None, C.c_int(self.numindivs)))
+        else:
+            xi = np.ascontiguousarray(xindex, np.int32); self.nrows = len(xi)
+            _chk(lib().eb_set_rows(self.h, _p(xi), C.c_int(len(xi))))
+
+    # ---- integer reductions
+    def snp_counts(self):
+        c0 = np.empty(self.nsnp, np.int32); c1 = np.empty(self.nsnp, np.int32); nm = np.empty(self.nsnp, np.int32)
+        _chk(lib().eb_snp_counts(self.h, _p(c0), _p(c1), _p(nm)))
+        return c0, c1, nm
+
+    def indiv_valid_counts(self, snp_keep=None):
+        out = np.empty(self.numindivs, np.int32)
+        keep = None if snp_keep is None else np.ascontiguousarray(snp_keep, np.uint8)
+        _chk(lib().eb_indiv_valid_counts(self.h, _p(keep), _p(out)))
+        return out
+
+    # ---- GRM
+    def _opts(self, fancynorm, altnormstyle, minallelecnt, maxmissing, snp_ignore, snp_weight):
+        ig = None if snp_ignore is None else np.ascontiguousarray(snp_ignore, np.uint8)
+        w = None if snp_weight is None else np.ascontiguousarray(snp_weight, np.float64)
+        self._keep = [ig, w]
+        return GrmOpts(fancynorm, altnormstyle, minallelecnt, maxmissing,
+                       None if ig is None else ig.ctypes.data, None if w is None else w.ctypes.data)
+
+    def grm(self, fancynorm=1, altnormstyle=1, minallelecnt=1, maxmissing=9999999, snp_ignore=None, snp_weight=None,
+            want_xtx=False, want_snp=True, partial=False):
+        o = self._opts(fancynorm, altnormstyle, minallelecnt, maxmissing, snp_ignore, snp_weight)
+        m = self.nsnp
+        r = {}
+        if want_snp:
+            r = dict(c0=np.empty(m, np.int32), c1=np.empty(m, np.int32), nmiss=np.empty(m, np.int32), used=np.empty(m, np.uint8),
+                     xmean=np.empty(m), xfancy=np.empty(m))
+        y = C.c_double(0); nused = C.c_int64(0)
+        xtx = np.empty((self.nrows, self.nrows)) if want_xtx else None
+        args = [_p(r.get(k)) for k in ("c0", "c1", "nmiss", "used", "xmean", "xfancy")]
+        if partial:
+            _chk(lib().eb_grm_partial(self.h, C.byref(o), *args, C.byref(nused)))
+        else:
+            _chk(lib().eb_grm(self.h, C.byref(o), *args, C.byref(y), C.byref(nused), _p(xtx)))
+            r["y"] = y.value
+            if want_xtx:
+                r["XTX"] = xtx
+        r["nused"] = nused.value
+        return r
+
+    def grm_device_ptr(self):
+        ld = C.c_int64(0); n = C.c_int64(0)
+        lib().eb_grm_device_ptr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        p = lib().eb_grm_device_ptr(self.h, C.byref(ld), C.byref(n))
+        return p, ld.value, n.value
+
+    def grm_finish(self, want_xtx=False):
+        y = C.c_double(0)
+        xtx = np.empty((self.nrows, self.nrows)) if want_xtx else None
+        _chk(lib().eb_grm_finish(self.h, C.byref(y), _p(xtx)))
+        return y.value, xtx
+
+    # ---- eigen
+    def eig(self, nvec):
+        lam = np.empty(self.nrows); vec = np.empty((max(nvec, 1), self.nrows))
+        _chk(lib().eb_eig(self.h, C.c_int(nvec), _p(lam), _p(vec)))
+        return lam, vec[:nvec]
+
+    def eigvecs(self, mat, nvec=None):
+        mat = np.ascontiguousarray(mat, np.float64); n = mat.shape[0]
+        nvec = n if nvec is None else nvec
+        lam = np.empty(n); vec = np.empty((max(nvec, 1), n))
+        _chk(lib().eb_eigvecs(self.h, _p(mat), _p(lam), _p(vec), C.c_int(n), C.c_int(nvec)))
+        return lam, vec[:nvec]
+
+    def pca_full(self, xindex=None, numeigs=10, numoutliter=5, numoutleigs=10, outlthresh=6.0, outliermode=0,
+                 fancynorm=1, altnormstyle=1, minallelecnt=1, maxmissing=9999999, snp_ignore=None, snp_weight=None):
+        xi = np.ascontiguousarray(np.arange(self.numindivs) if xindex is None else xindex, np.int32).copy()
+        n0 = len(xi)
+        o = PcaOpts(self._opts(fancynorm, altnormstyle, minallelecnt, maxmissing, snp_ignore, snp_weight),
+                    numeigs, numoutliter, numoutleigs, outlthresh, outliermode)
+        lam = np.empty(n0); vec = np.empty((max(numeigs, 1), n0))
+        used = np.empty(self.nsnp, np.uint8); xmean = np.empty(self.nsnp); xfancy = np.empty(self.nsnp)
+        ri = np.empty(n0, np.int32); rit = np.empty(n0, np.int32); rv = np.empty(n0, np.int32); rs = np.empty(n0)
+        res = PcaResult()
+        _chk(lib().eb_pca_full(self.h, C.byref(o), _p(xi), C.c_int(n0), _p(lam), _p(vec), _p(used), _p(xmean), _p(xfancy),
+                               _p(ri), _p(rit), _p(rv), _p(rs), C.byref(res)))
+        n = res.nrows_final; k = min(numeigs, n)
+        self.nrows = n
+        return dict(xindex=xi[:n].copy(), lambda_=lam[:n].copy(), evecs=vec.reshape(-1)[:k * n].reshape(k, n).copy(),
+                    used=used, xmean=xmean, xfancy=xfancy, removed_index=ri[:res.nremoved].copy(),
+                    removed_iter=rit[:res.nremoved].copy(), removed_vecno=rv[:res.nremoved].copy(),
+                    removed_score=rs[:res.nremoved].copy(), niter=res.niter, nused=res.nused, y=res.y,
+                    secs_grm=res.secs_grm, secs_eig=res.secs_eig, secs_total=res.secs_total)
+
+    # ---- fastmode / projections
+    def fpca(self, K, L, I, seed, fancynorm=1, altnormstyle=1):
+        ev = np.empty(K); vec = np.empty((self.nrows, K))
+        _chk(lib().eb_fpca(self.h, C.c_int(fancynorm), C.c_int(altnormstyle), C.c_size_t(K), C.c_size_t(L), C.c_size_t(I),
+                           C.c_long(seed), _p(ev), _p(vec)))
+        return ev, vec
+
+    def project(self, evecs):
+        evecs = np.ascontiguousarray(evecs, np.float64); k = evecs.shape[0]
+        ff = np.empty((k, self.nsnp)); fx = np.empty((k, self.nrows)); sc = np.empty(k)
+        _chk(lib().eb_project(self.h, _p(evecs), C.c_int(k), _p(ff), _p(fx), _p(sc)))
+        return ff, fx, sc
+
+    # ---- measurement
+    def timings(self):
+        t = Timings()
+        _chk(lib().eb_get_timings(self.h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in Timings._fields_}
+
+    def launch_count(self):
+        return lib().eb_launch_count(self.h)
+
+    def reset_launch_count(self):
+        lib().eb_reset_launch_count(self.h)
+
+    def stream(self):
+        return lib().eb_stream(self.h)
+
+    def sync(self):
+        _chk(lib().eb_sync(self.h))
+
+    def microbench_fp64(self):
+        a = C.c_double(0); b = C.c_double(0)
+        _chk(lib().eb_microbench_fp64(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value

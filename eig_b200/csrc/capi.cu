@@ -1,0 +1,431 @@
+// capi.cu -- extern "C" entry points of libeigb200.so (declared in include/eigb200.h) and host orchestration.
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include "common.cuh"
+
+namespace eb {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace eb
+
+using namespace eb;
+
+extern "C" {
+
+const char* eb_last_error(void) { return g_err; }
+int eb_version(void) { return 100; }
+
+int eb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+eb_ctx* eb_create(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    set_error("eb_create: no CUDA device visible (libeigb200 has no CPU fallback)");
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  if (device >= n) { set_error("eb_create: device %d out of range (%d visible)", device, n); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { set_error("eb_create: cudaSetDevice(%d) failed", device); return nullptr; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_error("eb_create: cudaGetDeviceProperties failed"); return nullptr; }
+  if (prop.major != 10) {
+    set_error("eb_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return nullptr;
+  }
+  eb_ctx* c = new eb_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("eb_create: stream"); delete c; return nullptr; }
+  for (int i = 0; i < 8; i++) cudaEventCreate(&c->ev[i]);
+  return c;
+}
+
+void eb_destroy(eb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+void* eb_stream(eb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int eb_sync(eb_ctx* c) {
+  if (!c) return EB_ERR_ARG;
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int64_t eb_launch_count(eb_ctx* c) { return c ? c->launches : 0; }
+void eb_reset_launch_count(eb_ctx* c) { if (c) c->launches = 0; }
+
+static int set_store(eb_ctx* c, int64_t nsnp, int numindivs) {
+  if (nsnp <= 0 || numindivs <= 0) { set_error("bad shape: nsnp=%lld numindivs=%d", (long long)nsnp, numindivs); return EB_ERR_ARG; }
+  c->nsnp = nsnp; c->numindivs = numindivs;
+  c->mpad = (nsnp + SNP_PAD - 1) / SNP_PAD * SNP_PAD;
+  c->rows_set = false; c->grm_valid = false;
+  int rc;
+  if ((rc = c->c0_d.ensure(c->mpad)) || (rc = c->c1_d.ensure(c->mpad)) || (rc = c->nmiss_d.ensure(c->mpad)) ||
+      (rc = c->used_d.ensure(c->mpad)) || (rc = c->ignore_d.ensure(c->mpad)) || (rc = c->xmean_d.ensure(c->mpad)) ||
+      (rc = c->xfancy_d.ensure(c->mpad)) || (rc = c->weight_d.ensure(c->mpad)) || (rc = c->table_d.ensure(c->mpad * 4)) ||
+      (rc = c->nused_d.ensure(1)))
+    return rc;
+  return 0;
+}
+
+int eb_upload_packed(eb_ctx* c, const uint8_t* packed, int64_t nsnp, int64_t rlen, int numindivs) {
+  if (!c || !packed) { set_error("eb_upload_packed: null argument"); return EB_ERR_ARG; }
+  if (rlen * 4 < numindivs) { set_error("eb_upload_packed: rlen %lld too small for %d individuals", (long long)rlen, numindivs); return EB_ERR_ARG; }
+  EB_CUDA(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = c->raw_own.ensure((size_t)nsnp * rlen))) return rc;
+  EB_CUDA(cudaMemcpyAsync(c->raw_own.p, packed, (size_t)nsnp * rlen, cudaMemcpyHostToDevice, c->stream));
+  c->raw = c->raw_own.p; c->raw_pitch = rlen;
+  return set_store(c, nsnp, numindivs);
+}
+
+int eb_upload_packed_rows(eb_ctx* c, const uint8_t* const* rows, int64_t nsnp, int64_t rlen, int numindivs) {
+  if (!c || !rows) { set_error("eb_upload_packed_rows: null argument"); return EB_ERR_ARG; }
+  if (rlen * 4 < numindivs) { set_error("eb_upload_packed_rows: rlen too small"); return EB_ERR_ARG; }
+  EB_CUDA(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = c->raw_own.ensure((size_t)nsnp * rlen))) return rc;
+  // coalesce runs of rows that are contiguous in host memory (the usual case: one packgenos slab)
+  int64_t i = 0;
+  while (i < nsnp) {
+    int64_t j = i + 1;
+    while (j < nsnp && rows[j] == rows[j - 1] + rlen) j++;
+    EB_CUDA(cudaMemcpyAsync(c->raw_own.p + (size_t)i * rlen, rows[i], (size_t)(j - i) * rlen, cudaMemcpyHostToDevice, c->stream));
+    i = j;
+  }
+  c->raw = c->raw_own.p; c->raw_pitch = rlen;
+  return set_store(c, nsnp, numindivs);
+}
+
+int eb_adopt_packed_device(eb_ctx* c, const void* dev, int64_t nsnp, int64_t pitch, int numindivs) {
+  if (!c || !dev) { set_error("eb_adopt_packed_device: null argument"); return EB_ERR_ARG; }
+  if (pitch * 4 < numindivs) { set_error("eb_adopt_packed_device: pitch too small"); return EB_ERR_ARG; }
+  EB_CUDA(cudaSetDevice(c->device));
+  c->raw_own.release();
+  c->raw = static_cast<const uint8_t*>(dev); c->raw_pitch = pitch;
+  return set_store(c, nsnp, numindivs);
+}
+
+int eb_synth_packed_device(eb_ctx* c, void* dev, int64_t nsnp, int64_t pitch, int numindivs, uint64_t seed, int64_t s0,
+                           double missing, int npops, double delta) {
+  if (!c || !dev) { set_error("eb_synth_packed_device: null argument"); return EB_ERR_ARG; }
+  EB_CUDA(cudaSetDevice(c->device));
+  return launch_synth(c, static_cast<uint8_t*>(dev), nsnp, pitch, numindivs, seed, s0, missing, npops, delta);
+}
+
+int eb_set_rows(eb_ctx* c, const int* xindex, int nrows) {
+  if (!c) return EB_ERR_ARG;
+  if (!c->raw) { set_error("eb_set_rows: no genotype store uploaded"); return EB_ERR_STATE; }
+  if (!xindex) nrows = c->numindivs;
+  if (nrows <= 0 || nrows > c->numindivs) { set_error("eb_set_rows: nrows=%d out of range", nrows); return EB_ERR_ARG; }
+  EB_CUDA(cudaSetDevice(c->device));
+  c->xindex_h.resize(nrows);
+  for (int i = 0; i < nrows; i++) {
+    const int v = xindex ? xindex[i] : i;
+    if (v < 0 || v >= c->numindivs || (i > 0 && v <= c->xindex_h[i - 1])) { set_error("eb_set_rows: xindex must be ascending within [0,numindivs)"); return EB_ERR_ARG; }
+    c->xindex_h[i] = v;
+  }
+  c->nrows = nrows;
+  c->npad = (nrows + TILE - 1) / TILE * TILE;
+  c->wpitch = c->npad / 4;
+  int rc;
+  if ((rc = c->xindex_d.ensure(nrows))) return rc;
+  if ((rc = c->work.ensure((size_t)c->mpad * c->wpitch))) return rc;
+  // the synchronous copy also orders the host vector against later reuse
+  EB_CUDA(cudaMemcpyAsync(c->xindex_d.p, c->xindex_h.data(), sizeof(int) * nrows, cudaMemcpyHostToDevice, c->stream));
+  EB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  if ((rc = launch_gather(c))) return rc;
+  EB_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->tm.gather_ms, c->ev[0], c->ev[1]);
+  c->rows_set = true; c->grm_valid = false;
+  return 0;
+}
+
+static int need_rows(eb_ctx* c, const char* who) {
+  if (!c) return EB_ERR_ARG;
+  if (!c->rows_set) { set_error("%s: call eb_upload_packed + eb_set_rows first", who); return EB_ERR_STATE; }
+  EB_CUDA(cudaSetDevice(c->device));
+  return 0;
+}
+
+static int stage_opts(eb_ctx* c, const eb_grm_opts* o) {
+  if (o->snp_ignore) EB_CUDA(cudaMemcpyAsync(c->ignore_d.p, o->snp_ignore, (size_t)c->nsnp, cudaMemcpyHostToDevice, c->stream));
+  if (o->snp_weight) EB_CUDA(cudaMemcpyAsync(c->weight_d.p, o->snp_weight, sizeof(double) * (size_t)c->nsnp, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
+static int fetch_snp_outputs(eb_ctx* c, int* c0, int* c1, int* nmiss, uint8_t* used, double* xmean, double* xfancy, int64_t* nused) {
+  const size_t m = (size_t)c->nsnp;
+  if (c0) EB_CUDA(cudaMemcpyAsync(c0, c->c0_d.p, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+  if (c1) EB_CUDA(cudaMemcpyAsync(c1, c->c1_d.p, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+  if (nmiss) EB_CUDA(cudaMemcpyAsync(nmiss, c->nmiss_d.p, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+  if (used) EB_CUDA(cudaMemcpyAsync(used, c->used_d.p, m, cudaMemcpyDeviceToHost, c->stream));
+  if (xmean) EB_CUDA(cudaMemcpyAsync(xmean, c->xmean_d.p, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+  if (xfancy) EB_CUDA(cudaMemcpyAsync(xfancy, c->xfancy_d.p, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
+  long long nu = 0;
+  EB_CUDA(cudaMemcpyAsync(&nu, c->nused_d.p, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  c->nused = nu;
+  if (nused) *nused = nu;
+  return 0;
+}
+
+int eb_snp_counts(eb_ctx* c, int* c0, int* c1, int* nmiss) {
+  int rc;
+  if ((rc = need_rows(c, "eb_snp_counts"))) return rc;
+  eb_grm_opts o = {1, 1, 0, 2147483647, nullptr, nullptr};
+  if ((rc = launch_stats(c, &o))) return rc;
+  c->grm_valid = false;
+  if ((rc = fetch_snp_outputs(c, c0, c1, nmiss, nullptr, nullptr, nullptr, nullptr))) return rc;
+  // plain counts: the all-missing sentinel (-1) of getcolxz_binary1 is reported as c0=c1=0, nmiss=nrows
+  for (int64_t s = 0; s < c->nsnp; s++) {
+    if (nmiss && nmiss[s] < 0) { nmiss[s] = c->nrows; if (c0) c0[s] = 0; if (c1) c1[s] = 0; }
+    else if (!nmiss && c0 && c0[s] < 0) { c0[s] = 0; if (c1) c1[s] = 0; }
+  }
+  return 0;
+}
+
+int eb_indiv_valid_counts(eb_ctx* c, const uint8_t* snp_keep, int* nvalid) {
+  if (!c || !nvalid) return EB_ERR_ARG;
+  if (!c->raw) { set_error("eb_indiv_valid_counts: no genotype store uploaded"); return EB_ERR_STATE; }
+  EB_CUDA(cudaSetDevice(c->device));
+  DevBuf<int> out;
+  int rc;
+  if ((rc = out.ensure(c->numindivs))) return rc;
+  if (snp_keep) EB_CUDA(cudaMemcpyAsync(c->ignore_d.p, snp_keep, (size_t)c->nsnp, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = launch_indiv_counts(c, snp_keep ? c->ignore_d.p : nullptr, out.p))) return rc;
+  EB_CUDA(cudaMemcpyAsync(nvalid, out.p, sizeof(int) * c->numindivs, cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int eb_grm_partial(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* nmiss, uint8_t* used, double* xmean, double* xfancy,
+                   int64_t* nused_out) {
+  int rc;
+  if ((rc = need_rows(c, "eb_grm"))) return rc;
+  if (!opts) { set_error("eb_grm: opts is NULL"); return EB_ERR_ARG; }
+  if (c->nrows < 2) { set_error("eb_grm: need at least 2 rows"); return EB_ERR_ARG; }
+  if ((rc = stage_opts(c, opts))) return rc;
+  EB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  if ((rc = launch_stats(c, opts))) return rc;
+  EB_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  if ((rc = grm_accumulate(c))) return rc;
+  if ((rc = fetch_snp_outputs(c, c0, c1, nmiss, used, xmean, xfancy, nused_out))) return rc;
+  cudaEventElapsedTime(&c->tm.stats_ms, c->ev[0], c->ev[1]);
+  cudaEventElapsedTime(&c->tm.grm_ms, c->ev[2], c->ev[3]);
+  cudaEventElapsedTime(&c->tm.finalize_ms, c->ev[3], c->ev[4]);
+  c->grm_valid = true;
+  return 0;
+}
+
+void* eb_grm_device_ptr(eb_ctx* c, int64_t* ld, int64_t* n) {
+  if (!c || !c->xtx.p) return nullptr;
+  if (ld) *ld = c->npad;
+  if (n) *n = c->nrows;
+  return c->xtx.p;
+}
+
+__global__ void scale_copy_kernel(const double* __restrict__ src, int64_t lds, double* __restrict__ dst, int n, double s) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+  if (col < n) dst[(size_t)row * n + col] = src[(size_t)row * lds + col] * s;
+}
+
+int eb_grm_finish(eb_ctx* c, double* y_out, double* XTX_host) {
+  if (!c || !c->grm_valid) { set_error("eb_grm_finish: no GRM resident"); return EB_ERR_STATE; }
+  EB_CUDA(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = grm_trace(c))) return rc;
+  if (std::isnan(c->y)) { set_error("bad XTX matrix"); return EB_ERR_NUMERIC; }                 // smartpca.c:1231
+  if (c->y <= 0.0) { set_error("XTX has zero trace (perhaps no data)"); return EB_ERR_NUMERIC; }  // smartpca.c:1234
+  if (y_out) *y_out = c->y;
+  if (XTX_host) {
+    // XTX / y, computed as XTX * (1/y) like vst(XTX, XTX, 1.0/y, ...) at smartpca.c:1236
+    DevBuf<double> tmp;
+    const int n = c->nrows;
+    if ((rc = tmp.ensure((size_t)n * n))) return rc;
+    dim3 grid((n + 255) / 256, n);
+    scale_copy_kernel<<<grid, 256, 0, c->stream>>>(c->xtx.p, c->npad, tmp.p, n, 1.0 / c->y);
+    EB_CHECK_LAUNCH(c);
+    EB_CUDA(cudaMemcpyAsync(XTX_host, tmp.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, c->stream));
+    EB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+int eb_grm(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* nmiss, uint8_t* used, double* xmean, double* xfancy,
+           double* y_out, int64_t* nused_out, double* XTX_host) {
+  int rc;
+  if ((rc = eb_grm_partial(c, opts, c0, c1, nmiss, used, xmean, xfancy, nused_out))) return rc;
+  return eb_grm_finish(c, y_out, XTX_host);
+}
+
+int eb_eig(eb_ctx* c, int nvec, double* lambda, double* evecs) {
+  if (!c || !c->grm_valid || c->y <= 0.0) { set_error("eb_eig: no normalised GRM resident (call eb_grm first)"); return EB_ERR_STATE; }
+  EB_CUDA(cudaSetDevice(c->device));
+  return eig_resident(c, c->xtx.p, c->npad, c->nrows, 1.0 / c->y, nvec, lambda, evecs);
+}
+
+int eb_eigvecs(eb_ctx* c, const double* mat, double* evals, double* evecs, int n, int nvec) {
+  if (!c || !mat || n <= 0) { set_error("eb_eigvecs: bad argument"); return EB_ERR_ARG; }
+  EB_CUDA(cudaSetDevice(c->device));
+  DevBuf<double> A;
+  int rc;
+  if ((rc = A.ensure((size_t)n * n))) return rc;
+  EB_CUDA(cudaMemcpyAsync(A.p, mat, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, c->stream));
+  return eig_resident(c, A.p, n, n, 1.0, nvec, evals, evecs);
+}
+
+// ridoutlier, smartsubs.c:18-93: same operation order as the reference so that |z| > thresh decisions agree bit for bit
+int eb_ridoutlier(const double* evecs, int n, int neigs, double thresh, int outliermode, int* badlist, int* vecno, double* score) {
+  if (outliermode > 1 || n < 3) return 0;
+  std::vector<double> ww(n), w2(n);
+  std::vector<int> vbad(n, 0);
+  for (int j = 0; j < n; j++) vecno[j] = -1;
+  for (int i = 0; i < neigs; i++) {
+    for (int j = 0; j < n; j++) ww[j] = evecs[(size_t)i * n + j];
+    if (outliermode == 0) {
+      double y1 = 0.0, y2 = 0.0;
+      for (int j = 0; j < n; j++) y1 += ww[j];
+      y1 /= (double)n;
+      for (int j = 0; j < n; j++) ww[j] = ww[j] + (-y1);
+      for (int j = 0; j < n; j++) y2 += ww[j] * ww[j];
+      y2 = y2 / (double)n;
+      y2 = sqrt(y2);
+      const double r = 1.0 / y2;
+      for (int j = 0; j < n; j++) ww[j] = ww[j] * r;
+      for (int j = 0; j < n; j++)
+        if (fabs(ww[j]) > thresh) { vbad[j] = 1; if (vecno[j] < 0) { vecno[j] = i; score[j] = ww[j]; } }
+    } else {
+      for (int j = 0; j < n; j++) {
+        const double yy = ww[j];
+        ww[j] = 0;
+        double y1 = 0.0, y2 = 0.0;
+        for (int k = 0; k < n; k++) y1 += ww[k];
+        y1 /= (double)(n - 1);
+        for (int k = 0; k < n; k++) w2[k] = ww[k] + (-y1);
+        w2[j] = 0;
+        for (int k = 0; k < n; k++) y2 += w2[k] * w2[k];
+        y2 = sqrt(y2 / (double)n);
+        double zz = yy - y1;
+        zz /= y2;
+        if (fabs(zz) > thresh) { vbad[j] = 1; if (vecno[j] < 0) { vecno[j] = i; score[j] = zz; } }
+        ww[j] = yy;
+      }
+    }
+  }
+  int nbad = 0;
+  for (int j = 0; j < n; j++) if (vbad[j]) badlist[nbad++] = j;
+  return nbad;
+}
+
+int eb_pca_full(eb_ctx* c, const eb_pca_opts* o, int* xindex_io, int nrows, double* lambda, double* evecs, uint8_t* snp_used,
+                double* xmean, double* xfancy, int* removed_index, int* removed_iter, int* removed_vecno, double* removed_score,
+                eb_pca_result* res) {
+  if (!c || !o || !xindex_io || !lambda || !res) { set_error("eb_pca_full: null argument"); return EB_ERR_ARG; }
+  const double t_start = now_s();
+  memset(res, 0, sizeof(*res));
+  int rc;
+  std::vector<uint8_t> ignore(c->nsnp, 0), used(c->nsnp);
+  if (o->grm.snp_ignore) memcpy(ignore.data(), o->grm.snp_ignore, c->nsnp);
+  std::vector<int> xi(xindex_io, xindex_io + nrows);
+  std::vector<int> bad(nrows), vecno(nrows);
+  std::vector<double> score(nrows);
+  const int numoutiter = o->numoutliter >= 1 ? o->numoutliter + 1 : 1;      // smartpca.c:1028-1040
+  const int outmode = o->numoutliter >= 1 ? o->outliermode : 2;
+  int nremoved = 0;
+  for (int iter = 1; iter <= numoutiter; iter++) {
+    if ((rc = eb_set_rows(c, xi.data(), (int)xi.size()))) return rc;
+    eb_grm_opts g = o->grm;
+    g.snp_ignore = ignore.data();
+    double y = 0; int64_t nused = 0;
+    double t0 = now_s();
+    if ((rc = eb_grm(c, &g, nullptr, nullptr, nullptr, used.data(), xmean, xfancy, &y, &nused, nullptr))) return rc;
+    res->secs_grm += now_s() - t0;
+    // SNPs dropped in a pass stay ignored in later passes (cupt->ignore = YES, smartpca.c:1136; loadsnpx 1085)
+    for (int64_t s = 0; s < c->nsnp; s++) if (!used[s]) ignore[s] = 1;
+    const int n = (int)xi.size();
+    const int nv = std::max(std::min(o->numeigs, n), std::min(std::min(o->numoutleigs, n - 1), n));
+    std::vector<double> ev((size_t)std::max(nv, 1) * n);
+    t0 = now_s();
+    if ((rc = eb_eig(c, nv, lambda, ev.data()))) return rc;
+    res->secs_eig += now_s() - t0;
+    res->niter = iter; res->y = y; res->nused = nused; res->nrows_final = n;
+    const int keep = std::min(o->numeigs, n);
+    if (evecs) memcpy(evecs, ev.data(), sizeof(double) * (size_t)keep * n);
+    if (snp_used) memcpy(snp_used, used.data(), c->nsnp);
+    if (iter > o->numoutliter) break;                                      // last pass skips outliers, smartpca.c:1246
+    const int neigs = std::min(o->numoutleigs, n - 1);                     // smartpca.c:1249
+    const int nbad = eb_ridoutlier(ev.data(), n, neigs, o->outlthresh, outmode, bad.data(), vecno.data(), score.data());
+    if (nbad == 0) break;
+    std::vector<char> kill(n, 0);
+    for (int b = 0; b < nbad; b++) {
+      const int j = bad[b];
+      kill[j] = 1;
+      if (removed_index) removed_index[nremoved] = xi[j];
+      if (removed_iter) removed_iter[nremoved] = iter;
+      if (removed_vecno) removed_vecno[nremoved] = vecno[j];
+      if (removed_score) removed_score[nremoved] = score[j];
+      nremoved++;
+    }
+    std::vector<int> nxt;
+    for (int j = 0; j < n; j++) if (!kill[j]) nxt.push_back(xi[j]);
+    xi.swap(nxt);
+  }
+  res->nremoved = nremoved;
+  for (size_t i = 0; i < xi.size(); i++) xindex_io[i] = xi[i];
+  res->secs_total = now_s() - t_start;
+  return 0;
+}
+
+int eb_fpca(eb_ctx* c, int fancynorm, int altnormstyle, size_t K, size_t L, size_t I, long seed, double* eval, double* evec) {
+  int rc;
+  if ((rc = need_rows(c, "eb_fpca"))) return rc;
+  if (K >= L || I == 0) { set_error("eb_fpca: need K < L and I > 0 (kjg_fpca.c:26-29)"); return EB_ERR_ARG; }
+  return fpca_run(c, fancynorm, altnormstyle, K, L, I, seed, eval, evec);
+}
+
+int eb_project(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, double* fxvecs, double* fxscal) {
+  int rc;
+  if ((rc = need_rows(c, "eb_project"))) return rc;
+  if (!c->grm_valid) { set_error("eb_project: run eb_grm first (needs the per-SNP normalisation)"); return EB_ERR_STATE; }
+  return project_run(c, evecs, numeigs, ffvecs, fxvecs, fxscal);
+}
+
+int eb_get_timings(eb_ctx* c, eb_timings* t) {
+  if (!c || !t) return EB_ERR_ARG;
+  *t = c->tm; t->nsplit = c->nsplit;
+  return 0;
+}
+
+int eb_microbench_fp64(eb_ctx* c, double* dmma, double* dfma) {
+  if (!c) return EB_ERR_ARG;
+  EB_CUDA(cudaSetDevice(c->device));
+  double a = 0, b = 0;
+  int rc = microbench_fp64(c, &a, &b);
+  if (dmma) *dmma = a;
+  if (dfma) *dfma = b;
+  return rc;
+}
+
+}  // extern "C"

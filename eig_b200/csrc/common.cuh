@@ -1,0 +1,123 @@
+// common.cuh -- shared declarations for libeigb200.so (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/eigb200.h"
+
+namespace eb {
+
+void set_error(const char* fmt, ...);
+
+#define EB_CUDA(call)                                                                        \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      eb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));   \
+      return EB_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+#define EB_CHECK_LAUNCH(ctx)                                                                 \
+  do {                                                                                       \
+    (ctx)->launches++;                                                                       \
+    cudaError_t e_ = cudaGetLastError();                                                     \
+    if (e_ != cudaSuccess) {                                                                 \
+      eb::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      return EB_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int ensure(size_t count) {
+    if (count <= n && p) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+    if (count == 0) return 0;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); return EB_ERR_NOMEM; }
+    n = count;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DevBuf() { release(); }
+};
+
+constexpr int TILE = 128;       // GRM tile edge in individuals (32 packed bytes)
+constexpr int KT = 128;         // SNPs per pipeline stage of the GRM kernel
+constexpr int SNP_PAD = KT;     // working matrix SNP count is padded to this (pad rows are all-missing)
+
+}  // namespace eb
+
+struct eb_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+
+  // raw slab as uploaded (reference layout, pitch = rlen or caller pitch)
+  eb::DevBuf<uint8_t> raw_own;
+  const uint8_t* raw = nullptr;
+  int64_t nsnp = 0, raw_pitch = 0;
+  int numindivs = 0;
+
+  // working matrix: selected rows only, SNP-major, pitch = npad/4 bytes, pad genotypes = 3
+  eb::DevBuf<uint8_t> work;
+  eb::DevBuf<int> xindex_d;
+  std::vector<int> xindex_h;
+  int nrows = 0;        // selected individuals
+  int npad = 0;         // nrows rounded up to TILE
+  int64_t mpad = 0;     // nsnp rounded up to SNP_PAD
+  int64_t wpitch = 0;   // bytes per SNP row of the working matrix
+  bool rows_set = false;
+
+  // per-SNP device arrays (length mpad)
+  eb::DevBuf<int> c0_d, c1_d, nmiss_d;
+  eb::DevBuf<uint8_t> used_d, ignore_d;
+  eb::DevBuf<double> xmean_d, xfancy_d, weight_d;
+  eb::DevBuf<double> table_d;     // [mpad][4]: cc0,cc1,cc2,0 (zero rows for unused SNPs)
+  eb::DevBuf<long long> nused_d;  // 1
+
+  // GRM
+  eb::DevBuf<double> partial;     // nsplit * npad * npad
+  eb::DevBuf<double> xtx;         // npad * npad, full symmetric, UNNORMALISED
+  eb::DevBuf<double> trace_d;     // 1
+  eb::DevBuf<int> workctr_d;      // 1
+  int nsplit = 1;
+  bool grm_valid = false;
+  double y = 0.0;                 // trace/(nrows-1)
+  int64_t nused = 0;
+
+  // eigensolver workspace
+  eb::DevBuf<double> eigA;        // npad*npad working copy (reflectors end up in its lower part)
+  eb::DevBuf<double> eigw;        // misc vectors
+  eb::DevBuf<double> eigV, eigW;  // panels
+  eb::DevBuf<double> lambda_d, zvec_d;
+
+  eb_timings tm = {};
+  cudaEvent_t ev[8] = {};
+};
+
+namespace eb {
+// pack_kernels.cu
+int launch_gather(eb_ctx* c);
+int launch_stats(eb_ctx* c, const eb_grm_opts* o);
+int launch_indiv_counts(eb_ctx* c, const uint8_t* keep_d, int* out_d);
+int launch_synth(eb_ctx* c, uint8_t* dst, int64_t nsnp, int64_t pitch, int numindivs, uint64_t seed, int64_t s0,
+                 double missing, int npops, double delta);
+// grm_kernel.cu
+int grm_accumulate(eb_ctx* c);   // work+table -> xtx (full symmetric, unnormalised), trace
+int grm_trace(eb_ctx* c);        // recompute trace_d / y from xtx
+int microbench_fp64(eb_ctx* c, double* dmma, double* dfma);
+// eig_kernels.cu
+int eig_resident(eb_ctx* c, const double* A_d, int64_t lda, int n, double scale, int nvec, double* lambda_h, double* evecs_h);
+// fpca_kernels.cu
+int fpca_run(eb_ctx* c, int fancynorm, int altnormstyle, size_t K, size_t L, size_t I, long seed, double* eval, double* evec);
+int project_run(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, double* fxvecs, double* fxscal);
+}  // namespace eb

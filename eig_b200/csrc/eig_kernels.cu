@@ -1,0 +1,501 @@
+// eig_kernels.cu -- symmetric eigensolver on a device-resident FP64 matrix.
+//
+// Replaces eigvecs() -> packsym -> eigxv_ -> LAPACK dspev_ (eigsubs.c:39-55,145-155; eigx.c:97-117):
+// all eigenvalues (descending) + the leading nvec eigenvectors, which is everything smartpca.c consumes
+// (lambda[] for .eval / Tracy-Widom, smartpca.c:1312-1431; evecs rows 0..numeigs-1, smartpca.c:1250,1444).
+//
+//   1. blocked Householder tridiagonalisation (dlatrd/dsytrd scheme, panel width NB): per column one
+//      HBM-bound GEMV over the trailing matrix + skinny corrections; per panel one FP64 tensor-core (DMMA)
+//      rank-2NB update of the full symmetric trailing block.  Reflector j is kept in row j of the matrix.
+//   2. all eigenvalues of the tridiagonal by Sturm-count bisection, one thread per eigenvalue.
+//   3. leading eigenvectors of the tridiagonal by inverse iteration with cluster re-orthogonalisation
+//      (dstein scheme), then back-transformation through the stored reflectors.
+#include <algorithm>
+#include <cmath>
+#include "common.cuh"
+
+namespace eb {
+
+constexpr int NB = 32;            // panel width
+constexpr int KA_THREADS = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double block_sum(double v, double* sh) {   // fixed-order => deterministic
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < nw; i++) r += sh[i];
+  return r;
+}
+
+struct Refl { double beta, tau, scal; };
+// dlarfg from alpha = x[0] and xnorm2 = sum x[1:]^2
+__device__ __forceinline__ Refl make_reflector(double alpha, double xnorm2) {
+  Refl r;
+  if (xnorm2 == 0.0) { r.beta = alpha; r.tau = 0.0; r.scal = 0.0; return r; }
+  const double nrm = sqrt(alpha * alpha + xnorm2);
+  r.beta = alpha >= 0.0 ? -nrm : nrm;
+  r.tau = (r.beta - alpha) / r.beta;
+  r.scal = 1.0 / (alpha - r.beta);
+  return r;
+}
+
+// KA: apply the panel's pending rank-2k update to row j (columns j..n-1), record d[j], and emit per-block
+// partial sums of squares of the part that will be annihilated (columns j+2..n-1).
+__global__ void __launch_bounds__(KA_THREADS) tri_row_update_kernel(double* __restrict__ A, int64_t lda, int n, int j, int k,
+                                                                    const double* __restrict__ Vp, const double* __restrict__ Wp,
+                                                                    double* __restrict__ d, double* __restrict__ partA,
+                                                                    double* __restrict__ alpha_slot) {
+  __shared__ double vj[NB], wj[NB], red[KA_THREADS / 32];
+  if ((int)threadIdx.x < k) { vj[threadIdx.x] = Vp[(size_t)threadIdx.x * n + j]; wj[threadIdx.x] = Wp[(size_t)threadIdx.x * n + j]; }
+  __syncthreads();
+  const int c = j + blockIdx.x * blockDim.x + threadIdx.x;
+  double sq = 0.0;
+  if (c < n) {
+    double a = A[(size_t)j * lda + c];
+    for (int m = 0; m < k; m++) a -= vj[m] * Wp[(size_t)m * n + c] + wj[m] * Vp[(size_t)m * n + c];
+    A[(size_t)j * lda + c] = a;
+    if (c == j) d[j] = a;
+    if (c == j + 1) alpha_slot[0] = a;   // row j is overwritten with v later; keep alpha = x[0]
+    if (c >= j + 2) sq = a * a;
+  }
+  const double s = block_sum(sq, red);
+  if (threadIdx.x == 0) partA[blockIdx.x] = s;
+}
+
+// KB: p_raw = A[j+1:, j+1:] * v  (one warp per row) with v formed on the fly from row j; extra blocks compute the
+// correction dots s1[m] = Wp[m].v, s2[m] = Vp[m].v (one warp per dot).
+__global__ void __launch_bounds__(256) tri_gemv_kernel(const double* __restrict__ A, int64_t lda, int n, int j, int k,
+                                                       const double* __restrict__ Vp, const double* __restrict__ Wp,
+                                                       const double* __restrict__ partA, int npartA, const double* __restrict__ alpha_slot,
+                                                       double* __restrict__ praw, double* __restrict__ s12, double* __restrict__ e, double* __restrict__ tau,
+                                                       int gemv_blocks) {
+  __shared__ Refl rf;
+  if (threadIdx.x == 0) {
+    double x2 = 0.0;
+    for (int i = 0; i < npartA; i++) x2 += partA[i];
+    rf = make_reflector(alpha_slot[0], x2);
+    if (blockIdx.x == 0) { e[j] = rf.beta; tau[j] = rf.tau; }
+  }
+  __syncthreads();
+  const double scal = rf.scal;
+  const double* x = A + (size_t)j * lda;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = j + 1;
+  if ((int)blockIdx.x < gemv_blocks) {
+    const int row = c0 + blockIdx.x * 8 + warp;
+    if (row >= n) return;
+    const double* ar = A + (size_t)row * lda;
+    double acc = 0.0;
+    for (int c = c0 + lane; c < n; c += 32) {
+      const double v = (c == c0) ? 1.0 : x[c] * scal;
+      acc += ar[c] * v;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) praw[row] = acc;
+  } else {
+    const int id = (blockIdx.x - gemv_blocks) * 8 + warp;     // 0..2k-1
+    if (id >= 2 * k) return;
+    const double* src = (id < k) ? Wp + (size_t)id * n : Vp + (size_t)(id - k) * n;
+    double acc = 0.0;
+    for (int c = c0 + lane; c < n; c += 32) {
+      const double v = (c == c0) ? 1.0 : x[c] * scal;
+      acc += src[c] * v;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s12[id] = acc;
+  }
+}
+
+// KC: p = tau * (p_raw - V s1 - W s2); store v (panel row k and row j of A); per-block partial of p.v
+__global__ void __launch_bounds__(KA_THREADS) tri_correct_kernel(double* __restrict__ A, int64_t lda, int n, int j, int k,
+                                                                 double* __restrict__ Vp, const double* __restrict__ Wp,
+                                                                 const double* __restrict__ partA, int npartA,
+                                                                 const double* __restrict__ alpha_slot,
+                                                                 const double* __restrict__ praw, const double* __restrict__ s12,
+                                                                 double* __restrict__ p, double* __restrict__ partC) {
+  __shared__ double s1[NB], s2[NB], red[KA_THREADS / 32];
+  __shared__ Refl rf;
+  if (threadIdx.x == 0) {
+    double x2 = 0.0;
+    for (int i = 0; i < npartA; i++) x2 += partA[i];
+    rf = make_reflector(alpha_slot[0], x2);
+  }
+  if ((int)threadIdx.x < k) { s1[threadIdx.x] = s12[threadIdx.x]; s2[threadIdx.x] = s12[k + threadIdx.x]; }
+  __syncthreads();
+  const int c = j + 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  double dot = 0.0;
+  if (c < n) {
+    const double v = (c == j + 1) ? 1.0 : A[(size_t)j * lda + c] * rf.scal;
+    double acc = praw[c];
+    for (int m = 0; m < k; m++) acc -= Vp[(size_t)m * n + c] * s1[m] + Wp[(size_t)m * n + c] * s2[m];
+    acc *= rf.tau;
+    p[c] = acc;
+    Vp[(size_t)k * n + c] = v;
+    A[(size_t)j * lda + c] = v;
+    dot = acc * v;
+  }
+  __syncthreads();   // all reads of row j happen before rf is reused; (A row j writes are per-thread own element)
+  const double s = block_sum(dot, red);
+  if (threadIdx.x == 0) partC[blockIdx.x] = s;
+}
+
+// KD: w = p - (tau/2)(p.v) v  -> panel row k
+__global__ void __launch_bounds__(KA_THREADS) tri_w_kernel(int n, int j, int k, const double* __restrict__ Vp, double* __restrict__ Wp,
+                                                           const double* __restrict__ p, const double* __restrict__ partC, int npartC,
+                                                           const double* __restrict__ tau) {
+  __shared__ double al;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < npartC; i++) s += partC[i];
+    al = -0.5 * tau[j] * s;
+  }
+  __syncthreads();
+  const int c = j + 1 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) Wp[(size_t)k * n + c] = p[c] + al * Vp[(size_t)k * n + c];
+}
+
+// Trailing update  A[j1:, j1:] -= sum_m V[m][i] W[m][c] + W[m][i] V[m][c]   (full symmetric block, DMMA).
+// CTA tile 128x128, 8 warps (64x32 each); K = 2*kp staged in shared memory in chunks of 16.
+__device__ __forceinline__ void dmma884e(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+constexpr int TU_K = 16, TU_LD = 136;
+__global__ void __launch_bounds__(256, 1) tri_trailing_kernel(double* __restrict__ A, int64_t lda, int n, int j1, int kp,
+                                                              const double* __restrict__ Vp, const double* __restrict__ Wp) {
+  __shared__ double Ps[TU_K][TU_LD], Qs[TU_K][TU_LD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wm = warp >> 2, wn = warp & 3, g = lane >> 2, q = lane & 3;
+  const int i0 = j1 + blockIdx.y * 128, c0 = j1 + blockIdx.x * 128;
+  double acc[8][4][2];
+#pragma unroll
+  for (int t = 0; t < 8; t++)
+#pragma unroll
+    for (int u = 0; u < 4; u++) acc[t][u][0] = acc[t][u][1] = 0.0;
+  const int K = 2 * kp;
+  for (int k0 = 0; k0 < K; k0 += TU_K) {
+    __syncthreads();
+    // P[kk][i] = (kk<kp ? V : W)[kk][i0+i] ; Q[kk][c] = (kk<kp ? W : V)[kk][c0+c]
+    for (int idx = threadIdx.x; idx < TU_K * 128; idx += 256) {
+      const int kk = idx >> 7, ii = idx & 127, kg = k0 + kk;
+      double pv = 0.0, qv = 0.0;
+      if (kg < K) {
+        const bool first = kg < kp;
+        const int m = first ? kg : kg - kp;
+        const double* Pm = (first ? Vp : Wp) + (size_t)m * n;
+        const double* Qm = (first ? Wp : Vp) + (size_t)m * n;
+        if (i0 + ii < n) pv = Pm[i0 + ii];
+        if (c0 + ii < n) qv = Qm[c0 + ii];
+      }
+      Ps[kk][ii] = pv; Qs[kk][ii] = qv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TU_K; kk += 4) {
+      double a[8], b[4];
+#pragma unroll
+      for (int t = 0; t < 8; t++) a[t] = Ps[kk + q][wm * 64 + t * 8 + g];
+#pragma unroll
+      for (int u = 0; u < 4; u++) b[u] = Qs[kk + q][wn * 32 + u * 8 + g];
+#pragma unroll
+      for (int t = 0; t < 8; t++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) dmma884e(acc[t][u][0], acc[t][u][1], a[t], b[u]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    const int row = i0 + wm * 64 + t * 8 + g;
+    if (row >= n) continue;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int col = c0 + wn * 32 + u * 8 + q * 2;
+      double* ptr = A + (size_t)row * lda + col;
+      if (col < n) ptr[0] -= acc[t][u][0];
+      if (col + 1 < n) ptr[1] -= acc[t][u][1];
+    }
+  }
+}
+
+// last 2x2 block -> d[n-2], e[n-2], d[n-1]; also applies the eigenvalue scale to d and e
+__global__ void tri_tail_scale_kernel(const double* __restrict__ A, int64_t lda, int n, double* __restrict__ d, double* __restrict__ e,
+                                      double scale) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (n >= 2) { d[n - 2] = A[(size_t)(n - 2) * lda + n - 2]; e[n - 2] = A[(size_t)(n - 2) * lda + n - 1]; }
+    d[n - 1] = A[(size_t)(n - 1) * lda + n - 1];
+    e[n - 1] = 0.0;
+  }
+}
+__global__ void scale_de_kernel(int n, double* __restrict__ d, double* __restrict__ e, double scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { d[i] *= scale; e[i] *= scale; }
+}
+
+// ------------------------------------------------------------------------------------------ bisection
+// Gershgorin bounds + norm of T (single block)
+__global__ void __launch_bounds__(1024) tri_bounds_kernel(int n, const double* __restrict__ d, const double* __restrict__ e,
+                                                          double* __restrict__ bounds) {
+  __shared__ double smin[32], smax[32];
+  double lo = 1e300, hi = -1e300;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < n - 1 ? fabs(e[i]) : 0.0);
+    lo = fmin(lo, d[i] - r); hi = fmax(hi, d[i] + r);
+  }
+  for (int o = 16; o > 0; o >>= 1) { lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) { lo = fmin(lo, smin[i]); hi = fmax(hi, smax[i]); }
+    const double tn = fmax(fabs(lo), fabs(hi));
+    bounds[0] = lo - 2.0 * tn * 2.3e-16 * n - 1e-300;
+    bounds[1] = hi + 2.0 * tn * 2.3e-16 * n + 1e-300;
+    bounds[2] = tn;
+  }
+}
+
+__device__ __forceinline__ int sturm_count(int n, const double* __restrict__ d, const double* __restrict__ e2, double x, double pivmin) {
+  double qv = d[0] - x;
+  if (fabs(qv) < pivmin) qv = -pivmin;
+  int cnt = qv < 0.0;
+  for (int i = 1; i < n; i++) {
+    qv = d[i] - x - e2[i - 1] / qv;
+    if (fabs(qv) < pivmin) qv = -pivmin;
+    cnt += qv < 0.0;
+  }
+  return cnt;
+}
+
+__global__ void __launch_bounds__(128) e2_kernel(int n, const double* __restrict__ e, double* __restrict__ e2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) e2[i] = e[i] * e[i];
+}
+
+// thread k finds the k-th smallest eigenvalue; output descending: lam[n-1-k]
+__global__ void __launch_bounds__(128) tri_bisect_kernel(int n, const double* __restrict__ d, const double* __restrict__ e2,
+                                                         const double* __restrict__ bounds, double* __restrict__ lam) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double lo = bounds[0], hi = bounds[1];
+  const double tn = bounds[2];
+  const double pivmin = fmax(2.3e-308 * fmax(1.0, tn * tn), 1e-300);
+  const double atol = 2.0 * 2.220446049250313e-16 * tn * 0.25 + 2.0 * pivmin;
+  for (int it = 0; it < 200; it++) {
+    const double mid = 0.5 * (lo + hi);
+    if (hi - lo <= atol + 2.220446049250313e-16 * fmax(fabs(lo), fabs(hi)) || mid <= lo || mid >= hi) break;
+    if (sturm_count(n, d, e2, mid, pivmin) > k) hi = mid; else lo = mid;
+  }
+  lam[n - 1 - k] = 0.5 * (lo + hi);
+}
+
+// ------------------------------------------------------------------------------------------ inverse iteration
+// Single block. For each of the nvec leading eigenvalues: solve (T - lam I) z = b with partial-pivoting LU
+// (thread 0, sequential), re-orthogonalise against earlier vectors of the same cluster, normalise; repeat.
+// work: 5*n doubles + n ints ; Z: [nvec][n]
+__global__ void __launch_bounds__(1024) tri_invit_kernel(int n, int nvec, const double* __restrict__ d, const double* __restrict__ e,
+                                                         const double* __restrict__ lam, const double* __restrict__ bounds,
+                                                         double* __restrict__ work, int* __restrict__ ipiv, double* __restrict__ Z) {
+  __shared__ double red[32];
+  double* dl = work;            // sub-diagonal multipliers
+  double* dd = work + n;        // U diagonal
+  double* du = work + 2 * n;    // U first super-diagonal
+  double* du2 = work + 3 * n;   // U second super-diagonal
+  double* b = work + 4 * n;
+  const double tn = bounds[2];
+  const double eps = 2.220446049250313e-16;
+  const double ortol = 1e-3 * tn;
+  int cluster_start = 0;
+  double prev_shift = 0.0;
+  for (int v = 0; v < nvec; v++) {
+    double shift = lam[v];
+    if (v > 0) {
+      if (fabs(lam[v - 1] - lam[v]) > ortol) cluster_start = v;
+      // keep shifts of near-coincident eigenvalues separated (dstein's perturbation)
+      const double sep = 10.0 * eps * fabs(shift) + 10.0 * eps * tn * 1e-3;
+      if (prev_shift - shift < sep) shift = prev_shift - sep;
+    }
+    prev_shift = shift;
+    double* z = Z + (size_t)v * n;
+    // deterministic pseudo-random start
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      uint32_t hsh = (uint32_t)(i * 2654435761u) ^ (uint32_t)((v + 1) * 40503u);
+      hsh ^= hsh >> 15; hsh *= 2246822519u; hsh ^= hsh >> 13;
+      b[i] = 0.5 + (double)(hsh & 0xFFFF) / 65536.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // LU of tridiagonal (T - shift I) with partial pivoting (dgttrf scheme)
+      for (int i = 0; i < n; i++) { dd[i] = d[i] - shift; if (i < n - 1) { dl[i] = e[i]; du[i] = e[i]; } du2[i] = 0.0; }
+      const double piv0 = eps * tn;
+      for (int i = 0; i < n - 1; i++) {
+        if (fabs(dd[i]) >= fabs(dl[i])) {
+          if (fabs(dd[i]) < piv0) dd[i] = piv0;
+          const double f = dl[i] / dd[i];
+          dl[i] = f; dd[i + 1] -= f * du[i]; ipiv[i] = 0;
+        } else {
+          const double f = dd[i] / dl[i];
+          dd[i] = dl[i]; dl[i] = f;
+          const double t = du[i];
+          du[i] = dd[i + 1]; dd[i + 1] = t - f * du[i];
+          if (i < n - 2) { du2[i] = du[i + 1]; du[i + 1] = -f * du[i + 1]; }
+          ipiv[i] = 1;
+        }
+      }
+      if (fabs(dd[n - 1]) < piv0) dd[n - 1] = piv0;
+    }
+    __syncthreads();
+    for (int iter = 0; iter < 4; iter++) {
+      if (threadIdx.x == 0) {
+        // forward: L y = P b
+        for (int i = 0; i < n - 1; i++) {
+          if (ipiv[i]) { const double t = b[i]; b[i] = b[i + 1]; b[i + 1] = t - dl[i] * b[i]; }
+          else b[i + 1] -= dl[i] * b[i];
+        }
+        // backward: U x = y
+        b[n - 1] /= dd[n - 1];
+        if (n > 1) b[n - 2] = (b[n - 2] - du[n - 2] * b[n - 1]) / dd[n - 2];
+        for (int i = n - 3; i >= 0; i--) b[i] = (b[i] - du[i] * b[i + 1] - du2[i] * b[i + 2]) / dd[i];
+      }
+      __syncthreads();
+      // re-orthogonalise within the cluster (modified Gram-Schmidt)
+      for (int u = cluster_start; u < v; u++) {
+        const double* zu = Z + (size_t)u * n;
+        double s = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s += zu[i] * b[i];
+        s = block_sum(s, red);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) b[i] -= s * zu[i];
+        __syncthreads();
+      }
+      double s = 0.0;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) s += b[i] * b[i];
+      s = block_sum(s, red);
+      const double inv = 1.0 / sqrt(s);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) b[i] *= inv;
+      __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) z[i] = b[i];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ back-transformation
+// One block per eigenvector: z <- H_0 H_1 ... H_{n-3} z, reflector j stored in row j of A (columns j+1..n-1, v[j+1]=1).
+__global__ void __launch_bounds__(1024) tri_backtransform_kernel(const double* __restrict__ A, int64_t lda, int n,
+                                                                 const double* __restrict__ tau, double* __restrict__ Z) {
+  __shared__ double red[32];
+  double* z = Z + (size_t)blockIdx.x * n;
+  for (int j = n - 3; j >= 0; j--) {
+    const double tj = tau[j];
+    if (tj == 0.0) continue;
+    const double* v = A + (size_t)j * lda;
+    double s = 0.0;
+    for (int c = j + 1 + threadIdx.x; c < n; c += blockDim.x) s += v[c] * z[c];
+    s = block_sum(s, red) * tj;
+    for (int c = j + 1 + threadIdx.x; c < n; c += blockDim.x) z[c] -= s * v[c];
+    __syncthreads();
+  }
+  // normalise (unit 2-norm, as LAPACK returns)
+  double s = 0.0;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) s += z[c] * z[c];
+  s = block_sum(s, red);
+  const double inv = 1.0 / sqrt(s);
+  for (int c = threadIdx.x; c < n; c += blockDim.x) z[c] *= inv;
+}
+
+__global__ void copy_matrix_kernel(const double* __restrict__ src, int64_t lds, double* __restrict__ dst, int64_t ldd, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (c < n) dst[(size_t)r * ldd + c] = src[(size_t)r * lds + c];
+}
+
+// ------------------------------------------------------------------------------------------ host driver
+int eig_resident(eb_ctx* c, const double* A_d, int64_t lda_in, int n, double scale, int nvec, double* lambda_h, double* evecs_h) {
+  if (n <= 0) return 0;
+  nvec = std::max(0, std::min(nvec, n));
+  cudaStream_t st = c->stream;
+  int rc;
+  const int64_t lda = (n + 15) & ~15;
+  if ((rc = c->eigA.ensure((size_t)lda * n))) return rc;
+  if ((rc = c->eigV.ensure((size_t)NB * n))) return rc;
+  if ((rc = c->eigW.ensure((size_t)NB * n))) return rc;
+  // eigw layout: d[n] e[n] tau[n] e2[n] p[n] praw[n] partA[1024] partC[1024] s12[2NB] bounds[4] work[5n] | ipiv
+  const size_t wn = (size_t)n * 11 + 2048 + 2 * NB + 8;
+  if ((rc = c->eigw.ensure(wn + (size_t)n))) return rc;
+  if ((rc = c->lambda_d.ensure(n))) return rc;
+  if ((rc = c->zvec_d.ensure((size_t)std::max(nvec, 1) * n))) return rc;
+  double* A = c->eigA.p;
+  double *d = c->eigw.p, *e = d + n, *tau = e + n, *e2 = tau + n, *p = e2 + n, *praw = p + n, *partA = praw + n, *partC = partA + 1024,
+         *s12 = partC + 1024, *bounds = s12 + 2 * NB, *work = bounds + 8;
+  int* ipiv = reinterpret_cast<int*>(work + (size_t)5 * n);
+  double *Vp = c->eigV.p, *Wp = c->eigW.p;
+
+  EB_CUDA(cudaEventRecord(c->ev[5], st));
+  {
+    dim3 grid((n + 255) / 256, n);
+    copy_matrix_kernel<<<grid, 256, 0, st>>>(A_d, lda_in, A, lda, n);
+    EB_CHECK_LAUNCH(c);
+  }
+  EB_CUDA(cudaMemsetAsync(tau, 0, sizeof(double) * n, st));
+  EB_CUDA(cudaMemsetAsync(e, 0, sizeof(double) * n, st));
+
+  const int ncols = std::max(0, n - 2);   // columns that get a reflector: j = 0..n-3
+  for (int j0 = 0; j0 < ncols; j0 += NB) {
+    const int kp = std::min(NB, ncols - j0);
+    for (int k = 0; k < kp; k++) {
+      const int j = j0 + k;
+      const int len = n - j;                 // columns j..n-1
+      const int gA = (len + KA_THREADS - 1) / KA_THREADS;
+      tri_row_update_kernel<<<gA, KA_THREADS, 0, st>>>(A, lda, n, j, k, Vp, Wp, d, partA, bounds + 4);
+      EB_CHECK_LAUNCH(c);
+      const int rows = n - j - 1;
+      const int gemv_blocks = (rows + 7) / 8, dot_blocks = (2 * k + 7) / 8;
+      tri_gemv_kernel<<<gemv_blocks + dot_blocks, 256, 0, st>>>(A, lda, n, j, k, Vp, Wp, partA, gA, bounds + 4, praw, s12, e, tau, gemv_blocks);
+      EB_CHECK_LAUNCH(c);
+      const int gC = (rows + KA_THREADS - 1) / KA_THREADS;
+      tri_correct_kernel<<<gC, KA_THREADS, 0, st>>>(A, lda, n, j, k, Vp, Wp, partA, gA, bounds + 4, praw, s12, p, partC);
+      EB_CHECK_LAUNCH(c);
+      tri_w_kernel<<<gC, KA_THREADS, 0, st>>>(n, j, k, Vp, Wp, p, partC, gC, tau);
+      EB_CHECK_LAUNCH(c);
+    }
+    const int j1 = j0 + kp;
+    const int rem = n - j1;
+    if (rem > 0) {
+      dim3 grid((rem + 127) / 128, (rem + 127) / 128);
+      tri_trailing_kernel<<<grid, 256, 0, st>>>(A, lda, n, j1, kp, Vp, Wp);
+      EB_CHECK_LAUNCH(c);
+    }
+  }
+  tri_tail_scale_kernel<<<1, 32, 0, st>>>(A, lda, n, d, e, scale);
+  EB_CHECK_LAUNCH(c);
+  scale_de_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, d, e, scale);
+  EB_CHECK_LAUNCH(c);
+  EB_CUDA(cudaEventRecord(c->ev[6], st));
+
+  e2_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, e, e2);
+  EB_CHECK_LAUNCH(c);
+  tri_bounds_kernel<<<1, 1024, 0, st>>>(n, d, e, bounds);
+  EB_CHECK_LAUNCH(c);
+  tri_bisect_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, c->lambda_d.p);
+  EB_CHECK_LAUNCH(c);
+  EB_CUDA(cudaEventRecord(c->ev[7], st));
+  if (nvec > 0) {
+    tri_invit_kernel<<<1, 1024, 0, st>>>(n, nvec, d, e, c->lambda_d.p, bounds, work, ipiv, c->zvec_d.p);
+    EB_CHECK_LAUNCH(c);
+    tri_backtransform_kernel<<<nvec, 1024, 0, st>>>(A, lda, n, tau, c->zvec_d.p);
+    EB_CHECK_LAUNCH(c);
+  }
+  EB_CUDA(cudaEventRecord(c->ev[1], st));
+  if (lambda_h) EB_CUDA(cudaMemcpyAsync(lambda_h, c->lambda_d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (evecs_h && nvec > 0) EB_CUDA(cudaMemcpyAsync(evecs_h, c->zvec_d.p, sizeof(double) * (size_t)nvec * n, cudaMemcpyDeviceToHost, st));
+  EB_CUDA(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&c->tm.tridiag_ms, c->ev[5], c->ev[6]);
+  cudaEventElapsedTime(&c->tm.bisect_ms, c->ev[6], c->ev[7]);
+  cudaEventElapsedTime(&c->tm.vectors_ms, c->ev[7], c->ev[1]);
+  return 0;
+}
+
+}  // namespace eb

@@ -1,0 +1,231 @@
+// pack_kernels.cu -- HBM-bound integer/byte kernels over the 2-bit packed genotype store.
+//   gather_rows_kernel   : raw slab [nsnp][rlen] + xindex -> working matrix [mpad][npad/4] (selected rows, pad = 3)
+//                          replaces getrawcol/getgtypes gathers (qpsubs.c:240-248, admutils.c:575-592)
+//   snp_stats_kernel     : per-SNP c0,c1,nmiss (getcolxz_binary1, smartpca.c:3261-3276) fused with the
+//                          normalisation (fvadjust_binary, smartpca.c:2282-2313), the drop rule
+//                          (smartpca.c:1131-1144) and the 4-entry decode table the GRM kernel consumes
+//   indiv_counts_kernel  : numvalidgtallind (admutils.c:1075-1097)
+//   synth_kernel         : synthetic Hardy-Weinberg generator (eig_b200/synth.py is the host twin)
+#include "common.cuh"
+
+namespace eb {
+
+// ---------------------------------------------------------------------------------------------- gather
+// One thread builds one 32-bit word of the working row = 16 consecutive selected individuals.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t nsnp,
+                                                          int64_t mpad, const int* __restrict__ xindex, int nrows,
+                                                          uint8_t* __restrict__ work, int64_t wpitch) {
+  const int wordsPerRow = (int)(wpitch >> 2);
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= wordsPerRow) return;
+  int src[16];
+#pragma unroll
+  for (int t = 0; t < 16; t++) {
+    int j = w * 16 + t;
+    src[t] = j < nrows ? xindex[j] : -1;
+  }
+  for (int64_t s = blockIdx.y; s < mpad; s += gridDim.y) {
+    uint32_t out = 0xFFFFFFFFu;
+    if (s < nsnp) {
+      const uint8_t* row = raw + s * raw_pitch;
+      out = 0;
+#pragma unroll
+      for (int t = 0; t < 16; t++) {
+        uint32_t code = 3;
+        if (src[t] >= 0) code = (row[src[t] >> 2] >> ((3 - (src[t] & 3)) << 1)) & 3u;
+        // byte t>>2 of the word (little endian), individual t&3 inside the byte MSB-first
+        out |= code << (((t >> 2) << 3) + ((3 - (t & 3)) << 1));
+      }
+    }
+    reinterpret_cast<uint32_t*>(work + s * wpitch)[w] = out;
+  }
+}
+
+int launch_gather(eb_ctx* c) {
+  const int wordsPerRow = (int)(c->wpitch >> 2);
+  dim3 block(256), grid((wordsPerRow + 255) / 256, (unsigned)std::min<int64_t>(c->mpad, 65535));
+  gather_rows_kernel<<<grid, block, 0, c->stream>>>(c->raw, c->raw_pitch, c->nsnp, c->mpad, c->xindex_d.p, c->nrows,
+                                                    c->work.p, c->wpitch);
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- stats
+__device__ __forceinline__ void count_word(uint32_t x, int& n1, int& n2, int& n3) {
+  const uint32_t lo = x & 0x55555555u, hi = (x >> 1) & 0x55555555u;
+  n1 += __popc(lo & ~hi);
+  n2 += __popc(hi & ~lo);
+  n3 += __popc(hi & lo);
+}
+
+// One warp per SNP row of the working matrix; warp-shuffle reduction of the three code counts.
+__global__ void __launch_bounds__(256) snp_stats_kernel(const uint8_t* __restrict__ work, int64_t wpitch, int64_t nsnp, int64_t mpad,
+                                                        int nrows, int npad, int fancynorm, int altnormstyle, int minallelecnt,
+                                                        int maxmissing, const uint8_t* __restrict__ ignore,
+                                                        const double* __restrict__ weight, int* __restrict__ c0o,
+                                                        int* __restrict__ c1o, int* __restrict__ nmisso, uint8_t* __restrict__ usedo,
+                                                        double* __restrict__ xmeano, double* __restrict__ xfancyo,
+                                                        double* __restrict__ table, unsigned long long* __restrict__ nused) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int vecs = (int)(wpitch >> 4);
+  const int padcount = npad - nrows;
+  for (int64_t s = warp; s < mpad; s += nwarps) {
+    double t0 = 0, t1 = 0, t2 = 0;
+    if (s < nsnp) {
+      const uint4* row = reinterpret_cast<const uint4*>(work + s * wpitch);
+      int n1 = 0, n2 = 0, n3 = 0;
+      for (int v = lane; v < vecs; v += 32) {
+        const uint4 q = __ldg(row + v);
+        count_word(q.x, n1, n2, n3); count_word(q.y, n1, n2, n3);
+        count_word(q.z, n1, n2, n3); count_word(q.w, n1, n2, n3);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        n3 += __shfl_xor_sync(0xffffffffu, n3, o);
+      }
+      if (lane == 0) {
+        int nmiss = n3 - padcount;
+        int a = n1 + 2 * n2;                       // c0 = sum g
+        int b = 2 * (nrows - nmiss) - a;           // c1 = sum (2-g)
+        double xm = 0.0, xf = 0.0;
+        int tt = nmiss;
+        if (nmiss == nrows) { a = -1; b = -1; tt = -1; }
+        else {
+          // fvadjust_binary, smartpca.c:2290-2305, with explicitly rounded operations (no FMA contraction)
+          const double ynum = (double)(nrows - nmiss), ysum = (double)a;
+          const double ymean = __ddiv_rn(ysum, ynum);
+          double yfancy = 1.0;
+          if (fancynorm) {
+            double p = __dmul_rn(0.5, ymean);
+            if (!altnormstyle) p = __ddiv_rn(__dadd_rn(ysum, 1.0), __dadd_rn(__dmul_rn(2.0, ynum), 2.0));
+            const double y = __dmul_rn(p, __dadd_rn(1.0, -p));
+            if (y > 0.0) yfancy = __ddiv_rn(1.0, __dsqrt_rn(y));
+          }
+          t0 = __dmul_rn(-ymean, yfancy);
+          t1 = __dmul_rn(__dadd_rn(1.0, -ymean), yfancy);
+          t2 = __dmul_rn(__dadd_rn(2.0, -ymean), yfancy);
+          xm = __dmul_rn(ymean, yfancy); xf = yfancy;
+        }
+        const int t = a < b ? a : b;
+        bool drop = (t < minallelecnt) || (tt > maxmissing) || (tt < 0) || (t == 0);
+        if (ignore && ignore[s]) { drop = true; xm = 0.0; xf = 0.0; }
+        if (drop) { t0 = t1 = t2 = 0.0; }
+        else if (weight) { const double w = weight[s]; t0 = __dmul_rn(t0, w); t1 = __dmul_rn(t1, w); t2 = __dmul_rn(t2, w); }
+        c0o[s] = a; c1o[s] = b; nmisso[s] = tt; usedo[s] = drop ? 0 : 1;
+        xmeano[s] = xm; xfancyo[s] = xf;
+        if (!drop) atomicAdd(nused, 1ull);
+      }
+    }
+    if (lane == 0) {
+      double4 row4 = make_double4(t0, t1, t2, 0.0);
+      reinterpret_cast<double4*>(table)[s] = row4;
+    }
+  }
+}
+
+int launch_stats(eb_ctx* c, const eb_grm_opts* o) {
+  const int warpsPerBlock = 8;
+  int64_t blocks = (c->mpad + warpsPerBlock - 1) / warpsPerBlock;
+  blocks = std::min<int64_t>(blocks, (int64_t)c->num_sms * 16);
+  EB_CUDA(cudaMemsetAsync(c->nused_d.p, 0, sizeof(long long), c->stream));
+  snp_stats_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(
+      c->work.p, c->wpitch, c->nsnp, c->mpad, c->nrows, c->npad, o->fancynorm, o->altnormstyle, o->minallelecnt, o->maxmissing,
+      o->snp_ignore ? c->ignore_d.p : nullptr, o->snp_weight ? c->weight_d.p : nullptr, c->c0_d.p, c->c1_d.p, c->nmiss_d.p,
+      c->used_d.p, c->xmean_d.p, c->xfancy_d.p, c->table_d.p, reinterpret_cast<unsigned long long*>(c->nused_d.p));
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- per-individual counts
+// thread = one raw byte column (4 individuals); blockIdx.y strides over SNPs; integer atomics (order-independent).
+__global__ void __launch_bounds__(256) indiv_counts_kernel(const uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t nsnp,
+                                                           int numindivs, const uint8_t* __restrict__ keep, int* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nbytes = (numindivs + 3) >> 2;
+  if (b >= nbytes) return;
+  int n[4] = {0, 0, 0, 0};
+  for (int64_t s = blockIdx.y; s < nsnp; s += gridDim.y) {
+    if (keep && !keep[s]) continue;
+    const uint32_t x = raw[s * raw_pitch + b];
+#pragma unroll
+    for (int t = 0; t < 4; t++) n[t] += (((x >> ((3 - t) << 1)) & 3u) != 3u);
+  }
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const int j = b * 4 + t;
+    if (j < numindivs && n[t]) atomicAdd(out + j, n[t]);
+  }
+}
+
+int launch_indiv_counts(eb_ctx* c, const uint8_t* keep_d, int* out_d) {
+  const int nbytes = (c->numindivs + 3) >> 2;
+  EB_CUDA(cudaMemsetAsync(out_d, 0, sizeof(int) * c->numindivs, c->stream));
+  dim3 grid((nbytes + 255) / 256, (unsigned)std::min<int64_t>(std::max<int64_t>(c->nsnp / 64, 1), 2048));
+  indiv_counts_kernel<<<grid, 256, 0, c->stream>>>(c->raw, c->raw_pitch, c->nsnp, c->numindivs, keep_d, out_d);
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- synthetic generator
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
+
+__global__ void __launch_bounds__(256) synth_kernel(uint8_t* __restrict__ dst, int64_t nsnp, int64_t pitch, int numindivs,
+                                                    uint64_t seed, int64_t s0, uint32_t Tmiss, int use_missing, int npops,
+                                                    double delta) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= pitch) return;
+  const uint64_t C0 = 0x9E3779B97F4A7C15ull, C1 = 0xBF58476D1CE4E5B9ull, C2 = 0x94D049BB133111EBull;
+  const uint64_t CM = 0xD6E8FEB86659FD93ull, CP = 0xA0761D6478BD642Full;
+  const double sqrt12 = __dsqrt_rn(12.0);
+  for (int64_t r = blockIdx.y; r < nsnp; r += gridDim.y) {
+    const uint64_t s = (uint64_t)(s0 + r);
+    const uint64_t base = seed * C0 + s * C1;
+    const double u0 = (double)(mix64(base + 0xFFFFFFFFull * C2) >> 11) / 9007199254740992.0;
+    const double p = __dadd_rn(0.05, __dmul_rn(0.9, u0));
+    uint32_t byte = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int i = b * 4 + t;
+      uint32_t code = 3;
+      if (i < numindivs) {
+        const uint64_t key = base + (uint64_t)i * C2;
+        const uint64_t h = mix64(key);
+        double pi = p;
+        if (npops > 1) {
+          const uint64_t k = ((uint64_t)i * (uint64_t)npops) / (uint64_t)numindivs;
+          const double u = (double)(mix64((base + k * C2) ^ CP) >> 11) / 9007199254740992.0;
+          const double t1 = __dmul_rn(__dadd_rn(u, -0.5), sqrt12);
+          const double t2 = __dmul_rn(delta, t1);
+          const double t3 = __dsqrt_rn(__dmul_rn(p, __dadd_rn(1.0, -p)));
+          pi = __dadd_rn(p, __dmul_rn(t2, t3));
+          pi = fmin(fmax(pi, 0.01), 0.99);
+        }
+        const uint64_t T = (uint64_t)__dmul_rn(pi, 4294967296.0);
+        code = (uint32_t)((h & 0xFFFFFFFFull) < T) + (uint32_t)((h >> 32) < T);
+        if (use_missing && (uint32_t)(mix64(key ^ CM) & 0xFFFFFFFFull) < Tmiss) code = 3;
+      }
+      byte |= code << ((3 - t) << 1);
+    }
+    dst[r * pitch + b] = (uint8_t)byte;
+  }
+}
+
+int launch_synth(eb_ctx* c, uint8_t* dst, int64_t nsnp, int64_t pitch, int numindivs, uint64_t seed, int64_t s0,
+                 double missing, int npops, double delta) {
+  dim3 grid((unsigned)((pitch + 255) / 256), (unsigned)std::min<int64_t>(nsnp, 65535));
+  const uint32_t Tm = (uint32_t)(uint64_t)(missing * 4294967296.0);
+  synth_kernel<<<grid, 256, 0, c->stream>>>(dst, nsnp, pitch, numindivs, seed, s0, Tm, missing > 0.0 ? 1 : 0, npops, delta);
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
+}  // namespace eb

@@ -1,0 +1,152 @@
+/* eigb200.h -- C-ABI of libeigb200.so: the B200 (sm_100a) replacement for EIGENSOFT smartpca's hot path.
+ *
+ * Plain C, no C++/torch types.  All host buffers are caller-allocated and caller-freed; device state is
+ * owned by an opaque eb_ctx (one per GPU).  Every function returns 0 on success and a negative code on
+ * failure, with text in eb_last_error(); the patched smartpca.c turns non-zero into fatalx() to keep the
+ * reference's fail-hard convention (strsubs.c:213).  Functions are called from smartpca's single main
+ * thread and are not re-entrant per context.  There is no CPU fallback anywhere behind this header.
+ *
+ * Each entry point names the reference interface it replaces (file:line under DReichLab/EIG).
+ */
+#ifndef EIGB200_H
+#define EIGB200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct eb_ctx eb_ctx;
+
+#define EB_OK 0
+#define EB_ERR_CUDA (-1)
+#define EB_ERR_ARG (-2)
+#define EB_ERR_STATE (-3)
+#define EB_ERR_NOMEM (-4)
+#define EB_ERR_NUMERIC (-5)
+
+/* -------- lifetime -------- */
+const char *eb_last_error (void);
+int eb_version (void);
+/* device < 0 -> current CUDA device.  Fails (NULL) when no sm_100 GPU is visible. */
+eb_ctx *eb_create (int device);
+void eb_destroy (eb_ctx *);
+int eb_device_count (void);
+/* stream the library launches on (cudaStream_t as void*), for callers that time with CUDA events */
+void *eb_stream (eb_ctx *);
+int eb_sync (eb_ctx *);
+/* counters since eb_create / last reset: number of kernel launches this library made */
+int64_t eb_launch_count (eb_ctx *);
+void eb_reset_launch_count (eb_ctx *);
+
+/* -------- genotype store (replaces SNP.pbuff / packgenos, admutils.h:49, mcio.c:2825-2863) --------
+ * Layout is the reference's: SNP-major, `rlen` bytes per SNP, 4 genotypes per byte MSB-first,
+ * 0/1/2 = allele count, 3 = missing (admutils.c:718-735). */
+int eb_upload_packed (eb_ctx *, const uint8_t * packed /* [nsnp][rlen] contiguous */ ,
+                      int64_t nsnp, int64_t rlen, int numindivs);
+/* same, from per-SNP row pointers (snp_pbuff[i] = xsnplist[i]->pbuff, qpsubs.c:222-237) */
+int eb_upload_packed_rows (eb_ctx *, const uint8_t * const *snp_pbuff, int64_t nsnp, int64_t rlen, int numindivs);
+/* adopt a slab that already lives in device memory (caller keeps ownership; pitch in bytes) */
+int eb_adopt_packed_device (eb_ctx *, const void *dev_packed, int64_t nsnp, int64_t pitch, int numindivs);
+/* fill a device slab with synthetic Hardy-Weinberg genotypes (eig_b200/synth.py documents the generator);
+ * used by bench/tests so that 50k x 600k never has to be generated on the host.  SNPs [s0, s0+nsnp). */
+int eb_synth_packed_device (eb_ctx *, void *dev_packed, int64_t nsnp, int64_t pitch, int numindivs,
+                            uint64_t seed, int64_t s0, double missing, int npops, double delta);
+
+/* rows used = xindex[0..nrows) ascending into 0..numindivs-1 (loadindx, qpsubs.c:202-219).
+ * xindex == NULL selects all individuals.  Re-gathers the working matrix on the device. */
+int eb_set_rows (eb_ctx *, const int *xindex, int nrows);
+
+/* -------- integer reductions (bit-exact) -------- */
+/* per SNP over the current rows: c0 = sum g, c1 = sum (2-g), nmiss (getcolxz_binary1, smartpca.c:3261-3276;
+ * numvalidgtx, admutils.c:1136: nvalid = nrows - nmiss) */
+int eb_snp_counts (eb_ctx *, int *c0, int *c1, int *nmiss);
+/* per individual (all numindivs) non-missing count over SNPs with snp_keep[s] != 0 (NULL = all):
+ * numvalidgtallind, admutils.c:1075-1097 */
+int eb_indiv_valid_counts (eb_ctx *, const uint8_t * snp_keep, int *nvalid);
+
+/* -------- GRM accumulation: the region smartpca.c:1088-1236 -------- */
+typedef struct {
+  int fancynorm;                /* usenorm:      smartpca.c:2130 ; globals.h:5 default YES */
+  int altnormstyle;             /* altnormstyle: smartpca.c:2136 ; default YES */
+  int minallelecnt;             /* smartpca.c:2164 ; default 1 */
+  int maxmissing;               /* smartpca.c:2167 ; default 9999999 */
+  const uint8_t *snp_ignore;    /* [nsnp] or NULL: SNPs already flagged ignore (skipped like loadsnpx does) */
+  const double *snp_weight;     /* [nsnp] or NULL: weightname (smartpca.c:1178-1180) */
+} eb_grm_opts;
+
+/* Per-SNP outputs (any pointer may be NULL), indexed like the uploaded SNPs:
+ *   c0,c1   n0,n1 of getcolxz_binary1 (-1,-1 if all missing);  nmiss (-1 if all missing)
+ *   used    1 if the SNP entered XTX, 0 if dropped by smartpca.c:1131-1144 or ignored
+ *   xmean   ymean*yfancy, xfancy yfancy (smartpca.c:3291-3295)   -- bit-exact vs the reference
+ * y_out     trace(XTX)/(nrows-1) (smartpca.c:1230).  nused_out = number of SNPs used.
+ * XTX_host  NULL, or nrows*nrows doubles receiving XTX/y (the matrix the reference holds after line 1236).
+ * The GRM stays resident on the device for eb_eig(). */
+int eb_grm (eb_ctx *, const eb_grm_opts * opts, int *c0, int *c1, int *nmiss, uint8_t * used,
+            double *xmean, double *xfancy, double *y_out, int64_t * nused_out, double *XTX_host);
+
+/* multi-GPU (one context per SNP shard): device pointer / leading dimension of the UNNORMALISED partial
+ * XTX left by eb_grm_partial, so that the caller's NCCL reduce can run on it in place, and the call that
+ * finishes the pass (trace, y) after the reduce. */
+int eb_grm_partial (eb_ctx *, const eb_grm_opts * opts, int *c0, int *c1, int *nmiss, uint8_t * used,
+                    double *xmean, double *xfancy, int64_t * nused_out);
+void *eb_grm_device_ptr (eb_ctx *, int64_t * ld_out, int64_t * n_out);
+int eb_grm_finish (eb_ctx *, double *y_out, double *XTX_host);
+
+/* -------- symmetric eigensolver on the resident GRM: eigvecs(), eigsubs.c:39-55 / dspev_, eigx.c:107 --------
+ * lambda[nrows] descending (all eigenvalues of XTX/y); evecs[nvec*nrows], row i = unit eigenvector i. */
+int eb_eig (eb_ctx *, int nvec, double *lambda, double *evecs);
+/* standalone drop-in with the reference's contract (mat row-major n*n, preserved): include/eigsubs.h:6-7 */
+int eb_eigvecs (eb_ctx *, const double *mat, double *evals, double *evecs, int n, int nvec);
+
+/* -------- outlier detection: ridoutlier(), smartsubs.c:18-93 (decisions bit-exact) -------- */
+int eb_ridoutlier (const double *evecs, int n, int neigs, double thresh, int outliermode,
+                   int *badlist, int *vecno, double *score);
+
+/* -------- whole full-mode pass with outlier iterations: smartpca.c:1077-1265 -------- */
+typedef struct {
+  eb_grm_opts grm;
+  int numeigs;                  /* numoutevec, smartpca.c:2118 */
+  int numoutliter;              /* numoutlieriter, default 5 */
+  int numoutleigs;              /* numoutlierevec, default 10 */
+  double outlthresh;            /* outliersigmathresh, default 6.0 */
+  int outliermode;              /* default 0 */
+} eb_pca_opts;
+typedef struct {
+  int nrows_final;              /* rows left after outlier removal */
+  int niter;                    /* GRM+eig passes executed */
+  int nremoved;                 /* outliers removed in total */
+  int64_t nused;                /* SNPs used in the last pass */
+  double y;                     /* trace/(nrows-1) of the last pass */
+  double secs_grm, secs_eig, secs_total;
+} eb_pca_result;
+/* xindex_io: in = initial rows, out = surviving rows (nrows_final).  removed_*: per removal (capacity nrows):
+ * original individual index, iteration (1-based), eigenvector number, z-score.
+ * lambda[nrows_final], evecs[numeigs*nrows_final]; snp_used/xmean/xfancy as in eb_grm for the last pass. */
+int eb_pca_full (eb_ctx *, const eb_pca_opts * opts, int *xindex_io, int nrows,
+                 double *lambda, double *evecs, uint8_t * snp_used, double *xmean, double *xfancy,
+                 int *removed_index, int *removed_iter, int *removed_vecno, double *removed_score,
+                 eb_pca_result * res);
+
+/* -------- fastmode: kjg_fpca(), kjg_fpca.c:24 after setgval(), gval.c:31 --------
+ * eval[K], evec[n*K] row-major as kjg_fpca leaves it (smartpca.c:971 transposes afterwards).
+ * The seeded Gaussian start matrix reproduces kjg_gsl.c:96-186 bit for bit. */
+int eb_fpca (eb_ctx *, int fancynorm, int altnormstyle, size_t K, size_t L, size_t I, long seed,
+             double *eval, double *evec);
+void eb_gauss_matrix (long seed, size_t n, size_t L, double *out);
+
+/* -------- next rows: SNP loadings / sample projections, smartpca.c:1485-1525 -------- */
+int eb_project (eb_ctx *, const double *evecs, int numeigs, double *ffvecs /* [numeigs][nsnp] */ ,
+                double *fxvecs /* [numeigs][nrows] */ , double *fxscal /* [numeigs] */ );
+
+/* -------- measurement helpers -------- */
+/* last pass timings measured with CUDA events on the library's stream (milliseconds) */
+typedef struct { float gather_ms, stats_ms, grm_ms, finalize_ms, tridiag_ms, bisect_ms, vectors_ms; int grm_launches; int nsplit; } eb_timings;
+int eb_get_timings (eb_ctx *, eb_timings * t);
+/* FP64 DMMA / DFMA issue-rate microbenchmarks (TFLOP/s) used as roofline cross-checks */
+int eb_microbench_fp64 (eb_ctx *, double *dmma_tflops, double *dfma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
