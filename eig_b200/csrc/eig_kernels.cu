@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(KA_THREADS) tri_w_kernel(int n, int j, int k, 
 __device__ __forceinline__ void dmma884e(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-constexpr int TU_K = 16, TU_LD = 136;
+constexpr int TU_K = 16, TU_LD = 132;   // == 4 mod 16 doubles: conflict-free DMMA fragment reads
 __global__ void __launch_bounds__(256, 1) tri_trailing_kernel(double* __restrict__ A, int64_t lda, int n, int j1, int kp,
                                                               const double* __restrict__ Vp, const double* __restrict__ Wp) {
   __shared__ double Ps[TU_K][TU_LD], Qs[TU_K][TU_LD];

@@ -1,16 +1,401 @@
-// fpca_kernels.cu -- fastmode (kjg_fpca) and projection passes on the packed matrix.  (placeholder: filled in next)
+// fpca_kernels.cu -- fastmode randomised PCA (kjg_fpca, kjg_fpca.c:24-101) and the projection passes
+// (smartpca.c:1485-1525) as products of the 2-bit packed matrix with skinny FP64 matrices.
+//
+// Replaces kjg_fpca_XTXA/_XA/_XTB (kjg_fpca.c:104-178: decode 256 SNP rows to FP64 with
+// kjg_geno_get_normalized_rows, gval.c:173-213, then gsl_blas_dgemm) and LAPACKE_dgesvd (kjg_gsl.c:203).
+//
+// All skinny matrices are kept TRANSPOSED on the device (Mt[col][len], each logical column contiguous):
+//   packed_gemm<XA>  : Out_t[l][s] = sum_i x_si In_t[l][i]      rows = SNPs,        K = individuals
+//   packed_gemm<XTB> : Out_t[l][i] = sum_s x_si In_t[l][s]      rows = individuals, K = SNPs
+// with x_si = table[s][code(s,i)] decoded in registers and fed to FP64 DMMA (m8n8k4); the dense operand is staged
+// through shared memory.  Orthonormalisation of the M x (I+1)L sketch uses Householder QR (unconditionally stable;
+// the sketch blocks differ in scale by (lambda_1/lambda_k)^I, so Gram-based QR is not an option); the final small
+// SVD uses the Gram matrix of B only for the leading K triplets, where it is accurate to rounding.
+#include <algorithm>
 #include <cmath>
+#include <vector>
 #include "common.cuh"
 
 namespace eb {
-int fpca_run(eb_ctx*, int, int, size_t, size_t, size_t, long, double*, double*) {
-  set_error("eb_fpca: not built yet");
-  return EB_ERR_STATE;
+
+constexpr int PG_ROWS = 256;      // output rows per CTA (8 warps x 32)
+constexpr int PG_KT = 64;         // K elements per stage
+constexpr int PG_LD = PG_KT + 4;  // dense tile row stride in doubles (== 4 mod 16 -> conflict-free B fragments)
+enum { MODE_XA = 0, MODE_XTB = 1 };
+
+__device__ __forceinline__ void dmma884f(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-int project_run(eb_ctx*, const double*, int, double*, double*, double*) {
-  set_error("eb_project: not built yet");
-  return EB_ERR_STATE;
+
+// XTB: work tile [PG_KT snps][64 bytes = 256 individuals], table tile [PG_KT][4]
+// XA : work tile [256 snps][16 bytes = 64 individuals] (row stride 20 B to spread banks), table [256][4] fixed per CTA
+template <int MODE, int NBLK>
+__global__ void __launch_bounds__(256, 1)
+packed_gemm_kernel(const uint8_t* __restrict__ work, int64_t wpitch, const double* __restrict__ table, int64_t mpad, int npad,
+                   const double* __restrict__ In_t, int64_t ld_in, double* __restrict__ Out_t, int64_t ld_out, int ncols, double oscale) {
+  constexpr int NC = NBLK * 8;
+  constexpr int XA_STRIDE = 20;
+  constexpr int WBYTES = MODE == MODE_XTB ? PG_KT * 64 : PG_ROWS * XA_STRIDE;
+  extern __shared__ __align__(16) uint8_t pg_smem[];
+  double (*In_s)[NC][PG_LD] = reinterpret_cast<double (*)[NC][PG_LD]>(pg_smem);
+  uint8_t (*W_s)[WBYTES] = reinterpret_cast<uint8_t (*)[WBYTES]>(pg_smem + sizeof(double) * 2 * NC * PG_LD);
+  double* T_s = reinterpret_cast<double*>(pg_smem + sizeof(double) * 2 * NC * PG_LD + 2 * WBYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, h = lane >> 4;
+  const int64_t r0 = (int64_t)blockIdx.x * PG_ROWS;          // first output row (SNP or individual)
+  const int l0 = blockIdx.y * NC;                             // first output column
+  const int64_t Klen = MODE == MODE_XTB ? mpad : npad;
+  const int nk = (int)(Klen / PG_KT);
+
+  double acc[4][NBLK][2];
+#pragma unroll
+  for (int t = 0; t < 4; t++)
+#pragma unroll
+    for (int u = 0; u < NBLK; u++) acc[t][u][0] = acc[t][u][1] = 0.0;
+
+  if (MODE == MODE_XA) {
+    for (int idx = threadIdx.x; idx < PG_ROWS * 4; idx += 256) {
+      const int64_t s = r0 + (idx >> 2);
+      T_s[idx] = s < mpad ? table[s * 4 + (idx & 3)] : 0.0;
+    }
+  }
+
+  auto load_stage = [&](int st, int kb) {
+    const int64_t k0 = (int64_t)kb * PG_KT;
+    // dense tile: NC rows x PG_KT doubles
+    for (int idx = threadIdx.x; idx < NC * (PG_KT / 2); idx += 256) {
+      const int l = idx / (PG_KT / 2), kk = (idx % (PG_KT / 2)) * 2;
+      double2 v = make_double2(0.0, 0.0);
+      if (l0 + l < ncols) v = *reinterpret_cast<const double2*>(In_t + (size_t)(l0 + l) * ld_in + k0 + kk);
+      *reinterpret_cast<double2*>(&In_s[st][l][kk]) = v;
+    }
+    if (MODE == MODE_XTB) {
+      // packed: PG_KT snp rows x 64 bytes (256 individuals starting at r0)
+      for (int idx = threadIdx.x; idx < PG_KT * 4; idx += 256) {
+        const int kk = idx >> 2, part = idx & 3;
+        uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
+        const int64_t byte0 = r0 / 4 + part * 16;
+        if (byte0 + 16 <= wpitch) v = *reinterpret_cast<const uint4*>(work + (k0 + kk) * wpitch + byte0);
+        *reinterpret_cast<uint4*>(&W_s[st][kk * 64 + part * 16]) = v;
+      }
+      for (int idx = threadIdx.x; idx < PG_KT * 4; idx += 256) T_s[st * PG_KT * 4 + idx] = table[k0 * 4 + idx];
+    } else {
+      // packed: 256 snp rows x 16 bytes (64 individuals starting at k0)
+      for (int idx = threadIdx.x; idx < PG_ROWS; idx += 256) {
+        const int64_t s = r0 + idx;
+        uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
+        if (s < mpad) v = *reinterpret_cast<const uint4*>(work + s * wpitch + k0 / 4);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&W_s[st][idx * XA_STRIDE]);
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+      }
+    }
+  };
+
+  load_stage(0, 0);
+  __syncthreads();
+  for (int kb = 0; kb < nk; kb++) {
+    const int st = kb & 1;
+    if (kb + 1 < nk) load_stage(st ^ 1, kb + 1);
+#pragma unroll 2
+    for (int kk = 0; kk < PG_KT; kk += 4) {
+      double a[4], b[NBLK];
+      if (MODE == MODE_XTB) {
+        const uint32_t sh = ((3 - (g & 3)) << 1) + (h << 3);
+        const uint2 w = *reinterpret_cast<const uint2*>(&W_s[st][(kk + q) * 64 + warp * 8]);
+        const double* tk = &T_s[st * PG_KT * 4 + (kk + q) * 4];
+        const uint32_t v0 = w.x >> sh, v1 = w.y >> sh;
+        a[0] = tk[v0 & 3]; a[1] = tk[(v0 >> 16) & 3]; a[2] = tk[v1 & 3]; a[3] = tk[(v1 >> 16) & 3];
+      } else {
+        // individuals k0+kk .. +3 live in byte kk/4 of the 16-byte row segment; this thread's code is q (MSB first)
+        const int byte = kk >> 2;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          const int row = warp * 32 + t * 8 + g;
+          const uint32_t bv = W_s[st][row * XA_STRIDE + byte];
+          a[t] = T_s[row * 4 + ((bv >> ((3 - q) << 1)) & 3)];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NBLK; u++) b[u] = In_s[st][u * 8 + g][kk + q];
+#pragma unroll
+      for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int u = 0; u < NBLK; u++) dmma884f(acc[t][u][0], acc[t][u][1], a[t], b[u]);
+    }
+    __syncthreads();
+  }
+  const int64_t rlimit = MODE == MODE_XTB ? npad : mpad;
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const int64_t r = r0 + warp * 32 + t * 8 + g;
+    if (r >= rlimit) continue;
+#pragma unroll
+    for (int u = 0; u < NBLK; u++) {
+      const int l = l0 + u * 8 + q * 2;
+      if (l < ncols) Out_t[(size_t)l * ld_out + r] = acc[t][u][0] * oscale;
+      if (l + 1 < ncols) Out_t[(size_t)(l + 1) * ld_out + r] = acc[t][u][1] * oscale;
+    }
+  }
 }
+
+template <int MODE>
+static int launch_packed_gemm(eb_ctx* c, const double* table, const double* In_t, int64_t ld_in, double* Out_t, int64_t ld_out,
+                              int ncols, double oscale) {
+  const int64_t rows = MODE == MODE_XTB ? c->npad : c->mpad;
+  const unsigned gx = (unsigned)((rows + PG_ROWS - 1) / PG_ROWS);
+  int done = 0;
+  while (done < ncols) {
+    const int rem = ncols - done;
+    const int nblk = std::min(8, (rem + 7) / 8);
+    const int take = std::min(rem, nblk * 8);
+    dim3 grid(gx, 1);
+    const double* in = In_t + (size_t)done * ld_in;
+    double* out = Out_t + (size_t)done * ld_out;
+#define PG_CASE(NB_)                                                                                                              \
+  case NB_: {                                                                                                                     \
+    const size_t smem = sizeof(double) * 2 * (NB_ * 8) * PG_LD + 2 * (MODE == MODE_XTB ? PG_KT * 64 : PG_ROWS * 20) +              \
+                        sizeof(double) * (MODE == MODE_XTB ? 2 * PG_KT * 4 : PG_ROWS * 4);                                        \
+    EB_CUDA(cudaFuncSetAttribute(packed_gemm_kernel<MODE, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+    packed_gemm_kernel<MODE, NB_><<<grid, 256, smem, c->stream>>>(c->work.p, c->wpitch, table, c->mpad, c->npad, in, ld_in, out,  \
+                                                                 ld_out, take, oscale);                                           \
+  } break;
+    switch (nblk) {
+      PG_CASE(1) PG_CASE(2) PG_CASE(3) PG_CASE(4) PG_CASE(5) PG_CASE(6) PG_CASE(7) PG_CASE(8)
+    }
+#undef PG_CASE
+    EB_CHECK_LAUNCH(c);
+    done += take;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ per-SNP tables
+// fastmode table, gval.c:73-79: mean = xmean/xfancy; gtable[k] = ((k - mean) * xfancy) / sqrt(2); missing -> 0
+__global__ void fpca_table_kernel(int64_t nsnp, int64_t mpad, const double* __restrict__ xmean, const double* __restrict__ xfancy,
+                                  const int* __restrict__ nmiss, double* __restrict__ table) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= mpad) return;
+  double t0 = 0, t1 = 0, t2 = 0;
+  if (s < nsnp && nmiss[s] >= 0) {
+    const double xf = xfancy[s], mean = __ddiv_rn(xmean[s], xf), r2 = __dsqrt_rn(2.0);
+    t0 = __ddiv_rn(__dmul_rn(__dadd_rn(0.0, -mean), xf), r2);
+    t1 = __ddiv_rn(__dmul_rn(__dadd_rn(1.0, -mean), xf), r2);
+    t2 = __ddiv_rn(__dmul_rn(__dadd_rn(2.0, -mean), xf), r2);
+  }
+  reinterpret_cast<double4*>(table)[s] = make_double4(t0, t1, t2, 0.0);
+}
+
+// projection table, fixxrow (qpsubs.c:338-352): g*xfancy - xmean for observed genotypes of used SNPs, else 0
+__global__ void fix_table_kernel(int64_t nsnp, int64_t mpad, const double* __restrict__ xmean, const double* __restrict__ xfancy,
+                                 const uint8_t* __restrict__ used, double* __restrict__ table) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= mpad) return;
+  double t0 = 0, t1 = 0, t2 = 0;
+  if (s < nsnp && used[s]) {
+    const double xf = xfancy[s], xm = xmean[s];
+    t0 = __dadd_rn(0.0, -xm); t1 = __dadd_rn(xf, -xm); t2 = __dadd_rn(__dmul_rn(2.0, xf), -xm);
+  }
+  reinterpret_cast<double4*>(table)[s] = make_double4(t0, t1, t2, 0.0);
+}
+
+// ------------------------------------------------------------------------------------------ Householder QR on transposed storage
+__device__ __forceinline__ double bsum(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int i = 0; i < nw; i++) r += sh[i];
+  return r;
+}
+
+// reflector j from row j of At (positions j..len-1); v stored in place with v[j] = 1; tau[j], diag[j] = beta
+__global__ void __launch_bounds__(1024) qr_reflector_kernel(double* __restrict__ At, int64_t ld, int64_t len, int j, double* __restrict__ tau,
+                                                            double* __restrict__ diag) {
+  __shared__ double sh[32];
+  double* row = At + (size_t)j * ld;
+  double s = 0.0;
+  for (int64_t i = j + 1 + threadIdx.x; i < len; i += blockDim.x) s += row[i] * row[i];
+  s = bsum(s, sh);
+  const double alpha = row[j];
+  double beta = alpha, tj = 0.0, scal = 0.0;
+  if (s != 0.0) {
+    const double nrm = sqrt(alpha * alpha + s);
+    beta = alpha >= 0.0 ? -nrm : nrm;
+    tj = (beta - alpha) / beta;
+    scal = 1.0 / (alpha - beta);
+  }
+  __syncthreads();
+  for (int64_t i = j + 1 + threadIdx.x; i < len; i += blockDim.x) row[i] *= scal;
+  if (threadIdx.x == 0) { row[j] = 1.0; tau[j] = tj; diag[j] = beta; }
+}
+
+// apply H = I - tau v v^T (v = Vt row jv, support [jv, len)) to rows [r_first, r_first + gridDim.x) of Ct
+__global__ void __launch_bounds__(1024) qr_apply_kernel(const double* __restrict__ Vt, int64_t ldv, int jv, const double* __restrict__ tau,
+                                                        double* __restrict__ Ct, int64_t ldc, int r_first, int64_t len) {
+  __shared__ double sh[32];
+  const double tj = tau[jv];
+  if (tj == 0.0) return;
+  const double* v = Vt + (size_t)jv * ldv;
+  double* z = Ct + (size_t)(r_first + blockIdx.x) * ldc;
+  double s = 0.0;
+  for (int64_t i = jv + threadIdx.x; i < len; i += blockDim.x) s += v[i] * z[i];
+  s = bsum(s, sh) * tj;
+  for (int64_t i = jv + threadIdx.x; i < len; i += blockDim.x) z[i] -= s * v[i];
+}
+
+__global__ void set_identity_rows_kernel(double* __restrict__ Ut, int64_t ld, int c) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < c) Ut[(size_t)r * ld + r] = 1.0;
+}
+
+// Gram matrix of the rows of Bt: G[a][b] = sum_i Bt[a][i] Bt[b][i]  (one block per pair a >= b, fixed-order reduction)
+__global__ void __launch_bounds__(256) gram_rows_kernel(const double* __restrict__ Bt, int64_t ld, int64_t len, int c, double* __restrict__ G) {
+  __shared__ double sh[32];
+  const int a = blockIdx.y, b = blockIdx.x;
+  if (b > a) return;
+  const double* ra = Bt + (size_t)a * ld;
+  const double* rb = Bt + (size_t)b * ld;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < len; i += blockDim.x) s += ra[i] * rb[i];
+  s = bsum(s, sh);
+  if (threadIdx.x == 0) { G[(size_t)a * c + b] = s; G[(size_t)b * c + a] = s; }
+}
+
+// U_t[k][i] = (sum_l V[k][l] Bt[l][i]) / sigma_k   ;  sigma_k = sqrt(lam[k])
+__global__ void __launch_bounds__(256) left_vectors_kernel(const double* __restrict__ Bt, int64_t ld, int64_t len, int c, const double* __restrict__ V,
+                                                           const double* __restrict__ lam, int K, double* __restrict__ Ut) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (i >= len) return;
+  double s = 0.0;
+  for (int l = 0; l < c; l++) s += V[(size_t)k * c + l] * Bt[(size_t)l * ld + i];
+  Ut[(size_t)k * len + i] = s / sqrt(lam[k]);
+}
+
+__global__ void col_sumsq_kernel(const double* __restrict__ At, int64_t ld, int64_t len, double* __restrict__ out) {
+  __shared__ double sh[32];
+  const double* r = At + (size_t)blockIdx.x * ld;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < len; i += blockDim.x) s += r[i] * r[i];
+  s = bsum(s, sh);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+static int qr_orthonormal_rows(eb_ctx* c, double* At, int64_t ld, int64_t len, int ncol, double* Ut, double* tau_d, double* diag_d) {
+  // At (ncol rows of length len) is overwritten by its reflectors; Ut receives an orthonormal basis of span(At rows)
+  for (int j = 0; j < ncol && j < len; j++) {
+    qr_reflector_kernel<<<1, 1024, 0, c->stream>>>(At, ld, len, j, tau_d, diag_d);
+    EB_CHECK_LAUNCH(c);
+    if (j + 1 < ncol) {
+      qr_apply_kernel<<<ncol - j - 1, 1024, 0, c->stream>>>(At, ld, j, tau_d, At, ld, j + 1, len);
+      EB_CHECK_LAUNCH(c);
+    }
+  }
+  EB_CUDA(cudaMemsetAsync(Ut, 0, sizeof(double) * (size_t)ncol * ld, c->stream));
+  set_identity_rows_kernel<<<(ncol + 127) / 128, 128, 0, c->stream>>>(Ut, ld, ncol);
+  EB_CHECK_LAUNCH(c);
+  for (int j = std::min<int64_t>(ncol, len) - 1; j >= 0; j--) {
+    qr_apply_kernel<<<ncol - j, 1024, 0, c->stream>>>(At, ld, j, tau_d, Ut, ld, j, len);
+    EB_CHECK_LAUNCH(c);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ fastmode driver
+int fpca_run(eb_ctx* c, int fancynorm, int altnormstyle, size_t K, size_t L, size_t I, long seed, double* eval, double* evec) {
+  int rc;
+  const int64_t m = c->nsnp, mpad = c->mpad;
+  const int n = c->nrows, npad = c->npad;
+  const int cw = (int)((I + 1) * L);
+  if ((int64_t)cw > m || cw > n) { set_error("eb_fpca: (I+1)*L = %d exceeds the matrix dimensions (%lld x %d)", cw, (long long)m, n); return EB_ERR_ARG; }
+  // per-SNP statistics over the current rows (no drop rule: every uploaded SNP stays a row of X, gval.c:56-86)
+  eb_grm_opts o = {fancynorm, altnormstyle, 0, 2147483647, nullptr, nullptr};
+  if ((rc = launch_stats(c, &o))) return rc;
+  c->grm_valid = false;
+  DevBuf<double> ftab, Gt, Qt, Ut, Bt, tau, diag, gram, uk;
+  if ((rc = ftab.ensure((size_t)mpad * 4)) || (rc = Gt.ensure((size_t)L * npad)) || (rc = Qt.ensure((size_t)cw * mpad)) ||
+      (rc = Ut.ensure((size_t)cw * mpad)) || (rc = Bt.ensure((size_t)cw * npad)) || (rc = tau.ensure(cw)) || (rc = diag.ensure(cw)) ||
+      (rc = gram.ensure((size_t)cw * cw)) || (rc = uk.ensure((size_t)K * n)))
+    return rc;
+  fpca_table_kernel<<<(unsigned)((mpad + 255) / 256), 256, 0, c->stream>>>(m, mpad, c->xmean_d.p, c->xfancy_d.p, c->nmiss_d.p, ftab.p);
+  EB_CHECK_LAUNCH(c);
+  // G1 <- seeded Gaussians (host RNG, bit-exact with kjg_gsl.c:145-186), uploaded transposed
+  {
+    std::vector<double> G((size_t)n * L), T((size_t)L * npad, 0.0);
+    eb_gauss_matrix(seed, (size_t)n, L, G.data());
+    for (int i = 0; i < n; i++) for (size_t l = 0; l < L; l++) T[l * npad + i] = G[(size_t)i * L + l];
+    EB_CUDA(cudaMemcpyAsync(Gt.p, T.data(), sizeof(double) * T.size(), cudaMemcpyHostToDevice, c->stream));
+    EB_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  EB_CUDA(cudaMemsetAsync(Qt.p, 0, sizeof(double) * (size_t)cw * mpad, c->stream));
+  const double inv_m = 1.0 / (double)m;
+  for (size_t it = 0; it <= I; it++) {
+    double* Qi = Qt.p + (size_t)it * L * mpad;
+    if ((rc = launch_packed_gemm<MODE_XA>(c, ftab.p, Gt.p, npad, Qi, mpad, (int)L, 1.0))) return rc;      // Q_i = X G       (kjg_fpca.c:121,148)
+    if (it == I) break;
+    if ((rc = launch_packed_gemm<MODE_XTB>(c, ftab.p, Qi, mpad, Gt.p, npad, (int)L, inv_m))) return rc;    // G = X^T Q_i / m (kjg_fpca.c:123,53)
+  }
+  // Q <- orthonormal basis of its column span (kjg_fpca.c:63-71 keeps U of the SVD; any orthonormal basis of the same
+  // span gives the same B B^T and therefore the same leading singular triplets)
+  if ((rc = qr_orthonormal_rows(c, Qt.p, mpad, m, cw, Ut.p, tau.p, diag.p))) return rc;
+  // B = X^T Q   (kjg_fpca.c:79-80)
+  if ((rc = launch_packed_gemm<MODE_XTB>(c, ftab.p, Ut.p, mpad, Bt.p, npad, cw, 1.0))) return rc;
+  // leading K left singular vectors / values of B through the cw x cw Gram matrix
+  {
+    dim3 grid(cw, cw);
+    gram_rows_kernel<<<grid, 256, 0, c->stream>>>(Bt.p, npad, n, cw, gram.p);
+    EB_CHECK_LAUNCH(c);
+  }
+  std::vector<double> lam(cw), V((size_t)K * cw);
+  if ((rc = eig_resident(c, gram.p, cw, cw, 1.0, (int)K, lam.data(), V.data()))) return rc;
+  {
+    dim3 grid((n + 255) / 256, (unsigned)K);
+    left_vectors_kernel<<<grid, 256, 0, c->stream>>>(Bt.p, npad, n, cw, c->zvec_d.p, c->lambda_d.p, (int)K, uk.p);
+    EB_CHECK_LAUNCH(c);
+  }
+  std::vector<double> U((size_t)K * n);
+  EB_CUDA(cudaMemcpyAsync(U.data(), uk.p, sizeof(double) * U.size(), cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t k = 0; k < K; k++) {
+    eval[k] = lam[k] * (1.0 / (double)m);                      // S^2 / m, kjg_fpca.c:91-95
+    for (int i = 0; i < n; i++) evec[(size_t)i * K + k] = U[k * n + i];
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ projections (smartpca.c:1485-1525)
+int project_run(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, double* fxvecs, double* fxscal) {
+  int rc;
+  const int64_t m = c->nsnp, mpad = c->mpad;
+  const int n = c->nrows, npad = c->npad;
+  DevBuf<double> Ft, FFt, FXt, ftab, ss;
+  if ((rc = Ft.ensure((size_t)numeigs * npad)) || (rc = FFt.ensure((size_t)numeigs * mpad)) || (rc = FXt.ensure((size_t)numeigs * npad)) ||
+      (rc = ftab.ensure((size_t)mpad * 4)) || (rc = ss.ensure(numeigs)))
+    return rc;
+  // fvecs = 10 * evecs (setfvecs, smartpca.c:1444)
+  std::vector<double> T((size_t)numeigs * npad, 0.0);
+  for (int j = 0; j < numeigs; j++) for (int i = 0; i < n; i++) T[(size_t)j * npad + i] = 10.0 * evecs[(size_t)j * n + i];
+  EB_CUDA(cudaMemcpyAsync(Ft.p, T.data(), sizeof(double) * T.size(), cudaMemcpyHostToDevice, c->stream));
+  EB_CUDA(cudaMemsetAsync(FFt.p, 0, sizeof(double) * (size_t)numeigs * mpad, c->stream));
+  // ffvecs[j][s] = sum_k fvecs[j][k] x_ks with the GRM decode table (dropped / ignored SNPs contribute zero columns)
+  if ((rc = launch_packed_gemm<MODE_XA>(c, c->table_d.p, Ft.p, npad, FFt.p, mpad, numeigs, 1.0))) return rc;
+  fix_table_kernel<<<(unsigned)((mpad + 255) / 256), 256, 0, c->stream>>>(m, mpad, c->xmean_d.p, c->xfancy_d.p, c->used_d.p, ftab.p);
+  EB_CHECK_LAUNCH(c);
+  if ((rc = launch_packed_gemm<MODE_XTB>(c, ftab.p, FFt.p, mpad, FXt.p, npad, numeigs, 1.0))) return rc;
+  col_sumsq_kernel<<<numeigs, 256, 0, c->stream>>>(FXt.p, npad, n, ss.p);
+  EB_CHECK_LAUNCH(c);
+  std::vector<double> s(numeigs);
+  EB_CUDA(cudaMemcpyAsync(s.data(), ss.p, sizeof(double) * numeigs, cudaMemcpyDeviceToHost, c->stream));
+  if (ffvecs) EB_CUDA(cudaMemcpy2DAsync(ffvecs, sizeof(double) * m, FFt.p, sizeof(double) * mpad, sizeof(double) * m, numeigs, cudaMemcpyDeviceToHost, c->stream));
+  if (fxvecs) EB_CUDA(cudaMemcpy2DAsync(fxvecs, sizeof(double) * n, FXt.p, sizeof(double) * npad, sizeof(double) * n, numeigs, cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  if (fxscal) for (int j = 0; j < numeigs; j++) fxscal[j] = 1.0 / sqrt(s[j]);
+  return 0;
+}
+
 }  // namespace eb
 
 // Seeded Gaussian start matrix: kjg_gsl.c:96-113 (GSL mt19937, seed 0 -> 4357) and kjg_gsl.c:145-186

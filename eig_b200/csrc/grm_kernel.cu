@@ -95,7 +95,7 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restri
     // ===== TMA producer warp (one elected lane) =====
     if (lane == 0) {
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int t = item / nsplit, chunk = item - t * nsplit;
+        const int chunk = item / ntiles_tri, t = item - chunk * ntiles_tri;   // chunk-major: co-resident CTAs share one SNP range in L2
         int ti, tj; tri_decode(t, ti, tj);
         const int kb0 = (int)(((long long)nkblocks * chunk) / nsplit), kb1 = (int)(((long long)nkblocks * (chunk + 1)) / nsplit);
         for (int kb = kb0; kb < kb1; kb++) {
@@ -125,7 +125,7 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restri
     for (int u = 0; u < 4; u++) acc[t][u][0] = acc[t][u][1] = 0.0;
 
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int t_ = item / nsplit, chunk = item - t_ * nsplit;
+    const int chunk = item / ntiles_tri, t_ = item - chunk * ntiles_tri;
     int ti, tj; tri_decode(t_, ti, tj);
     const int kb0 = (int)(((long long)nkblocks * chunk) / nsplit), kb1 = (int)(((long long)nkblocks * (chunk + 1)) / nsplit);
     for (int kb = kb0; kb < kb1; kb++) {
