@@ -120,18 +120,10 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def cuda_array(ptr, shape, typestr="<f8"):
-    class _H:
-        pass
-    h = _H()
-    h.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2, "strides": None}
-    return h
-
-
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from eig_b200 import capi, synth
+    from eig_b200 import capi, parallel, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -158,7 +150,7 @@ def run_b200(args):
 
     def reduce_partials():
         ptr, ld, n = ctx.grm_device_ptr()
-        t = torch.as_tensor(cuda_array(ptr, (ld, ld)), device=dev)
+        t = parallel.device_view(ptr, (ld, ld), dev)
         dist.all_reduce(t)             # every rank ends with the full GRM (the eigensolver then runs replicated / row-distributed)
         torch.cuda.synchronize()
 
