@@ -5,11 +5,12 @@
 //
 // Design (sm_100a):
 //   * FP64 tensor path = mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4); tcgen05 has no f64 kind.
-//   * CTA = 128x128 output tile, 8 consumer warps (2x4, 64x32 each, 64 FP64 accumulators/thread) + 1 TMA
-//     producer warp.  Lower-triangle tiles only; optional split over SNP chunks into separate partial
+//   * CTA = 128x128 output tile, 8 warps (2x4, 64x32 each, 64 FP64 accumulators/thread); lane 0 of warp 0 doubles
+//     as the TMA producer.  Lower-triangle tiles only; optional split over SNP chunks into separate partial
 //     buffers (deterministic, no atomics) so that small N still fills 148 SMs for many waves.
 //   * Per stage the producer TMA-loads KT=128 SNPs x 32 bytes for the row tile and the column tile
 //     (cp.async.bulk.tensor.2d) and the 128x4 FP64 decode table (cp.async.bulk), mbarrier full/empty ring.
+//   * The decode of k-step i+1 is issued before the 32 DMMAs of k-step i (explicit software pipeline, LDS only).
 //   * Operands never exist in memory as FP64: each thread pulls the 16 (A) / 8 (B) packed bytes that hold
 //     its 8 / 4 fragment elements of SNP k, extracts the 2-bit codes with shifts and reads the FP64 value
 //     from the per-SNP 4-entry table in shared memory (bank-conflict free: 4 SNPs x 4 entries x 8 B = 128 B).
@@ -20,8 +21,7 @@
 namespace eb {
 
 constexpr int STAGES = 4;
-constexpr int CONSUMER_WARPS = 8;
-constexpr int GRM_THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int GRM_THREADS = 256;
 constexpr int STAGE_A = KT * 32;          // bytes
 constexpr int STAGE_T = KT * 4 * 8;       // bytes
 constexpr int STAGE_BYTES = 2 * STAGE_A + STAGE_T;
@@ -65,6 +65,22 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+  uint2 v;
+  asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+
 // tile pair index t -> (ti >= tj)
 __device__ __forceinline__ void tri_decode(int t, int& ti, int& tj) {
   int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
@@ -73,9 +89,19 @@ __device__ __forceinline__ void tri_decode(int t, int& ti, int& tj) {
   ti = r; tj = t - r * (r + 1) / 2;
 }
 
-__global__ void __launch_bounds__(GRM_THREADS, 1)
+// WARPS_M x WARPS_N consumer warps, each TB x UB m8n8 blocks (tile = 128 x 128).  There is no dedicated producer warp:
+// lane 0 of warp 0 keeps the TMA ring PREFETCH stages ahead, which leaves the full 64K registers to 8 warps (the
+// software-pipelined decode needs ~240/thread).  m8 row blocks that lie entirely in the pad region (rows >= nrows)
+// are skipped with a warp-uniform predicate.
+template <int WARPS_M, int WARPS_N, int TB, int UB, int UNROLL>
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, 1)
 grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ table, double* __restrict__ partial,
-                int npad, int ntiles_tri, int nsplit, int nkblocks) {
+                   int npad, int nrows, int ntiles_tri, int nsplit, int nkblocks) {
+  static_assert(WARPS_M * TB * 8 == TILE && WARPS_N * UB * 8 == TILE, "tile must be 128 x 128");
+  static_assert(TB == 4 || TB == 8, "A segment is 8 or 16 bytes");
+  static_assert(UB == 4 || UB == 8, "B segment is 8 or 16 bytes");
+  constexpr int NWARPS = WARPS_M * WARPS_N;
+  constexpr int PREFETCH = STAGES - 2;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -83,96 +109,144 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, CONSUMER_WARPS); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, NWARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   const int nitems = ntiles_tri * nsplit;
-  uint32_t stage = 0, phase = 0;
-
-  if (warp == CONSUMER_WARPS) {
-    // ===== TMA producer warp (one elected lane) =====
-    if (lane == 0) {
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int chunk = item / ntiles_tri, t = item - chunk * ntiles_tri;   // chunk-major: co-resident CTAs share one SNP range in L2
-        int ti, tj; tri_decode(t, ti, tj);
-        const int kb0 = (int)(((long long)nkblocks * chunk) / nsplit), kb1 = (int)(((long long)nkblocks * (chunk + 1)) / nsplit);
-        for (int kb = kb0; kb < kb1; kb++) {
-          mbar_wait(empty + stage, phase ^ 1);
-          uint8_t* sb = smem + stage * STAGE_BYTES;
-          mbar_expect_tx(full + stage, STAGE_BYTES);
-          tma_load_2d(sb, &tmap, ti * 32, kb * KT, full + stage);
-          tma_load_2d(sb + STAGE_A, &tmap, tj * 32, kb * KT, full + stage);
-          bulk_load_1d(sb + 2 * STAGE_A, table + (size_t)kb * KT * 4, STAGE_T, full + stage);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
+  // producer cursor (meaningful in thread 0 only)
+  int p_item = blockIdx.x, p_kb = 0, p_kb1 = 0, p_ti = 0, p_tj = 0;
+  uint32_t p_stage = 0, p_phase = 0;
+  bool p_open = false;          // p_item decoded
+  int ahead = 0;                // blocks issued but not yet consumed
+  auto produce = [&]() {
+    // keep the ring PREFETCH blocks ahead of the consumer
+    while (ahead < PREFETCH) {
+      if (!p_open) {
+        if (p_item >= nitems) return;
+        const int chunk = p_item / ntiles_tri, t = p_item - chunk * ntiles_tri;
+        tri_decode(t, p_ti, p_tj);
+        p_kb = (int)(((long long)nkblocks * chunk) / nsplit);
+        p_kb1 = (int)(((long long)nkblocks * (chunk + 1)) / nsplit);
+        p_open = true;
       }
+      mbar_wait(empty + p_stage, p_phase ^ 1);
+      uint8_t* sb = smem + p_stage * STAGE_BYTES;
+      mbar_expect_tx(full + p_stage, STAGE_BYTES);
+      tma_load_2d(sb, &tmap, p_ti * 32, p_kb * KT, full + p_stage);
+      tma_load_2d(sb + STAGE_A, &tmap, p_tj * 32, p_kb * KT, full + p_stage);
+      bulk_load_1d(sb + 2 * STAGE_A, table + (size_t)p_kb * KT * 4, STAGE_T, full + p_stage);
+      if (++p_stage == STAGES) { p_stage = 0; p_phase ^= 1; }
+      ahead++;
+      if (++p_kb == p_kb1) { p_open = false; p_item += gridDim.x; }
     }
-    return;
-  }
+  };
 
-  // ===== consumer warps =====
-  const int wm = warp >> 2, wn = warp & 3;     // 2 x 4 warps, 64 x 32 each
-  const int g = lane >> 2, q = lane & 3;       // fragment row / k index
-  const int h = lane >> 4;                     // which byte of the pair holds this thread's individual
-  const uint32_t sh = ((3 - (g & 3)) << 1) + (h << 3);   // bit position of element t=0 inside word 0
+  const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+  const int g = lane >> 2, q = lane & 3, h = lane >> 4;
+  const uint32_t sh = ((3 - (g & 3)) << 1) + (h << 3);
 
-  double acc[8][4][2];
+  double acc[TB][UB][2];
 #pragma unroll
-  for (int t = 0; t < 8; t++)
+  for (int t = 0; t < TB; t++)
 #pragma unroll
-    for (int u = 0; u < 4; u++) acc[t][u][0] = acc[t][u][1] = 0.0;
+    for (int u = 0; u < UB; u++) acc[t][u][0] = acc[t][u][1] = 0.0;
 
+  uint32_t stage = 0, phase = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int chunk = item / ntiles_tri, t_ = item - chunk * ntiles_tri;
     int ti, tj; tri_decode(t_, ti, tj);
     const int kb0 = (int)(((long long)nkblocks * chunk) / nsplit), kb1 = (int)(((long long)nkblocks * (chunk + 1)) / nsplit);
+    // valid m8 row blocks of this warp (rows beyond nrows are padding and decode to zero anyway)
+    int tvalid = (nrows - (ti * TILE + wm * TB * 8) + 7) >> 3;
+    tvalid = tvalid < 0 ? 0 : (tvalid > TB ? TB : tvalid);
     for (int kb = kb0; kb < kb1; kb++) {
+      if (threadIdx.x == 0) produce();
+      __syncwarp();
       mbar_wait(full + stage, phase);
-      const uint8_t* sb = smem + stage * STAGE_BYTES;
-      const uint8_t* pa = sb + wm * 16 + q * 32;
-      const uint8_t* pb = sb + STAGE_A + wn * 8 + q * 32;
-      const uint8_t* pt = sb + 2 * STAGE_A + q * 32;
-#pragma unroll 1
-      for (int kk = 0; kk < KT; kk += 4) {
-        const uint4 wa = *reinterpret_cast<const uint4*>(pa + kk * 32);
-        const uint2 wb = *reinterpret_cast<const uint2*>(pb + kk * 32);
-        const uint8_t* tk = pt + kk * 32;
-        double a[8], b[4];
-        {
-          const uint32_t v0 = wa.x >> sh, v1 = wa.y >> sh, v2 = wa.z >> sh, v3 = wa.w >> sh;
-          a[0] = *reinterpret_cast<const double*>(tk + ((v0 << 3) & 0x18));
-          a[1] = *reinterpret_cast<const double*>(tk + ((v0 >> 13) & 0x18));
-          a[2] = *reinterpret_cast<const double*>(tk + ((v1 << 3) & 0x18));
-          a[3] = *reinterpret_cast<const double*>(tk + ((v1 >> 13) & 0x18));
-          a[4] = *reinterpret_cast<const double*>(tk + ((v2 << 3) & 0x18));
-          a[5] = *reinterpret_cast<const double*>(tk + ((v2 >> 13) & 0x18));
-          a[6] = *reinterpret_cast<const double*>(tk + ((v3 << 3) & 0x18));
-          a[7] = *reinterpret_cast<const double*>(tk + ((v3 >> 13) & 0x18));
-          const uint32_t u0 = wb.x >> sh, u1 = wb.y >> sh;
-          b[0] = *reinterpret_cast<const double*>(tk + ((u0 << 3) & 0x18));
-          b[1] = *reinterpret_cast<const double*>(tk + ((u0 >> 13) & 0x18));
-          b[2] = *reinterpret_cast<const double*>(tk + ((u1 << 3) & 0x18));
-          b[3] = *reinterpret_cast<const double*>(tk + ((u1 >> 13) & 0x18));
+      // 32-bit shared-space addresses (explicit LDS; the table row base is 32-byte aligned so OR replaces ADD)
+      const uint32_t sb = smem_u32(smem + stage * STAGE_BYTES);
+      const uint32_t pa = sb + wm * (TB * 2) + q * 32;
+      const uint32_t pb = sb + STAGE_A + wn * (UB * 2) + q * 32;
+      const uint32_t pt = sb + 2 * STAGE_A + q * 32;
+      // decode one k-step (4 SNPs): packed bytes -> 2-bit codes -> FP64 values from the per-SNP table
+      auto decode = [&](int kk, double (&a)[TB], double (&b)[UB]) {
+        const uint32_t tk = pt + kk * 32;
+        uint32_t wa[TB / 2], wb[UB / 2];
+        if (TB == 8) { const uint4 w = lds_v4(pa + kk * 32); wa[0] = w.x; wa[1] = w.y; wa[TB / 2 - 2] = w.z; wa[TB / 2 - 1] = w.w; }
+        else { const uint2 w = lds_v2(pa + kk * 32); wa[0] = w.x; wa[1] = w.y; }
+        if (UB == 8) { const uint4 w = lds_v4(pb + kk * 32); wb[0] = w.x; wb[1] = w.y; wb[UB / 2 - 2] = w.z; wb[UB / 2 - 1] = w.w; }
+        else { const uint2 w = lds_v2(pb + kk * 32); wb[0] = w.x; wb[1] = w.y; }
+#pragma unroll
+        for (int i = 0; i < TB / 2; i++) {
+          const uint32_t v = wa[i] >> sh;
+          a[2 * i] = lds_f64(tk | ((v << 3) & 0x18));
+          a[2 * i + 1] = lds_f64(tk | ((v >> 13) & 0x18));
         }
 #pragma unroll
-        for (int t = 0; t < 8; t++)
+        for (int i = 0; i < UB / 2; i++) {
+          const uint32_t v = wb[i] >> sh;
+          b[2 * i] = lds_f64(tk | ((v << 3) & 0x18));
+          b[2 * i + 1] = lds_f64(tk | ((v >> 13) & 0x18));
+        }
+      };
+      if (tvalid == TB) {
+        if (UNROLL == 2) {
+          // software pipeline: the operands of k-step i+1 are decoded before the 32 DMMAs of k-step i are issued, so
+          // the two warps of an SMSP never both sit in a decode bubble while the DMMA pipe drains
+          double a0[TB], b0[UB], a1[TB], b1[UB];
+          decode(0, a0, b0);
+#pragma unroll 1
+          for (int kk = 0; kk < KT; kk += 8) {
+            decode(kk + 4, a1, b1);
 #pragma unroll
-          for (int u = 0; u < 4; u++) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
+            for (int t = 0; t < TB; t++)
+#pragma unroll
+              for (int u = 0; u < UB; u++) dmma884(acc[t][u][0], acc[t][u][1], a0[t], b0[u]);
+            if (kk + 8 < KT) decode(kk + 8, a0, b0);
+#pragma unroll
+            for (int t = 0; t < TB; t++)
+#pragma unroll
+              for (int u = 0; u < UB; u++) dmma884(acc[t][u][0], acc[t][u][1], a1[t], b1[u]);
+          }
+        } else {
+#pragma unroll 1
+          for (int kk = 0; kk < KT; kk += 4) {
+            double a[TB], b[UB];
+            decode(kk, a, b);
+#pragma unroll
+            for (int t = 0; t < TB; t++)
+#pragma unroll
+              for (int u = 0; u < UB; u++) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
+          }
+        }
+      } else if (tvalid > 0) {
+#pragma unroll 1
+        for (int kk = 0; kk < KT; kk += 4) {
+          double a[TB], b[UB];
+          decode(kk, a, b);
+#pragma unroll
+          for (int t = 0; t < TB; t++) {
+            if (t < tvalid) {
+#pragma unroll
+              for (int u = 0; u < UB; u++) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
+            }
+          }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + stage);
+      if (threadIdx.x == 0) ahead--;
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
-    // epilogue: accumulators -> partial[chunk], lower tile (ti,tj)
     double* out = partial + (size_t)chunk * npad * npad;
 #pragma unroll
-    for (int t = 0; t < 8; t++) {
-      const size_t row = (size_t)ti * TILE + wm * 64 + t * 8 + g;
+    for (int t = 0; t < TB; t++) {
+      const size_t row = (size_t)ti * TILE + wm * (TB * 8) + t * 8 + g;
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const size_t col = (size_t)tj * TILE + wn * 32 + u * 8 + q * 2;
+      for (int u = 0; u < UB; u++) {
+        const size_t col = (size_t)tj * TILE + wn * (UB * 8) + u * 8 + q * 2;
         *reinterpret_cast<double2*>(out + row * npad + col) = make_double2(acc[t][u][0], acc[t][u][1]);
         acc[t][u][0] = acc[t][u][1] = 0.0;
       }
@@ -277,15 +351,20 @@ int grm_accumulate(eb_ctx* c) {
 
   CUtensorMap map;
   if ((rc = make_work_tensormap(c, &map))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EB_CUDA(cudaFuncSetAttribute(grm_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRM_SMEM));
-    attr_set = true;
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("EB_GRM_VARIANT");          // 1 = non-pipelined decode (debug / A-B only)
+    variant = e ? atoi(e) : 2;
+    EB_CUDA(cudaFuncSetAttribute(grm_syrk_kernel<2, 4, 8, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRM_SMEM));
+    EB_CUDA(cudaFuncSetAttribute(grm_syrk_kernel<2, 4, 8, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRM_SMEM));
   }
   const int nitems = ntri * nsplit;
   const int grid = std::min(nitems, c->num_sms);
   EB_CUDA(cudaEventRecord(c->ev[2], c->stream));
-  grm_syrk_kernel<<<grid, GRM_THREADS, GRM_SMEM, c->stream>>>(map, c->table_d.p, c->partial.p, c->npad, ntri, nsplit, nkb);
+  if (variant == 1)
+    grm_syrk_kernel<2, 4, 8, 4, 1><<<grid, GRM_THREADS, GRM_SMEM, c->stream>>>(map, c->table_d.p, c->partial.p, c->npad, c->nrows, ntri, nsplit, nkb);
+  else
+    grm_syrk_kernel<2, 4, 8, 4, 2><<<grid, GRM_THREADS, GRM_SMEM, c->stream>>>(map, c->table_d.p, c->partial.p, c->npad, c->nrows, ntri, nsplit, nkb);
   EB_CHECK_LAUNCH(c);
   EB_CUDA(cudaEventRecord(c->ev[3], c->stream));
   const int T32 = c->npad / 32;
