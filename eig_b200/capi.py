@@ -36,7 +36,8 @@ class PcaResult(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("gather_ms", C.c_float), ("stats_ms", C.c_float), ("grm_ms", C.c_float), ("finalize_ms", C.c_float),
                 ("tridiag_ms", C.c_float), ("bisect_ms", C.c_float), ("vectors_ms", C.c_float),
-                ("grm_launches", C.c_int), ("nsplit", C.c_int)]
+                ("grm_launches", C.c_int), ("nsplit", C.c_int), ("eig_method", C.c_int), ("chfsi_iters", C.c_int),
+                ("chfsi_matvecs", C.c_int)]
 
 
 EXPORTS = [
@@ -44,7 +45,7 @@ EXPORTS = [
     "eb_reset_launch_count", "eb_upload_packed", "eb_upload_packed_rows", "eb_adopt_packed_device", "eb_synth_packed_device",
     "eb_set_rows", "eb_snp_counts", "eb_indiv_valid_counts", "eb_grm", "eb_grm_partial", "eb_grm_device_ptr", "eb_grm_finish",
     "eb_eig", "eb_eigvecs", "eb_ridoutlier", "eb_pca_full", "eb_fpca", "eb_gauss_matrix", "eb_project", "eb_get_timings",
-    "eb_microbench_fp64",
+    "eb_microbench_fp64", "eb_set_option", "eb_debug_tridiag",
 ]
 
 _lib = None
@@ -190,8 +191,18 @@ class Context:
         return y.value, xtx
 
     # ---- eigen
-    def eig(self, nvec):
-        lam = np.empty(self.nrows); vec = np.empty((max(nvec, 1), self.nrows))
+    def set_option(self, key, value):
+        _chk(lib().eb_set_option(self.h, key.encode(), C.c_int(value)))
+
+    def debug_tridiag(self, mat, want_band=True):
+        mat = np.ascontiguousarray(mat, np.float64); n = mat.shape[0]
+        d = np.empty(n); e = np.empty(n); band = np.empty((n, 128)) if want_band else None
+        _chk(lib().eb_debug_tridiag(self.h, _p(mat), C.c_int(n), _p(d), _p(e), _p(band)))
+        return d, e[:n - 1], band
+
+    def eig(self, nvec, want_lambda=True):
+        lam = np.empty(self.nrows) if want_lambda else None
+        vec = np.empty((max(nvec, 1), self.nrows))
         _chk(lib().eb_eig(self.h, C.c_int(nvec), _p(lam), _p(vec)))
         return lam, vec[:nvec]
 

@@ -52,7 +52,7 @@ eb_ctx* eb_create(int device) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("eb_create: stream"); delete c; return nullptr; }
-  for (int i = 0; i < 8; i++) cudaEventCreate(&c->ev[i]);
+  for (int i = 0; i < 12; i++) cudaEventCreate(&c->ev[i]);
   return c;
 }
 
@@ -60,7 +60,7 @@ void eb_destroy(eb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  for (int i = 0; i < 8; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 12; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -291,9 +291,37 @@ int eb_eigvecs(eb_ctx* c, const double* mat, double* evals, double* evecs, int n
   EB_CUDA(cudaSetDevice(c->device));
   DevBuf<double> A;
   int rc;
-  if ((rc = A.ensure((size_t)n * n))) return rc;
-  EB_CUDA(cudaMemcpyAsync(A.p, mat, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, c->stream));
-  return eig_resident(c, A.p, n, n, 1.0, nvec, evals, evecs);
+  const int64_t lda = ((int64_t)n + 15) & ~15ll;      // 128-byte rows: legal TMA pitch for any n
+  if ((rc = A.ensure((size_t)n * lda))) return rc;
+  EB_CUDA(cudaMemcpy2DAsync(A.p, sizeof(double) * lda, mat, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice, c->stream));
+  return eig_resident(c, A.p, lda, n, 1.0, nvec, evals, evecs);
+}
+
+// testing aid: two-stage tridiagonalisation of a host matrix; d[n], e[n] (unscaled), band[n*128] or NULL
+int eb_debug_tridiag(eb_ctx* c, const double* mat, int n, double* d, double* e, double* band) {
+  if (!c || !mat || n < 3) { set_error("eb_debug_tridiag: bad argument"); return EB_ERR_ARG; }
+  EB_CUDA(cudaSetDevice(c->device));
+  DevBuf<double> A, de;
+  int rc;
+  const int64_t lda = ((int64_t)n + 15) & ~15ll;
+  if ((rc = A.ensure((size_t)n * lda)) || (rc = de.ensure((size_t)2 * n))) return rc;
+  EB_CUDA(cudaMemcpy2DAsync(A.p, sizeof(double) * lda, mat, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice, c->stream));
+  c->dbg_band_h = band;
+  rc = two_stage_tridiag(c, A.p, lda, n, de.p, de.p + n);
+  c->dbg_band_h = nullptr;
+  if (rc) return rc;
+  EB_CUDA(cudaMemcpyAsync(d, de.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaMemcpyAsync(e, de.p + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int eb_set_option(eb_ctx* c, const char* key, int value) {
+  if (!c || !key) return EB_ERR_ARG;
+  if (!strcmp(key, "eig_method")) { c->opt_eig_method = value; return 0; }
+  if (!strcmp(key, "two_stage_min")) { c->opt_two_stage_min = value; return 0; }
+  set_error("eb_set_option: unknown key '%s'", key);
+  return EB_ERR_ARG;
 }
 
 // ridoutlier, smartsubs.c:18-93: same operation order as the reference so that |z| > thresh decisions agree bit for bit
@@ -367,17 +395,29 @@ int eb_pca_full(eb_ctx* c, const eb_pca_opts* o, int* xindex_io, int nrows, doub
     const int n = (int)xi.size();
     const int nv = std::max(std::min(o->numeigs, n), std::min(std::min(o->numoutleigs, n - 1), n));
     std::vector<double> ev((size_t)std::max(nv, 1) * n);
+    // Large n: the outlier passes only need the leading vectors (smartpca.c:1250); the full spectrum (.eval, Tracy-Widom)
+    // is computed once, on the pass that turns out to be the last.  Small n: one-stage solver, everything each pass.
+    const bool two = eig_uses_two_stage(c, n, nv);
     t0 = now_s();
-    if ((rc = eb_eig(c, nv, lambda, ev.data()))) return rc;
+    if ((rc = eb_eig(c, nv, two ? nullptr : lambda, ev.data()))) return rc;
     res->secs_eig += now_s() - t0;
     res->niter = iter; res->y = y; res->nused = nused; res->nrows_final = n;
     const int keep = std::min(o->numeigs, n);
     if (evecs) memcpy(evecs, ev.data(), sizeof(double) * (size_t)keep * n);
     if (snp_used) memcpy(snp_used, used.data(), c->nsnp);
-    if (iter > o->numoutliter) break;                                      // last pass skips outliers, smartpca.c:1246
-    const int neigs = std::min(o->numoutleigs, n - 1);                     // smartpca.c:1249
-    const int nbad = eb_ridoutlier(ev.data(), n, neigs, o->outlthresh, outmode, bad.data(), vecno.data(), score.data());
-    if (nbad == 0) break;
+    int nbad = 0;
+    if (iter <= o->numoutliter) {                                          // last pass skips outliers, smartpca.c:1246
+      const int neigs = std::min(o->numoutleigs, n - 1);                   // smartpca.c:1249
+      nbad = eb_ridoutlier(ev.data(), n, neigs, o->outlthresh, outmode, bad.data(), vecno.data(), score.data());
+    }
+    if (nbad == 0) {
+      if (two) {
+        t0 = now_s();
+        if ((rc = eb_eig(c, 0, lambda, nullptr))) return rc;
+        res->secs_eig += now_s() - t0;
+      }
+      break;
+    }
     std::vector<char> kill(n, 0);
     for (int b = 0; b < nbad; b++) {
       const int j = bad[b];

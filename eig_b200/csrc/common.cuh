@@ -99,9 +99,14 @@ struct eb_ctx {
   eb::DevBuf<double> eigw;        // misc vectors
   eb::DevBuf<double> eigV, eigW;  // panels
   eb::DevBuf<double> lambda_d, zvec_d;
+  eb::DevBuf<double> eig2w, chfsiw;   // two-stage reduction / subspace-iteration workspaces (eig2_kernels.cu)
+  std::vector<double> ritz;        // scaled Ritz values of the last subspace iteration
+  double* dbg_band_h = nullptr;    // eb_debug_tridiag only
+  int opt_eig_method = 0;          // 0 auto, 1 one-stage (dsytrd-style), 2 two-stage + subspace iteration
+  int opt_two_stage_min = 1536;    // auto: n at which the two-stage path takes over
 
   eb_timings tm = {};
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[12] = {};
 };
 
 namespace eb {
@@ -117,6 +122,10 @@ int grm_trace(eb_ctx* c);        // recompute trace_d / y from xtx
 int microbench_fp64(eb_ctx* c, double* dmma, double* dfma);
 // eig_kernels.cu
 int eig_resident(eb_ctx* c, const double* A_d, int64_t lda, int n, double scale, int nvec, double* lambda_h, double* evecs_h);
+bool eig_uses_two_stage(const eb_ctx* c, int n, int nvec);
+// eig2_kernels.cu
+int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, double* e);
+int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* theta_h, double* vec_d, int* iters_out, int* matvecs_out);
 // fpca_kernels.cu
 int fpca_run(eb_ctx* c, int fancynorm, int altnormstyle, size_t K, size_t L, size_t I, long seed, double* eval, double* evec);
 int project_run(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, double* fxvecs, double* fxscal);

@@ -1,0 +1,962 @@
+// eig2_kernels.cu -- large-N symmetric eigensolver on a device-resident FP64 matrix (replaces eigvecs() -> dspev_,
+// eigsubs.c:39-55 / eigx.c:97-117, for the sizes where a one-stage reduction is HBM-bound).
+//
+//   spectrum (all eigenvalues, what .eval / Tracy-Widom consume, smartpca.c:1312-1431):
+//     stage 1  dense -> band (bandwidth 64): per 64-column panel a grid-cooperative Householder QR (one grid barrier per
+//              column, panel resident in shared memory), W = A22 V and the rank-128 update A22 -= V Z^T + Z V^T on the FP64
+//              tensor cores (eig2_gemm.cu).  Only the lower triangle is maintained.
+//     stage 2  band -> tridiagonal by column-wise bulge chasing; one CTA per sweep, sweeps pipelined two blocks apart
+//              through release/acquire progress counters, band (51 MB at n = 50k) resident in L2.
+//     then the Sturm-count bisection of eig_kernels.cu.
+//   leading eigenvectors (what ridoutlier and the .evec consume, smartpca.c:1250,1444): Chebyshev-filtered subspace
+//     iteration on the ORIGINAL matrix with a 64-wide block: block mat-vecs on the tensor cores, shifted CholeskyQR,
+//     Rayleigh-Ritz through a 64 x 64 parallel Jacobi solver.  No back-transformation through the two stages is needed.
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "dmma_tile.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace eb {
+
+int launch_sym_skinny(eb_ctx* c, const double* A, int64_t lda, int n, int t0, const double* Bt, int64_t ldb, double* Wpart, int64_t ldw,
+                      int max_ksplit, int* ksplit_out);
+int launch_syr2k_lower(eb_ctx* c, double* A, int64_t lda, int n, int t0, const double* VZ, int64_t ldv);
+
+constexpr int BW = 64;             // band width after stage 1 == panel width
+constexpr int MAX_KSPLIT = 4;
+
+__device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Grid-wide barrier for kernels launched cooperatively (all CTAs co-resident): monotonic arrival counter, zeroed by the
+// host before the launch.  A bounded spin turns a lost CTA into an error flag instead of a hung GPU.
+__device__ __forceinline__ void grid_barrier(int* bar, int target, int* err) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1);
+    long long spins = 0;
+    while (ld_acquire(bar) < target) {
+      if (++spins > (1ll << 26)) { atomicExch(err, 3); break; }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// =================================================================================================== panel QR
+struct PanelParams {
+  double* A; int64_t lda; int n; int j;
+  double* VZ; int64_t ldv;
+  double* T;          // [64][64] row-major, upper triangular
+  double* gpart;      // [2][G][64]
+  double* rowk;       // [2][64]
+  double* G2part;     // [G][64][64]
+  double* G2;         // [64][64]
+  double* gscratch;   // chunk storage when it does not fit shared memory
+  int* bar; int* err; // grid barrier counter (zeroed before launch), error flag
+  int rows_per; int use_global;
+};
+
+__global__ void __launch_bounds__(256, 1) panel_qr_kernel(PanelParams p) {
+  extern __shared__ __align__(16) double psm[];
+  const int G = gridDim.x, tid = threadIdx.x, c = tid & 63, part = tid >> 6;
+  int bar_target = 0;
+  const int r0 = p.j + BW, np = p.n - r0;
+  const int row0 = blockIdx.x * p.rows_per;
+  const int rows = max(0, min(p.rows_per, np - row0));
+  double* P = p.use_global ? p.gscratch + (size_t)blockIdx.x * p.rows_per * 64 : psm;
+  double* sh = p.use_global ? psm : psm + (size_t)p.rows_per * 64;
+  double (*red)[64] = reinterpret_cast<double (*)[64]>(sh);     // [4][64]
+  double* gsum = sh + 256;
+  double* rk = sh + 320;
+  double* scal_s = sh + 384;
+  double* tau_s = sh + 448;
+  const bool owner = blockIdx.x == 0;                            // rows_per >= 64: panel rows 0..63 live in CTA 0
+
+  for (int idx = tid; idx < rows * 64; idx += 256) {
+    const int i = idx >> 6, cc = idx & 63;
+    P[idx] = p.A[(size_t)(r0 + row0 + i) * p.lda + p.j + cc];
+  }
+  if (blockIdx.x == G - 1) {
+    // absolute rows j..j+63 of Vt are above the active block from now on
+    for (int idx = tid; idx < 64 * 64; idx += 256) p.VZ[(size_t)(idx >> 6) * p.ldv + p.j + (idx & 63)] = 0.0;
+  }
+  if (tid < 64) { scal_s[tid] = 0.0; tau_s[tid] = 0.0; }
+  __syncthreads();
+
+  const int nr = min(64, np - 1);
+  for (int k = 0; k < nr; k++) {
+    double acc = 0.0;
+    if (c >= k) {
+      int i = part;
+      if (owner) while (i <= k) i += 4;                        // only rows below the diagonal enter the dots
+      for (; i < rows; i += 4) acc += P[i * 64 + k] * P[i * 64 + c];
+    }
+    red[part][c] = acc;
+    __syncthreads();
+    if (tid < 64) {
+      __stcg(&p.gpart[((size_t)(k & 1) * G + blockIdx.x) * 64 + tid], red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid]);
+      if (owner) __stcg(&p.rowk[(k & 1) * 64 + tid], P[k * 64 + tid]);
+    }
+    grid_barrier(p.bar, bar_target += G, p.err);
+    acc = 0.0;
+    for (int b = part; b < G; b += 4) acc += ldcg(&p.gpart[((size_t)(k & 1) * G + b) * 64 + c]);
+    __syncthreads();                                            // red[] of the first phase has been consumed
+    red[part][c] = acc;
+    __syncthreads();
+    if (tid < 64) { gsum[tid] = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid]; rk[tid] = ldcg(&p.rowk[(k & 1) * 64 + tid]); }
+    __syncthreads();
+    const double alpha = rk[k], sigma = gsum[k];
+    double tau = 0.0, scal = 0.0, beta = alpha;
+    if (sigma != 0.0) {
+      const double nrm = sqrt(alpha * alpha + sigma);
+      beta = alpha >= 0.0 ? -nrm : nrm;
+      tau = (beta - alpha) / beta;
+      scal = 1.0 / (alpha - beta);
+    }
+    if (c > k && tau != 0.0) {
+      const double vtp = rk[c] + scal * gsum[c];
+      const double f = tau * scal * vtp;
+      int i = part;
+      if (owner) {
+        if ((k & 3) == part) P[k * 64 + c] -= tau * vtp;        // row k itself (v_k = 1)
+        while (i <= k) i += 4;
+      }
+      for (; i < rows; i += 4) P[i * 64 + c] -= P[i * 64 + k] * f;
+    }
+    if (tid == 0) {
+      if (owner) P[k * 64 + k] = beta;
+      scal_s[k] = scal; tau_s[k] = tau;
+    }
+    __syncthreads();
+  }
+
+  // R back into the matrix (band part): rows r0..r0+63, columns j..j+63, upper triangular
+  if (owner) {
+    for (int idx = tid; idx < min(rows, 64) * 64; idx += 256) {
+      const int i = idx >> 6, cc = idx & 63;
+      p.A[(size_t)(r0 + i) * p.lda + p.j + cc] = (i <= cc) ? P[idx] : 0.0;
+    }
+  }
+  __syncthreads();
+  // P -> V (unit lower trapezoidal; columns >= nr and columns with tau == 0 are zero below the diagonal)
+  for (int idx = tid; idx < rows * 64; idx += 256) {
+    const int i = idx >> 6, cc = idx & 63, gi = row0 + i;
+    double v = 0.0;
+    if (cc < nr) v = gi > cc ? P[idx] * scal_s[cc] : (gi == cc ? 1.0 : 0.0);
+    P[idx] = v;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < rows * 64; idx += 256) {
+    const int cc = idx / rows, i = idx - cc * rows;
+    p.VZ[(size_t)cc * p.ldv + r0 + row0 + i] = P[i * 64 + cc];
+  }
+  // partial Gram V^T V (a < c part is what T needs)
+  {
+    double g2[16];
+#pragma unroll
+    for (int a = 0; a < 16; a++) g2[a] = 0.0;
+    for (int i = 0; i < rows; i++) {
+      const double vc = P[i * 64 + c];
+#pragma unroll
+      for (int a = 0; a < 16; a++) g2[a] += P[i * 64 + part * 16 + a] * vc;
+    }
+#pragma unroll
+    for (int a = 0; a < 16; a++) __stcg(&p.G2part[((size_t)blockIdx.x * 64 + part * 16 + a) * 64 + c], g2[a]);
+  }
+  grid_barrier(p.bar, bar_target += G, p.err);
+  for (int a = blockIdx.x; a < 64; a += G) {
+    double acc = 0.0;
+    for (int b = part; b < G; b += 4) acc += ldcg(&p.G2part[((size_t)b * 64 + a) * 64 + c]);
+    __syncthreads();
+    red[part][c] = acc;
+    __syncthreads();
+    if (tid < 64) __stcg(&p.G2[a * 64 + tid], red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid]);
+  }
+  grid_barrier(p.bar, bar_target += G, p.err);
+  if (blockIdx.x == 0) {
+    // T (dlarft, forward columnwise): T[0:k,k] = -tau_k T[0:k,0:k] (V^T v_k)
+    double* Ts = P;                 // 64 x 65 (P is at least 64 x 64 ... use stride 64 to stay inside the chunk)
+    double* Gs = p.use_global ? p.gscratch + 4096 : psm + 4096;   // second 64x64 block of the chunk area (rows_per >= 128 guaranteed by host)
+    for (int idx = tid; idx < 4096; idx += 256) { Ts[idx] = 0.0; Gs[idx] = ldcg(&p.G2[idx]); }
+    __syncthreads();
+    for (int k = 0; k < 64; k++) {
+      const double tk = tau_s[k];
+      if (tid < k && tk != 0.0) {
+        double s = 0.0;
+        for (int m = tid; m < k; m++) s += Ts[tid * 64 + m] * Gs[m * 64 + k];
+        Ts[tid * 64 + k] = -tk * s;
+      }
+      if (tid == k) Ts[k * 64 + k] = tk;
+      __syncthreads();
+    }
+    for (int idx = tid; idx < 4096; idx += 256) p.T[idx] = Ts[idx];
+  }
+}
+
+// =================================================================================================== skinny helpers
+// Out[c][i] = a1 * sum_ks Wpart[ks][c][i] + a2 * Y1[c][i] + a3 * Y0[c][i]   for i in [i_lo, n), zero for [i_zero0, i_lo)
+__global__ void __launch_bounds__(256) combine_kernel(const double* __restrict__ Wpart, int ksplit, int64_t ldw, double* __restrict__ Out,
+                                                      int64_t ldo, int n, int i_zero0, int i_lo, double a1, const double* __restrict__ Y1,
+                                                      double a2, const double* __restrict__ Y0, double a3, int64_t ldy) {
+  const int i = i_zero0 + blockIdx.x * 256 + threadIdx.x, c = blockIdx.y;
+  if (i >= n) return;
+  double v = 0.0;
+  if (i >= i_lo) {
+    for (int ks = 0; ks < ksplit; ks++) v += Wpart[((size_t)ks * 64 + c) * ldw + i];
+    v *= a1;
+    if (Y1) v += a2 * Y1[(size_t)c * ldy + i];
+    if (Y0) v += a3 * Y0[(size_t)c * ldy + i];
+  }
+  Out[(size_t)c * ldo + i] = v;
+}
+
+// Gpart[chunk][a][c] = sum_{i in chunk} Xt[a][i] * Yt[c][i], chunks of GR_CHUNK over [i0, n)
+__global__ void __launch_bounds__(256) gram64_kernel(const double* __restrict__ Xt, int64_t ldx, const double* __restrict__ Yt, int64_t ldy,
+                                                     int i0, int n, int GR_CHUNK, double* __restrict__ Gpart) {
+  __shared__ double Xs[64][33], Ys[64][33];
+  const int tid = threadIdx.x, ta = tid >> 4, tc = tid & 15;
+  const int lo = i0 + blockIdx.x * GR_CHUNK, hi = min(n, lo + GR_CHUNK);
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+  for (int s = lo; s < hi; s += 32) {
+    __syncthreads();
+    for (int idx = tid; idx < 64 * 32; idx += 256) {
+      const int r = idx >> 5, ii = idx & 31, i = s + ii;
+      Xs[r][ii] = i < hi ? Xt[(size_t)r * ldx + i] : 0.0;
+      Ys[r][ii] = i < hi ? Yt[(size_t)r * ldy + i] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int ii = 0; ii < 32; ii++) {
+      double xa[4], yb[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) xa[a] = Xs[ta * 4 + a][ii];
+#pragma unroll
+      for (int b = 0; b < 4; b++) yb[b] = Ys[tc * 4 + b][ii];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] += xa[a] * yb[b];
+    }
+  }
+  double* out = Gpart + (size_t)blockIdx.x * 4096;
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) out[(ta * 4 + a) * 64 + tc * 4 + b] = acc[a][b];
+}
+
+// Out[c][i] = sum_k C1[k][c] X1[k][i] (+ sum_k C2[k][c] X2[k][i]) for i in [i0, n); C row-major 64 x 64
+__global__ void __launch_bounds__(256) left_mult_kernel(const double* __restrict__ C1, const double* __restrict__ X1,
+                                                        const double* __restrict__ C2, const double* __restrict__ X2, int64_t ldx,
+                                                        double* __restrict__ Out, int64_t ldo, int i0, int n) {
+  extern __shared__ __align__(16) double lm[];
+  double* C1s = lm;            // [64][64]
+  double* X1s = lm + 4096;     // [64][64]
+  double* C2s = lm + 8192;
+  double* X2s = lm + 12288;
+  const int tid = threadIdx.x, il = tid & 63, cgp = tid >> 6;
+  const int ibase = i0 + blockIdx.x * 64;
+  for (int idx = tid; idx < 4096; idx += 256) {
+    const int k = idx >> 6, ii = idx & 63, i = ibase + ii;
+    C1s[idx] = C1[idx];
+    X1s[idx] = i < n ? X1[(size_t)k * ldx + i] : 0.0;
+    if (C2) { C2s[idx] = C2[idx]; X2s[idx] = i < n ? X2[(size_t)k * ldx + i] : 0.0; }
+  }
+  __syncthreads();
+  double acc[16];
+#pragma unroll
+  for (int cc = 0; cc < 16; cc++) acc[cc] = 0.0;
+  for (int k = 0; k < 64; k++) {
+    const double x = X1s[k * 64 + il];
+#pragma unroll
+    for (int cc = 0; cc < 16; cc++) acc[cc] += C1s[k * 64 + cgp * 16 + cc] * x;
+  }
+  if (C2) {
+    for (int k = 0; k < 64; k++) {
+      const double x = X2s[k * 64 + il];
+#pragma unroll
+      for (int cc = 0; cc < 16; cc++) acc[cc] += C2s[k * 64 + cgp * 16 + cc] * x;
+    }
+  }
+  const int i = ibase + il;
+  if (i < n) {
+#pragma unroll
+    for (int cc = 0; cc < 16; cc++) Out[(size_t)(cgp * 16 + cc) * ldo + i] = acc[cc];
+  }
+}
+
+// one CTA: S = sum_chunks Spart; M = T^T S T; C1 = T, C2 = -M/2
+__global__ void __launch_bounds__(256) sbr_small_kernel(const double* __restrict__ Spart, int nchunk, const double* __restrict__ T,
+                                                        double* __restrict__ C1, double* __restrict__ C2) {
+  extern __shared__ __align__(16) double ss[];
+  double* S = ss; double* Ts = ss + 4096; double* U = ss + 8192;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < 4096; idx += 256) {
+    double v = 0.0;
+    for (int ch = 0; ch < nchunk; ch++) v += Spart[(size_t)ch * 4096 + idx];
+    S[idx] = v; Ts[idx] = T[idx];
+  }
+  __syncthreads();
+  // U = S T
+  for (int idx = tid; idx < 4096; idx += 256) {
+    const int r = idx >> 6, cc = idx & 63;
+    double v = 0.0;
+    for (int k = 0; k <= cc; k++) v += S[r * 64 + k] * Ts[k * 64 + cc];      // T upper triangular
+    U[idx] = v;
+  }
+  __syncthreads();
+  // M = T^T U
+  for (int idx = tid; idx < 4096; idx += 256) {
+    const int r = idx >> 6, cc = idx & 63;
+    double v = 0.0;
+    for (int k = 0; k <= r; k++) v += Ts[k * 64 + r] * U[k * 64 + cc];
+    C2[idx] = -0.5 * v;
+    C1[idx] = Ts[idx];
+  }
+}
+
+// =================================================================================================== band storage
+// AB[col][d] = A[col+d][col] for d <= BW (lower triangle of A), zero for BW < d < 2*BW
+__global__ void __launch_bounds__(128) band_extract_kernel(const double* __restrict__ A, int64_t lda, int n, double* __restrict__ AB) {
+  const int col = blockIdx.x, d = threadIdx.x;
+  double v = 0.0;
+  if (d <= BW && col + d < n) v = A[(size_t)(col + d) * lda + col];
+  AB[(size_t)col * (2 * BW) + d] = v;
+}
+__global__ void band_de_kernel(const double* __restrict__ AB, int n, double* __restrict__ d, double* __restrict__ e) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { d[i] = AB[(size_t)i * (2 * BW)]; e[i] = i < n - 1 ? AB[(size_t)i * (2 * BW) + 1] : 0.0; }
+}
+
+// =================================================================================================== bulge chasing
+
+constexpr int BC_THREADS = 256;
+constexpr int BC_LD = 65;
+constexpr int BC_DONE = 0x3fffffff;
+constexpr int BC_SMEM = (2 * 64 * BC_LD + 64 * 5 + 256) * 8;
+
+struct HouseSh { double tau, beta; };
+
+// reflector from x[0..len) held in xs (shared): leaves v in vs (v[0] = 1), returns tau/beta through hs.  warp 0 only.
+__device__ __forceinline__ void bc_make_reflector(const double* xs, int len, double* vs, HouseSh* hs, int lane) {
+  double s = 0.0;
+  for (int i = 1 + lane; i < len; i += 32) s += xs[i] * xs[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const double alpha = xs[0];
+  double tau = 0.0, beta = alpha, scal = 0.0;
+  if (s != 0.0) {
+    const double nrm = sqrt(alpha * alpha + s);
+    beta = alpha >= 0.0 ? -nrm : nrm;
+    tau = (beta - alpha) / beta;
+    scal = 1.0 / (alpha - beta);
+  }
+  __syncwarp();
+  for (int i = lane; i < 64; i += 32) vs[i] = i == 0 ? 1.0 : (i < len ? xs[i] * scal : 0.0);
+  if (lane == 0) { hs->tau = tau; hs->beta = beta; }
+}
+
+// D (len x len symmetric, full in shared, ld BC_LD, D[c][i]) <- H D H with H = I - tau v v^T
+__device__ __forceinline__ void bc_two_sided(double* Ds, int len, const double* vs, double tau, double* red, double* ps, double* ws,
+                                             int tid) {
+  const int i = tid & 63, part = tid >> 6;
+  double acc = 0.0;
+  if (i < len)
+    for (int cc = part * 16; cc < part * 16 + 16; cc++) acc += Ds[cc * BC_LD + i] * vs[cc];   // vs is zero beyond len, Ds too
+  red[part * 64 + i] = acc;
+  __syncthreads();
+  if (tid < 64) ps[tid] = tau * (red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid]);
+  __syncthreads();
+  if (tid < 32) {
+    double s = ps[tid] * vs[tid] + ps[tid + 32] * vs[tid + 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const double al = -0.5 * tau * s;
+    ws[tid] = ps[tid] + al * vs[tid];
+    ws[tid + 32] = ps[tid + 32] + al * vs[tid + 32];
+  }
+  __syncthreads();
+  if (i < len) {
+    const double vi = vs[i], wi = ws[i];
+    for (int cc = part * 16; cc < part * 16 + 16; cc++) Ds[cc * BC_LD + i] -= vi * ws[cc] + wi * vs[cc];
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(BC_THREADS) bulge_chase_kernel(double* __restrict__ AB, int n, int* __restrict__ prog, int* __restrict__ err) {
+  extern __shared__ __align__(16) double bcs[];
+  double* Bs = bcs;                       // [64][BC_LD]
+  double* Ds = bcs + 64 * BC_LD;          // [64][BC_LD]
+  double* v1 = Ds + 64 * BC_LD;
+  double* v2 = v1 + 64;
+  double* xs = v2 + 64;
+  double* red = xs + 64;                  // [256]
+  double* ps = red + 256;
+  double* ws = ps + 64;
+  __shared__ HouseSh hs_s;
+  __shared__ int abort_flag;
+  HouseSh& hs = hs_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, i = tid & 63, part = tid >> 6;
+  constexpr int LDAB = 2 * BW;
+  if (tid == 0) abort_flag = 0;
+  __syncthreads();
+
+  auto wait_for = [&](int s_prev, int need) {
+    if (s_prev >= 0) {
+      if (tid == 0) {
+        long long spins = 0;
+        while (ld_acquire(prog + s_prev) < need) {
+          if (spins > 4) __nanosleep(spins < 64 ? 20 : 400);
+          if (++spins > (1ll << 24)) { abort_flag = 1; atomicExch(err, 1); break; }
+          if (spins % 4096 == 0 && ld_acquire(err)) { abort_flag = 1; break; }
+        }
+      }
+      __syncthreads();
+    }
+  };
+  auto publish = [&](int s, int val) {
+    __syncthreads();                       // every thread's band stores precede the barrier ...
+    if (tid == 0) { __threadfence(); st_release(prog + s, val); }   // ... and are published cumulatively by one fence + release
+  };
+
+  for (int s = blockIdx.x; s < n - 2; s += gridDim.x) {
+    // ---- block 0: annihilate column s below the sub-diagonal
+    wait_for(s - 1, 2);
+    if (abort_flag) return;
+    int r0 = s + 1, la = min(BW, n - r0);
+    if (tid < 64) xs[tid] = tid < la ? __ldcg(&AB[(size_t)s * LDAB + 1 + tid]) : 0.0;
+    // diagonal block rows/cols r0..r0+la-1 -> full symmetric in Ds[c][i]
+    for (int cc = part; cc < 64; cc += 4) {
+      if (i >= cc) {
+        const double v = (cc < la && i < la) ? __ldcg(&AB[(size_t)(r0 + cc) * LDAB + (i - cc)]) : 0.0;
+        Ds[cc * BC_LD + i] = v;
+        Ds[i * BC_LD + cc] = v;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) bc_make_reflector(xs, la, v1, &hs, lane);
+    __syncthreads();
+    double tau = hs.tau;
+    if (tid < la) __stcg(&AB[(size_t)s * LDAB + 1 + tid], tid == 0 ? hs.beta : 0.0);
+    bc_two_sided(Ds, la, v1, tau, red, ps, ws, tid);
+    for (int cc = part; cc < la; cc += 4)
+      if (i >= cc && i < la) __stcg(&AB[(size_t)(r0 + cc) * LDAB + (i - cc)], Ds[cc * BC_LD + i]);
+    publish(s, 1);
+
+    // ---- chase the bulge down the band
+    double* vprev = v1; double* vnext = v2;
+    for (int k = 1;; k++) {
+      const int r1 = r0 + la;
+      const int lb = min(BW, n - r1);
+      if (lb <= 0) break;
+      wait_for(s - 1, k + 2);
+      if (abort_flag) return;
+      // B: rows r1..r1+lb-1, cols r0..r0+la-1  -> Bs[c][i];  D: rows/cols r1..r1+lb-1
+      for (int cc = part; cc < 64; cc += 4) {
+        double vb = 0.0;
+        if (cc < la && i < lb) vb = __ldcg(&AB[(size_t)(r0 + cc) * LDAB + (la + i - cc)]);
+        Bs[cc * BC_LD + i] = vb;
+        if (i >= cc) {
+          const double vd = (cc < lb && i < lb) ? __ldcg(&AB[(size_t)(r1 + cc) * LDAB + (i - cc)]) : 0.0;
+          Ds[cc * BC_LD + i] = vd;
+          Ds[i * BC_LD + cc] = vd;
+        }
+      }
+      __syncthreads();
+      // right-apply previous reflector: B <- B (I - tau v v^T)
+      {
+        double acc = 0.0;
+        for (int cc = part * 16; cc < part * 16 + 16; cc++) acc += Bs[cc * BC_LD + i] * vprev[cc];
+        red[part * 64 + i] = acc;
+        __syncthreads();
+        const double wi = tau * (red[i] + red[64 + i] + red[128 + i] + red[192 + i]);
+        for (int cc = part * 16; cc < part * 16 + 16; cc++) Bs[cc * BC_LD + i] -= wi * vprev[cc];
+        __syncthreads();
+      }
+      // new reflector from column 0 of B
+      if (tid < 64) xs[tid] = Bs[tid];
+      __syncthreads();
+      if (warp == 0) bc_make_reflector(xs, lb, vnext, &hs, lane);
+      __syncthreads();
+      const double tau2 = hs.tau;
+      // left-apply: B <- (I - tau2 v2 v2^T) B ; thread (c = i, part over rows)
+      {
+        double acc = 0.0;
+        for (int r = part * 16; r < part * 16 + 16; r++) acc += vnext[r] * Bs[i * BC_LD + r];
+        red[part * 64 + i] = acc;
+        __syncthreads();
+        if (tid < 64) ps[tid] = tau2 * (red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid]);   // u[c]
+        __syncthreads();
+        const double vi = vnext[i];
+        for (int cc = part * 16; cc < part * 16 + 16; cc++) Bs[cc * BC_LD + i] -= vi * ps[cc];
+        __syncthreads();
+      }
+      if (tid < 64) Bs[tid] = tid == 0 ? hs.beta : 0.0;           // column 0 is (beta, 0, ..., 0)
+      bc_two_sided(Ds, lb, vnext, tau2, red, ps, ws, tid);         // (starts with a barrier-protected phase; Bs col 0 write is ordered by its syncs)
+      for (int cc = part; cc < 64; cc += 4) {
+        if (cc < la && i < lb) __stcg(&AB[(size_t)(r0 + cc) * LDAB + (la + i - cc)], Bs[cc * BC_LD + i]);
+        if (cc < lb && i >= cc && i < lb) __stcg(&AB[(size_t)(r1 + cc) * LDAB + (i - cc)], Ds[cc * BC_LD + i]);
+      }
+      publish(s, k + 1);
+      r0 = r1; la = lb; tau = tau2;
+      double* t = vprev; vprev = vnext; vnext = t;
+    }
+    publish(s, BC_DONE);
+  }
+}
+
+// =================================================================================================== 64 x 64 dense helpers
+// Parallel two-sided Jacobi (round-robin ordering).  In: Hpart (nchunk x 64 x 64 partial Grams, summed and symmetrised here).
+// Out: theta[64] descending, Z[k][c] (row-major) = eigenvector c.
+__global__ void __launch_bounds__(256) jacobi64_kernel(const double* __restrict__ Hpart, int nchunk, double* __restrict__ theta,
+                                                       double* __restrict__ Z) {
+  extern __shared__ __align__(16) double jsm[];
+  double* H = jsm; double* V = jsm + 64 * 65;
+  __shared__ double cs[32], sn[32], redw[8];
+  __shared__ int pp[32], qq[32], rank[64];
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < 4096; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    double a = 0.0, b = 0.0;
+    for (int ch = 0; ch < nchunk; ch++) { a += Hpart[(size_t)ch * 4096 + r * 64 + c]; b += Hpart[(size_t)ch * 4096 + c * 64 + r]; }
+    H[r * 65 + c] = 0.5 * (a + b);
+    V[r * 65 + c] = r == c ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  __shared__ int nrot;
+  for (int sweep = 0; sweep < 30; sweep++) {
+    if (tid == 0) nrot = 0;
+    __syncthreads();
+    for (int round = 0; round < 63; round++) {
+      if (tid < 32) {
+        int a, b;
+        if (tid == 0) { a = 63; b = round; }
+        else { a = (round + tid) % 63; b = (round - tid + 63) % 63; }
+        const int p = min(a, b), q = max(a, b);
+        pp[tid] = p; qq[tid] = q;
+        const double hpq = H[p * 65 + q], hpp = H[p * 65 + p], hqq = H[q * 65 + q];
+        double c = 1.0, s = 0.0;
+        if (fabs(hpq) > 1.0e-16 * sqrt(fabs(hpp * hqq)) && fabs(hpq) > 1e-300) {
+          const double th = (hqq - hpp) / (2.0 * hpq);
+          const double t = (th >= 0.0 ? 1.0 : -1.0) / (fabs(th) + sqrt(1.0 + th * th));
+          c = 1.0 / sqrt(1.0 + t * t); s = t * c;
+          atomicAdd(&nrot, 1);
+        }
+        cs[tid] = c; sn[tid] = s;
+      }
+      __syncthreads();
+      // columns: X[:, p], X[:, q] <- X J for H and V
+      for (int idx = tid; idx < 32 * 64; idx += 256) {
+        const int pr = idx >> 6, r = idx & 63;
+        const double c = cs[pr], s = sn[pr];
+        if (s == 0.0) continue;
+        const int p = pp[pr], q = qq[pr];
+        const double hp = H[r * 65 + p], hq = H[r * 65 + q];
+        H[r * 65 + p] = c * hp - s * hq; H[r * 65 + q] = s * hp + c * hq;
+        const double vp = V[r * 65 + p], vq = V[r * 65 + q];
+        V[r * 65 + p] = c * vp - s * vq; V[r * 65 + q] = s * vp + c * vq;
+      }
+      __syncthreads();
+      // rows: H[p, :], H[q, :] <- J^T H ; the annihilated pair is set to exactly zero
+      for (int idx = tid; idx < 32 * 64; idx += 256) {
+        const int pr = idx >> 6, cc = idx & 63;
+        const double c = cs[pr], s = sn[pr];
+        if (s == 0.0) continue;
+        const int p = pp[pr], q = qq[pr];
+        const double hp = H[p * 65 + cc], hq = H[q * 65 + cc];
+        double np_ = c * hp - s * hq, nq_ = s * hp + c * hq;
+        if (cc == q) np_ = 0.0;
+        if (cc == p) nq_ = 0.0;
+        H[p * 65 + cc] = np_; H[q * 65 + cc] = nq_;
+      }
+      __syncthreads();
+    }
+    if (nrot == 0) break;
+    __syncthreads();
+  }
+  // sort descending
+  if (tid < 64) {
+    const double me = H[tid * 65 + tid];
+    int rk = 0;
+    for (int j = 0; j < 64; j++) { const double o = H[j * 65 + j]; rk += (o > me) || (o == me && j < tid); }
+    rank[tid] = rk;
+    theta[rk] = me;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 4096; idx += 256) {
+    const int k = idx >> 6, c = idx & 63;
+    Z[k * 64 + rank[c]] = V[k * 65 + c];
+  }
+}
+
+// G = sum Gpart (+ shift * trace on the diagonal) = R^T R ; out Rinv (row-major, upper) so that W Rinv is orthonormal.
+__global__ void __launch_bounds__(256) cholinv64_kernel(const double* __restrict__ Gpart, int nchunk, double shift_rel, double* __restrict__ Rinv,
+                                                        int* __restrict__ err) {
+  extern __shared__ __align__(16) double csm[];
+  double* Gs = csm; double* Ri = csm + 64 * 65;
+  __shared__ double tr;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < 4096; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    double a = 0.0, b = 0.0;
+    for (int ch = 0; ch < nchunk; ch++) { a += Gpart[(size_t)ch * 4096 + r * 64 + c]; b += Gpart[(size_t)ch * 4096 + c * 64 + r]; }
+    Gs[r * 65 + c] = 0.5 * (a + b);
+  }
+  __syncthreads();
+  if (tid == 0) { double s = 0.0; for (int k = 0; k < 64; k++) s += Gs[k * 65 + k]; tr = s; }
+  __syncthreads();
+  if (tid < 64) Gs[tid * 65 + tid] += shift_rel * tr;
+  __syncthreads();
+  // right-looking Cholesky, upper factor R stored in the upper triangle of Gs: G = R^T R
+  for (int k = 0; k < 64; k++) {
+    if (tid == 0) {
+      double d = Gs[k * 65 + k];
+      if (!(d > 0.0)) { atomicExch(err, 2); d = 1.0; }
+      Gs[k * 65 + k] = sqrt(d);
+    }
+    __syncthreads();
+    const double rkk = Gs[k * 65 + k];
+    if (tid > k && tid < 64) Gs[k * 65 + tid] /= rkk;
+    __syncthreads();
+    for (int idx = tid; idx < 4096; idx += 256) {
+      const int r = idx >> 6, c = idx & 63;
+      if (r > k && c >= r) Gs[r * 65 + c] -= Gs[k * 65 + r] * Gs[k * 65 + c];
+    }
+    __syncthreads();
+  }
+  // Rinv: solve R x = e_c column by column (thread c), x upper triangular
+  if (tid < 64) {
+    const int c = tid;
+    for (int r = 63; r >= 0; r--) {
+      double v = 0.0;
+      if (r <= c) {
+        v = r == c ? 1.0 : 0.0;
+        for (int m = r + 1; m <= c; m++) v -= Gs[r * 65 + m] * Ri[m * 65 + c];
+        v /= Gs[r * 65 + r];
+      }
+      Ri[r * 65 + c] = v;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 4096; idx += 256) Rinv[idx] = Ri[(idx >> 6) * 65 + (idx & 63)];
+}
+
+// res2[c] = sum_i (AV[c][i] - theta[c] V[c][i])^2 : one CTA per column (fixed-order reduction)
+__global__ void __launch_bounds__(256) resnorm_kernel(const double* __restrict__ AVt, const double* __restrict__ Vt, int64_t ld, int n,
+                                                      const double* __restrict__ theta, double* __restrict__ res2) {
+  __shared__ double red[256];
+  const int c = blockIdx.x;
+  const double th = theta[c];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) { const double r = AVt[(size_t)c * ld + i] - th * Vt[(size_t)c * ld + i]; s += r * r; }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) res2[c] = red[0];
+}
+
+__global__ void __launch_bounds__(256) randinit_kernel(double* __restrict__ Vt, int64_t ld, int n) {
+  const int i = blockIdx.x * 256 + threadIdx.x, c = blockIdx.y;
+  if (i >= n) return;
+  uint64_t x = ((uint64_t)(c + 1) << 40) ^ (uint64_t)i * 0x9E3779B97F4A7C15ull;
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  Vt[(size_t)c * ld + i] = ((double)(x >> 11) * (1.0 / 9007199254740992.0)) - 0.5;
+}
+
+__global__ void __launch_bounds__(256) normalize_rows_kernel(double* __restrict__ Vt, int64_t ld, int n) {
+  __shared__ double red[256];
+  double* v = Vt + (size_t)blockIdx.x * ld;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += v[i] * v[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+  const double inv = 1.0 / sqrt(red[0]);
+  for (int i = threadIdx.x; i < n; i += 256) v[i] *= inv;
+}
+
+// =================================================================================================== host drivers
+static int coop_launch(eb_ctx* c, const void* fn, dim3 grid, dim3 block, void** args, size_t smem) {
+  EB_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, smem, c->stream));
+  c->launches++;
+  return 0;
+}
+
+// chunk length for gram64: a multiple of 32, at least 256, at most ~2 CTAs per SM
+static int gram_chunk(const eb_ctx* c, int len) {
+  int ch = (len + 2 * c->num_sms - 1) / (2 * c->num_sms);
+  ch = (std::max(ch, 256) + 31) & ~31;
+  return ch;
+}
+
+struct Eig2Work {
+  double *VZ, *Wpart, *Wt, *T, *C1, *C2, *gpart, *rowk, *G2part, *G2, *Spart, *AB, *gscratch;
+  int* prog; int* err;
+  int64_t ldv;
+};
+
+// Stage 1 + stage 2: A (n x n, lda, lower triangle + complete diagonal tiles valid; destroyed) -> d, e (unscaled)
+int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, double* e) {
+  cudaStream_t st = c->stream;
+  int rc;
+  const int64_t ldv = ((int64_t)n + 7) & ~7ll;
+  const int G_max = c->num_sms;
+  const int nchunk_max = (n + 255) / 256 + 1;
+  // workspace (doubles)
+  size_t off = 0;
+  auto take = [&](size_t cnt) { size_t o = off; off += (cnt + 15) & ~size_t(15); return o; };
+  const size_t oVZ = take((size_t)128 * ldv), oWp = take((size_t)MAX_KSPLIT * 64 * ldv), oWt = take((size_t)64 * ldv), oT = take(4096),
+               oC1 = take(4096), oC2 = take(4096), ogp = take((size_t)2 * G_max * 64), ork = take(128), oG2p = take((size_t)G_max * 4096),
+               oG2 = take(4096), oSp = take((size_t)nchunk_max * 4096), oAB = take((size_t)n * 2 * BW);
+  // panel chunk: shared memory holds up to PANEL_SMEM_ROWS rows; beyond that the chunk lives in global scratch
+  constexpr int SH_EXTRA = 512 * 8;                    // reduction scratch (doubles * 8)
+  const int max_rows_smem = (int)((227 * 1024 - SH_EXTRA - 1024) / 512);
+  int rows_per0 = std::max(128, (((n - BW + G_max - 1) / G_max) + 3) & ~3);
+  const bool use_global = rows_per0 > max_rows_smem;
+  const size_t oGs = take(use_global ? (size_t)G_max * rows_per0 * 64 : 16);
+  const size_t oInt = take(((size_t)n + 64) / 2 + 16);
+  if ((rc = c->eig2w.ensure(off))) return rc;
+  double* W = c->eig2w.p;
+  Eig2Work w;
+  w.VZ = W + oVZ; w.Wpart = W + oWp; w.Wt = W + oWt; w.T = W + oT; w.C1 = W + oC1; w.C2 = W + oC2; w.gpart = W + ogp; w.rowk = W + ork;
+  w.G2part = W + oG2p; w.G2 = W + oG2; w.Spart = W + oSp; w.AB = W + oAB; w.gscratch = W + oGs; w.ldv = ldv;
+  w.prog = reinterpret_cast<int*>(W + oInt); w.err = w.prog + n + 8;
+  EB_CUDA(cudaMemsetAsync(w.VZ, 0, sizeof(double) * 128 * ldv, st));
+  EB_CUDA(cudaMemsetAsync(w.prog, 0, sizeof(int) * ((size_t)n + 16), st));
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    EB_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    EB_CUDA(cudaFuncSetAttribute(left_mult_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    EB_CUDA(cudaFuncSetAttribute(sbr_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 8));
+    attr_set = true;
+  }
+
+  for (int j = 0; n - j - BW >= 2; j += BW) {
+    const int r0 = j + BW, np = n - r0, t0 = r0 / DT_M;
+    // ---- panel QR
+    PanelParams pp;
+    pp.A = A; pp.lda = lda; pp.n = n; pp.j = j; pp.VZ = w.VZ; pp.ldv = ldv; pp.T = w.T; pp.gpart = w.gpart; pp.rowk = w.rowk;
+    pp.G2part = w.G2part; pp.G2 = w.G2; pp.gscratch = w.gscratch; pp.use_global = use_global ? 1 : 0;
+    pp.bar = w.err + 1; pp.err = w.err;
+    EB_CUDA(cudaMemsetAsync(pp.bar, 0, sizeof(int), st));
+    int rows_per = std::max(128, (((np + G_max - 1) / G_max) + 3) & ~3);
+    if (use_global) rows_per = rows_per0;
+    const int G = (np + rows_per - 1) / rows_per;
+    pp.rows_per = rows_per;
+    const size_t smem = use_global ? (size_t)(8192 + 512) * 8 : (size_t)rows_per * 512 + SH_EXTRA;
+    void* args[] = {&pp};
+    if ((rc = coop_launch(c, (const void*)panel_qr_kernel, dim3(G), dim3(256), args, smem))) return rc;
+    // ---- W = A22 V
+    int ksplit = 1;
+    if ((rc = launch_sym_skinny(c, A, lda, n, t0, w.VZ, ldv, w.Wpart, ldv, MAX_KSPLIT, &ksplit))) return rc;
+    const int i_z0 = t0 * DT_M;
+    {
+      dim3 grid((n - i_z0 + 255) / 256, 64);
+      combine_kernel<<<grid, 256, 0, st>>>(w.Wpart, ksplit, ldv, w.Wt, ldv, n, i_z0, r0, 1.0, nullptr, 0.0, nullptr, 0.0, ldv);
+      EB_CHECK_LAUNCH(c);
+    }
+    // ---- S = V^T W ; C1 = T ; C2 = -T^T S T / 2 ; Z = W C1 + V C2
+    const int gch = gram_chunk(c, n - r0);
+    const int nchunk = (n - r0 + gch - 1) / gch;
+    gram64_kernel<<<nchunk, 256, 0, st>>>(w.VZ, ldv, w.Wt, ldv, r0, n, gch, w.Spart);
+    EB_CHECK_LAUNCH(c);
+    sbr_small_kernel<<<1, 256, 12288 * 8, st>>>(w.Spart, nchunk, w.T, w.C1, w.C2);
+    EB_CHECK_LAUNCH(c);
+    left_mult_kernel<<<(n - i_z0 + 63) / 64, 256, 16384 * 8, st>>>(w.C1, w.Wt, w.C2, w.VZ, ldv, w.VZ + (size_t)64 * ldv, ldv, i_z0, n);
+    EB_CHECK_LAUNCH(c);
+    // ---- A22 -= V Z^T + Z V^T
+    if ((rc = launch_syr2k_lower(c, A, lda, n, t0, w.VZ, ldv))) return rc;
+  }
+
+  // ---- stage 2
+  band_extract_kernel<<<n, 128, 0, st>>>(A, lda, n, w.AB);
+  EB_CHECK_LAUNCH(c);
+  if (c->dbg_band_h) {   // testing aid: the band matrix before bulge chasing ([n][128], AB[col][d] = A[col+d][col])
+    EB_CUDA(cudaMemcpyAsync(c->dbg_band_h, w.AB, sizeof(double) * (size_t)n * 2 * BW, cudaMemcpyDeviceToHost, st));
+    EB_CUDA(cudaStreamSynchronize(st));
+  }
+  if (n > 2) {
+    int per_sm = 0;
+    EB_CUDA(cudaFuncSetAttribute(bulge_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BC_SMEM));
+    EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bulge_chase_kernel, BC_THREADS, BC_SMEM));
+    per_sm = std::max(1, std::min(per_sm, 3));
+    // sweeps run two blocks apart, so at most ~n/128 are ever active: idle CTAs would only add polling traffic
+    const int useful = n / (2 * BW) + 4;
+    const int grid = std::max(1, std::min(std::min(per_sm * c->num_sms, n - 2), useful));
+    double* ab = w.AB; int nn = n; int* prog = w.prog; int* err = w.err;
+    void* args[] = {&ab, &nn, &prog, &err};
+    if ((rc = coop_launch(c, (const void*)bulge_chase_kernel, dim3(grid), dim3(BC_THREADS), args, BC_SMEM))) return rc;
+  }
+  band_de_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.AB, n, d, e);
+  EB_CHECK_LAUNCH(c);
+  int herr = 0;
+  EB_CUDA(cudaMemcpyAsync(&herr, w.err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  EB_CUDA(cudaStreamSynchronize(st));
+  if (herr) { set_error("two_stage_tridiag: a device-side wait timed out (code %d: 1 = bulge-chase predecessor, 3 = panel grid barrier)", herr); return EB_ERR_NUMERIC; }
+  return 0;
+}
+
+// Leading nvec eigenpairs of the symmetric matrix A (n x n, lda; lower triangle + complete diagonal tiles valid, preserved).
+// theta_h[nvec] (unscaled), vec_d: device [nvec][n] unit vectors.
+int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* theta_h, double* vec_d, int* iters_out, int* matvecs_out) {
+  cudaStream_t st = c->stream;
+  int rc;
+  const int64_t ld = ((int64_t)n + 7) & ~7ll;
+  const int gch = gram_chunk(c, n);
+  const int nchunk = (n + gch - 1) / gch;
+  size_t off = 0;
+  auto take = [&](size_t cnt) { size_t o = off; off += (cnt + 15) & ~size_t(15); return o; };
+  size_t oY[5];
+  for (int i = 0; i < 5; i++) oY[i] = take((size_t)64 * ld);
+  const size_t oWp = take((size_t)MAX_KSPLIT * 64 * ld), oGp = take((size_t)nchunk * 4096), oZ = take(4096), oTh = take(64), oRes = take(64),
+               oErr = take(16);
+  if ((rc = c->chfsiw.ensure(off))) return rc;
+  double* W = c->chfsiw.p;
+  double* Y[5];
+  for (int i = 0; i < 5; i++) Y[i] = W + oY[i];
+  double *Wpart = W + oWp, *Gpart = W + oGp, *Zm = W + oZ, *theta_d = W + oTh, *res_d = W + oRes;
+  int* err_d = reinterpret_cast<int*>(W + oErr);
+  EB_CUDA(cudaMemsetAsync(err_d, 0, sizeof(int), st));
+  for (int i = 0; i < 5; i++) EB_CUDA(cudaMemsetAsync(Y[i], 0, sizeof(double) * 64 * ld, st));
+  constexpr int SM64x2 = 2 * 64 * 65 * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EB_CUDA(cudaFuncSetAttribute(left_mult_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    EB_CUDA(cudaFuncSetAttribute(jacobi64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM64x2));
+    EB_CUDA(cudaFuncSetAttribute(cholinv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM64x2));
+    attr_set = true;
+  }
+  const dim3 cgrid((n + 255) / 256, 64);
+  const int lm_grid = (n + 63) / 64;
+  int nmat = 0;
+
+  auto matvec = [&](const double* X, double* Out, double a1, const double* Y1, double a2, const double* Y0, double a3) -> int {
+    int ks = 1, r;
+    if ((r = launch_sym_skinny(c, A, lda, n, 0, X, ld, Wpart, ld, MAX_KSPLIT, &ks))) return r;
+    combine_kernel<<<cgrid, 256, 0, st>>>(Wpart, ks, ld, Out, ld, n, 0, 0, a1, Y1, a2, Y0, a3, ld);
+    EB_CHECK_LAUNCH(c);
+    nmat++;
+    return 0;
+  };
+  // X <- orthonormal basis of span(X) (shifted CholeskyQR, then two plain passes); result ends up in *X, *tmp is scratch
+  auto chol_qr = [&](double*& X, double*& tmp) -> int {
+    for (int pass = 0; pass < 3; pass++) {
+      gram64_kernel<<<nchunk, 256, 0, st>>>(X, ld, X, ld, 0, n, gch, Gpart);
+      EB_CHECK_LAUNCH(c);
+      const double shift = pass == 0 ? 11.0 * (64.0 * n + 64.0 * 65.0) * 1.1e-16 : 0.0;
+      cholinv64_kernel<<<1, 256, SM64x2, st>>>(Gpart, nchunk, shift, Zm, err_d);
+      EB_CHECK_LAUNCH(c);
+      left_mult_kernel<<<lm_grid, 256, 16384 * 8, st>>>(Zm, X, nullptr, nullptr, ld, tmp, ld, 0, n);
+      EB_CHECK_LAUNCH(c);
+      std::swap(X, tmp);
+    }
+    return 0;
+  };
+
+  double *V = Y[0], *AV = Y[1], *Ya = Y[2], *Yb = Y[3], *Yc = Y[4];
+  randinit_kernel<<<cgrid, 256, 0, st>>>(V, ld, n);
+  EB_CHECK_LAUNCH(c);
+  if ((rc = chol_qr(V, Ya))) return rc;
+
+  double th[64], res2[64];
+  const bool debug = getenv("EB_DEBUG") != nullptr;
+  const double tol = std::max(2e-14, 6e-16 * sqrt((double)n));
+  double prev_worst = 1e300, prev2_worst = 1e300;
+  double lo = 0.0;
+  int outer = 0;
+  bool converged = false;
+  const int maxouter = 80;
+  for (outer = 0; outer < maxouter; outer++) {
+    // Rayleigh-Ritz
+    if ((rc = matvec(V, AV, 1.0, nullptr, 0.0, nullptr, 0.0))) return rc;
+    gram64_kernel<<<nchunk, 256, 0, st>>>(V, ld, AV, ld, 0, n, gch, Gpart);
+    EB_CHECK_LAUNCH(c);
+    jacobi64_kernel<<<1, 256, SM64x2, st>>>(Gpart, nchunk, theta_d, Zm);
+    EB_CHECK_LAUNCH(c);
+    left_mult_kernel<<<lm_grid, 256, 16384 * 8, st>>>(Zm, V, nullptr, nullptr, ld, Ya, ld, 0, n);
+    EB_CHECK_LAUNCH(c);
+    left_mult_kernel<<<lm_grid, 256, 16384 * 8, st>>>(Zm, AV, nullptr, nullptr, ld, Yb, ld, 0, n);
+    EB_CHECK_LAUNCH(c);
+    std::swap(V, Ya); std::swap(AV, Yb);
+    resnorm_kernel<<<64, 256, 0, st>>>(AV, V, ld, n, theta_d, res_d);
+    EB_CHECK_LAUNCH(c);
+    EB_CUDA(cudaMemcpyAsync(th, theta_d, sizeof(double) * 64, cudaMemcpyDeviceToHost, st));
+    EB_CUDA(cudaMemcpyAsync(res2, res_d, sizeof(double) * 64, cudaMemcpyDeviceToHost, st));
+    EB_CUDA(cudaStreamSynchronize(st));
+    const double anorm = std::max(fabs(th[0]), fabs(th[63]));
+    double worst = 0.0;
+    for (int i = 0; i < nvec; i++) worst = std::max(worst, sqrt(res2[i]));
+    if (debug) fprintf(stderr, "[chfsi] outer %d matvecs %d theta0 %.6e theta_k %.6e cut %.6e worst_res/anorm %.3e\n", outer, nmat, th[0],
+                       th[std::max(nvec - 1, 0)], th[63], worst / anorm);
+    // converged: residual at the rounding floor of an n-term FP64 mat-vec, or stagnating just above it
+    if (!(anorm > 0.0) || worst <= tol * anorm) { converged = true; break; }
+    if (worst <= 1e-11 * anorm && worst > 0.5 * prev_worst && prev_worst > 0.5 * prev2_worst) { converged = true; break; }
+    prev2_worst = prev_worst; prev_worst = worst;
+    // Chebyshev filter damping [lo, cut]
+    const double cut = th[63];
+    lo = std::min(lo, cut);
+    double cc = 0.5 * (cut + lo), ee = 0.5 * (cut - lo);
+    if (!(ee > 0.0)) ee = 1e-3 * anorm;
+    const double xi1 = std::max((th[0] - cc) / ee, 1.0 + 1e-12);
+    int deg = (int)floor(acosh(1e8) / std::max(acosh(xi1), 1e-6));
+    deg = std::max(2, std::min(deg, 40));
+    double sigma1 = ee / (th[0] - cc), sigma = sigma1;
+    // Y1 = (A V - c V) sigma1/e   (A V is already in AV)
+    {
+      const double a1 = sigma1 / ee;
+      combine_kernel<<<cgrid, 256, 0, st>>>(AV, 1, ld, Ya, ld, n, 0, 0, a1, V, -cc * a1, nullptr, 0.0, ld);
+      EB_CHECK_LAUNCH(c);
+    }
+    double *y0 = V, *y1 = Ya, *y2 = Yb;          // AV and Yc are free scratch now
+    double* spare = AV;
+    for (int jd = 2; jd <= deg; jd++) {
+      const double sn = 1.0 / (2.0 / sigma1 - sigma);
+      const double a1 = 2.0 * sn / ee;
+      if ((rc = matvec(y1, y2, a1, y1, -cc * a1, y0, -sigma * sn))) return rc;
+      double* t = y0; y0 = y1; y1 = y2; y2 = (jd == 2) ? spare : t;
+      if (jd == 2) spare = t;                    // V's buffer joins the rotation after its last use
+      sigma = sn;
+    }
+    // orthonormalise the filtered block -> V
+    double* X = y1; double* tmp = Yc;
+    if ((rc = chol_qr(X, tmp))) return rc;
+    // re-assign buffer roles: V = X, the other four are scratch
+    double* all[5] = {Y[0], Y[1], Y[2], Y[3], Y[4]};
+    int k = 0; double* others[4];
+    for (int i = 0; i < 5; i++) if (all[i] != X) others[k++] = all[i];
+    V = X; AV = others[0]; Ya = others[1]; Yb = others[2]; Yc = others[3];
+  }
+  int herr = 0;
+  EB_CUDA(cudaMemcpyAsync(&herr, err_d, sizeof(int), cudaMemcpyDeviceToHost, st));
+  EB_CUDA(cudaStreamSynchronize(st));
+  if (herr) { set_error("chfsi_top: Cholesky breakdown in the block orthonormalisation"); return EB_ERR_NUMERIC; }
+  if (!converged) { set_error("chfsi_top: no convergence after %d outer iterations", maxouter); return EB_ERR_NUMERIC; }
+  normalize_rows_kernel<<<nvec, 256, 0, st>>>(V, ld, n);
+  EB_CHECK_LAUNCH(c);
+  EB_CUDA(cudaMemcpy2DAsync(vec_d, sizeof(double) * n, V, sizeof(double) * ld, sizeof(double) * n, nvec, cudaMemcpyDeviceToDevice, st));
+  for (int i = 0; i < nvec; i++) theta_h[i] = th[i];
+  if (iters_out) *iters_out = outer + 1;
+  if (matvecs_out) *matvecs_out = nmat;
+  return 0;
+}
+
+}  // namespace eb

@@ -413,9 +413,73 @@ __global__ void copy_matrix_kernel(const double* __restrict__ src, int64_t lds, 
 }
 
 // ------------------------------------------------------------------------------------------ host driver
+// all eigenvalues of the tridiagonal (d, e; scaled in place by `scale`) -> c->lambda_d descending
+static int tridiag_spectrum(eb_ctx* c, int n, double* d, double* e, double* e2, double* bounds, double scale) {
+  cudaStream_t st = c->stream;
+  scale_de_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, d, e, scale);
+  EB_CHECK_LAUNCH(c);
+  e2_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, e, e2);
+  EB_CHECK_LAUNCH(c);
+  tri_bounds_kernel<<<1, 1024, 0, st>>>(n, d, e, bounds);
+  EB_CHECK_LAUNCH(c);
+  tri_bisect_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, c->lambda_d.p);
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
+// large-n path: spectrum by two-stage tridiagonalisation (only if lambda_h), leading vectors by subspace iteration
+static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, double scale, int nvec, double* lambda_h, double* evecs_h) {
+  cudaStream_t st = c->stream;
+  int rc;
+  c->tm.tridiag_ms = c->tm.bisect_ms = c->tm.vectors_ms = 0.f;
+  c->tm.chfsi_iters = c->tm.chfsi_matvecs = 0;
+  if ((rc = c->lambda_d.ensure(n))) return rc;
+  if (lambda_h) {
+    const int64_t lda = ((int64_t)n + 15) & ~15ll;
+    if ((rc = c->eigA.ensure((size_t)lda * n))) return rc;
+    const size_t wn = (size_t)n * 4 + 64;
+    if ((rc = c->eigw.ensure(wn))) return rc;
+    double *d = c->eigw.p, *e = d + n, *e2 = e + n, *bounds = e2 + n;
+    EB_CUDA(cudaEventRecord(c->ev[5], st));
+    dim3 grid((n + 255) / 256, n);
+    copy_matrix_kernel<<<grid, 256, 0, st>>>(A_d, lda_in, c->eigA.p, lda, n);
+    EB_CHECK_LAUNCH(c);
+    if ((rc = two_stage_tridiag(c, c->eigA.p, lda, n, d, e))) return rc;
+    EB_CUDA(cudaEventRecord(c->ev[6], st));
+    if ((rc = tridiag_spectrum(c, n, d, e, e2, bounds, scale))) return rc;
+    EB_CUDA(cudaEventRecord(c->ev[7], st));
+    EB_CUDA(cudaMemcpyAsync(lambda_h, c->lambda_d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    EB_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c->tm.tridiag_ms, c->ev[5], c->ev[6]);
+    cudaEventElapsedTime(&c->tm.bisect_ms, c->ev[6], c->ev[7]);
+  }
+  if (nvec > 0) {
+    if ((rc = c->zvec_d.ensure((size_t)nvec * n))) return rc;
+    std::vector<double> th(nvec);
+    EB_CUDA(cudaEventRecord(c->ev[8], st));
+    if ((rc = chfsi_top(c, A_d, lda_in, n, nvec, th.data(), c->zvec_d.p, &c->tm.chfsi_iters, &c->tm.chfsi_matvecs))) return rc;
+    EB_CUDA(cudaEventRecord(c->ev[9], st));
+    if (evecs_h) EB_CUDA(cudaMemcpyAsync(evecs_h, c->zvec_d.p, sizeof(double) * (size_t)nvec * n, cudaMemcpyDeviceToHost, st));
+    EB_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&c->tm.vectors_ms, c->ev[8], c->ev[9]);
+    c->ritz.assign(th.begin(), th.end());
+    for (auto& v : c->ritz) v *= scale;
+  }
+  return 0;
+}
+
+bool eig_uses_two_stage(const eb_ctx* c, int n, int nvec) {
+  int method = c->opt_eig_method;
+  if (method == 0) method = n >= c->opt_two_stage_min ? 2 : 1;
+  return method == 2 && nvec <= 40 && n >= 256;      // block width 64 bounds the subspace iteration
+}
+
 int eig_resident(eb_ctx* c, const double* A_d, int64_t lda_in, int n, double scale, int nvec, double* lambda_h, double* evecs_h) {
   if (n <= 0) return 0;
   nvec = std::max(0, std::min(nvec, n));
+  const int method = (eig_uses_two_stage(c, n, nvec) && !(lda_in & 1)) ? 2 : 1;
+  c->tm.eig_method = method;
+  if (method == 2) return eig_two_stage(c, A_d, lda_in, n, scale, nvec, lambda_h, evecs_h);
   cudaStream_t st = c->stream;
   int rc;
   const int64_t lda = (n + 15) & ~15;
@@ -471,16 +535,8 @@ int eig_resident(eb_ctx* c, const double* A_d, int64_t lda_in, int n, double sca
   }
   tri_tail_scale_kernel<<<1, 32, 0, st>>>(A, lda, n, d, e, scale);
   EB_CHECK_LAUNCH(c);
-  scale_de_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, d, e, scale);
-  EB_CHECK_LAUNCH(c);
   EB_CUDA(cudaEventRecord(c->ev[6], st));
-
-  e2_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, e, e2);
-  EB_CHECK_LAUNCH(c);
-  tri_bounds_kernel<<<1, 1024, 0, st>>>(n, d, e, bounds);
-  EB_CHECK_LAUNCH(c);
-  tri_bisect_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, c->lambda_d.p);
-  EB_CHECK_LAUNCH(c);
+  if ((rc = tridiag_spectrum(c, n, d, e, e2, bounds, scale))) return rc;
   EB_CUDA(cudaEventRecord(c->ev[7], st));
   if (nvec > 0) {
     tri_invit_kernel<<<1, 1024, 0, st>>>(n, nvec, d, e, c->lambda_d.p, bounds, work, ipiv, c->zvec_d.p);

@@ -94,10 +94,20 @@ void *eb_grm_device_ptr (eb_ctx *, int64_t * ld_out, int64_t * n_out);
 int eb_grm_finish (eb_ctx *, double *y_out, double *XTX_host);
 
 /* -------- symmetric eigensolver on the resident GRM: eigvecs(), eigsubs.c:39-55 / dspev_, eigx.c:107 --------
- * lambda[nrows] descending (all eigenvalues of XTX/y); evecs[nvec*nrows], row i = unit eigenvector i. */
+ * lambda[nrows] descending (all eigenvalues of XTX/y); evecs[nvec*nrows], row i = unit eigenvector i.
+ * lambda may be NULL (leading vectors only: what the outlier iterations need, smartpca.c:1250) and nvec may be 0
+ * (spectrum only). */
 int eb_eig (eb_ctx *, int nvec, double *lambda, double *evecs);
 /* standalone drop-in with the reference's contract (mat row-major n*n, preserved): include/eigsubs.h:6-7 */
 int eb_eigvecs (eb_ctx *, const double *mat, double *evals, double *evecs, int n, int nvec);
+
+/* eigensolver selection: key "eig_method" = 0 auto | 1 one-stage | 2 two-stage + subspace iteration;
+ * "two_stage_min" = n at which auto switches to 2.  Returns EB_ERR_ARG for an unknown key. */
+int eb_set_option (eb_ctx *, const char *key, int value);
+
+/* testing aid: two-stage tridiagonalisation alone.  d[n], e[n] of the similar tridiagonal (unscaled); band (may be
+ * NULL) receives the intermediate band matrix, [n][128] with band[col][k] = B[col+k][col], k <= 64. */
+int eb_debug_tridiag (eb_ctx *, const double *mat, int n, double *d, double *e, double *band);
 
 /* -------- outlier detection: ridoutlier(), smartsubs.c:18-93 (decisions bit-exact) -------- */
 int eb_ridoutlier (const double *evecs, int n, int neigs, double thresh, int outliermode,
@@ -141,7 +151,12 @@ int eb_project (eb_ctx *, const double *evecs, int numeigs, double *ffvecs /* [n
 
 /* -------- measurement helpers -------- */
 /* last pass timings measured with CUDA events on the library's stream (milliseconds) */
-typedef struct { float gather_ms, stats_ms, grm_ms, finalize_ms, tridiag_ms, bisect_ms, vectors_ms; int grm_launches; int nsplit; } eb_timings;
+typedef struct {
+  float gather_ms, stats_ms, grm_ms, finalize_ms, tridiag_ms, bisect_ms, vectors_ms;
+  int grm_launches; int nsplit;
+  int eig_method;               /* 1 = one-stage Householder, 2 = two-stage (band) + subspace iteration */
+  int chfsi_iters, chfsi_matvecs;
+} eb_timings;
 int eb_get_timings (eb_ctx *, eb_timings * t);
 /* FP64 DMMA / DFMA issue-rate microbenchmarks (TFLOP/s) used as roofline cross-checks */
 int eb_microbench_fp64 (eb_ctx *, double *dmma_tflops, double *dfma_tflops);

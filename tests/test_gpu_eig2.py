@@ -1,0 +1,149 @@
+"""GPU parity for the large-n eigensolver (eig_b200/csrc/eig2_*.cu): two-stage tridiagonalisation (dense -> band -> tridiagonal)
+for the spectrum, Chebyshev-filtered subspace iteration for the leading vectors -- against LAPACK (numpy/scipy), the port and
+the compiled reference's eigvecs() -> dspev_ (eigsubs.c:39-55, eigx.c:97-117)."""
+import numpy as np
+import pytest
+import scipy.linalg as sl
+
+from eig_b200 import synth
+from oracle import bindings as ob
+
+pytestmark = pytest.mark.gpu
+
+EVAL_RTOL = 1e-9      # north_star: eigenvalues within 1e-9 relative (absolute floor 1e-6 * lambda_max, statsubs.c:1729)
+COS_TOL = 1e-9
+
+
+def _spd(n, seed, npops=4, delta=0.3):
+    rs = np.random.RandomState(seed)
+    M = 3 * n
+    X = rs.randn(n, M)
+    if npops > 1:
+        X += delta * rs.randn(npops, M)[rs.randint(0, npops, n)]
+    return X @ X.T / M
+
+
+def _eval_check(lam, ref):
+    scale = np.abs(ref).max()
+    big = np.abs(ref) > 1e-6 * scale
+    assert (np.abs(lam[big] - ref[big]) / np.abs(ref[big])).max() <= EVAL_RTOL
+    assert np.abs(lam[~big] - ref[~big]).max(initial=0.0) <= EVAL_RTOL * scale
+
+
+@pytest.fixture()
+def ctx2(ctx):
+    ctx.set_option("eig_method", 2)
+    yield ctx
+    ctx.set_option("eig_method", 0)
+
+
+@pytest.mark.parametrize("n", [259, 320, 449, 1000, 1537])
+def test_two_stage_tridiagonal_is_similar(ctx, n):
+    """band matrix after stage 1 and tridiagonal after stage 2 keep the spectrum (ragged last panels / blocks included)"""
+    A = _spd(n, n)
+    w = np.linalg.eigvalsh(A)[::-1]
+    d, e, band = ctx.debug_tridiag(A)
+    ab = np.zeros((65, n))
+    for k in range(65):
+        ab[k, :n - k] = band[:n - k, k]
+    assert np.abs(band[:, 65:]).max() == 0.0
+    _eval_check(sl.eigvals_banded(ab, lower=True)[::-1], w)
+    _eval_check(sl.eigvalsh_tridiagonal(d, e)[::-1], w)
+    assert abs(d.sum() - np.trace(A)) <= 1e-12 * np.trace(A)
+
+
+@pytest.mark.parametrize("n,npops", [(700, 4), (1537, 1), (2050, 6)])
+def test_eigvecs_two_stage_vs_lapack(ctx2, n, npops):
+    A = _spd(n, 7 + n, npops=npops)
+    lam, vec = ctx2.eigvecs(A, nvec=10)
+    assert ctx2.timings()["eig_method"] == 2
+    w, v = np.linalg.eigh(A)
+    w = w[::-1]; v = v[:, ::-1].T
+    _eval_check(lam, w)
+    for i in range(10):
+        gap = min(w[i - 1] - w[i] if i else np.inf, w[i] - w[i + 1])
+        assert np.linalg.norm(A @ vec[i] - lam[i] * vec[i]) <= 2e-13 * w[0]
+        assert abs(np.linalg.norm(vec[i]) - 1.0) < 1e-12
+        if gap > 1e-4 * w[0]:
+            assert abs(abs(float(vec[i] @ v[i])) - 1.0) <= COS_TOL, (i, gap)
+
+
+def test_eigvecs_two_stage_degenerate(ctx2):
+    """rank-deficient input (zero panels in the band reduction, zero Ritz values below the cut)"""
+    n = 600
+    rs = np.random.RandomState(3)
+    X = rs.randn(n, 40)
+    A = X @ X.T / 40
+    lam, vec = ctx2.eigvecs(A, nvec=5)
+    w = np.linalg.eigvalsh(A)[::-1]
+    assert np.abs(lam - w).max() <= 1e-12 * w[0]
+    for i in range(5):
+        assert np.linalg.norm(A @ vec[i] - lam[i] * vec[i]) <= 2e-13 * w[0]
+
+
+def test_vectors_only_and_spectrum_only(ctx2):
+    nsnp, nind = 5000, 600
+    P = synth.pack(synth.genotypes(5, nsnp, nind, missing=0.03, npops=4, delta=0.3))
+    ctx2.upload_packed(P, nind); ctx2.set_rows(None)
+    r = ctx2.grm(want_xtx=True)
+    lam, vec = ctx2.eig(6)
+    _, vec2 = ctx2.eig(6, want_lambda=False)
+    lam3, _ = ctx2.eig(0)
+    assert np.array_equal(lam, lam3)
+    assert np.abs(np.abs(np.sum(vec * vec2, axis=1)) - 1).max() < 1e-12
+    o = ob.port_grm(P, nind); rl, rv = ob.port_eigvecs(o["XTX"] / o["y"])
+    _eval_check(lam, rl)
+    for i in range(3):
+        assert abs(abs(float(vec[i] @ rv[i])) - 1.0) <= COS_TOL
+
+
+def test_grm_eig_two_stage_vs_reference(ctx2):
+    nsnp, nind = 8000, 640
+    g = synth.genotypes(22, nsnp, nind, missing=0.05, npops=5, delta=0.25)
+    P = synth.pack(g)
+    ctx2.upload_packed(P, nind); ctx2.set_rows(None)
+    ctx2.grm()
+    lam, vec = ctx2.eig(10)
+    assert ctx2.timings()["eig_method"] == 2
+    if ob.ref() is not None:
+        o = ob.ref_grm(P, nind); rl, rv = ob.ref_eigvecs(o["XTX"] / o["y"])
+    else:
+        o = ob.port_grm(P, nind); rl, rv = ob.port_eigvecs(o["XTX"] / o["y"])
+    _eval_check(lam, rl)
+    for i in range(4):
+        assert abs(abs(float(vec[i] @ rv[i])) - 1.0) <= COS_TOL
+
+
+def test_pca_full_outlier_loop_two_stage(ctx2):
+    """same planted-outlier scenario as test_gpu_eig.py, through the vectors-only passes + final spectrum"""
+    nsnp, nind = 5000, 300
+    pd = np.array([0.05] * 3 + [1.5])
+    g = synth.genotypes(4, nsnp, nind, missing=0.02, npops=4, pop_delta=pd)
+    pop = synth.pop_of(nind, 4)
+    g0 = synth.genotypes(4, nsnp, nind, missing=0.02, npops=4, pop_delta=np.array([0.05, 0.05, 0.05, 0.05]))
+    sel = (pop == 3) & (np.arange(nind) < 298)
+    g[:, sel] = g0[:, sel]
+    P = synth.pack(g)
+    ctx2.upload_packed(P, nind)
+    res = ctx2.pca_full(numeigs=5, numoutliter=5, numoutleigs=5, outlthresh=6.0)
+    assert ctx2.timings()["eig_method"] == 2
+    xi = np.arange(nind, dtype=np.int32); removed = []
+    ignore = np.zeros(nsnp, bool)
+    for it in range(1, 7):
+        Pk = P[~ignore]
+        o = ob.port_grm(Pk, nind, xindex=xi)
+        idx = np.flatnonzero(~ignore); ignore[idx[o["used"] == 0]] = True
+        lam, vec = ob.port_eigvecs(o["XTX"] / o["y"])
+        if it > 5:
+            break
+        bad, vecno, score = ob.port_ridoutlier(vec[:5], 5, 6.0, 0)
+        if len(bad) == 0:
+            break
+        removed += [(int(xi[j]), it, int(vecno[j])) for j in bad]
+        xi = np.delete(xi, bad)
+    assert len(removed) > 0
+    assert [(int(a), int(b), int(c)) for a, b, c in zip(res["removed_index"], res["removed_iter"], res["removed_vecno"])] == removed
+    assert np.array_equal(res["xindex"], xi)
+    _eval_check(res["lambda_"], lam)
+    for i in range(2):
+        assert abs(abs(res["evecs"][i] @ vec[i]) - 1) < 1e-9
