@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
     for s in SRCS:
         o = os.path.join(objdir, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        cmd = [NVCC] + FLAGS + os.environ.get("EB_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     ok = True
     for s, p in procs:

@@ -181,24 +181,44 @@ syr2k_lower_kernel(const __grid_constant__ CUtensorMap mapVZ_km, const __grid_co
       if (lane == 0) dt_mbar_arrive(sm.empty + stage);
       if (++stage == DT_STAGES) { stage = 0; phase ^= 1; }
     }
+    // read-modify-write of the 128 x 64 tile in batches of two row blocks: 8 independent 16-byte loads in flight per
+    // thread before the first dependent store (a one-at-a-time RMW would serialise 32 global round trips)
+    const bool interior = (I + 1) * DT_M <= n && (J64 + 1) * DT_N <= n;
 #pragma unroll
-    for (int t = 0; t < 8; t++) {
-      const int row = I * DT_M + wm * 64 + t * 8 + g;
+    for (int t2 = 0; t2 < 8; t2 += 2) {
+      if (interior) {
+        double2 v[2][4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int col = J64 * DT_N + wn * 32 + u * 8 + q * 2;
-        if (row < n && col < n) {
-          double* p = A + (size_t)row * lda + col;
-          if (col + 1 < n) {
-            double2 v = *reinterpret_cast<double2*>(p);
-            v.x -= acc[t][u][0]; v.y -= acc[t][u][1];
-            *reinterpret_cast<double2*>(p) = v;
-          } else {
-            p[0] -= acc[t][u][0];
+        for (int tt = 0; tt < 2; tt++)
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            v[tt][u] = __ldcg(reinterpret_cast<const double2*>(A + (size_t)(I * DT_M + wm * 64 + (t2 + tt) * 8 + g) * lda + J64 * DT_N + wn * 32 + u * 8 + q * 2));
+#pragma unroll
+        for (int tt = 0; tt < 2; tt++)
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            v[tt][u].x -= acc[t2 + tt][u][0]; v[tt][u].y -= acc[t2 + tt][u][1];
+            *reinterpret_cast<double2*>(A + (size_t)(I * DT_M + wm * 64 + (t2 + tt) * 8 + g) * lda + J64 * DT_N + wn * 32 + u * 8 + q * 2) = v[tt][u];
+          }
+      } else {
+#pragma unroll
+        for (int tt = 0; tt < 2; tt++) {
+          const int row = I * DT_M + wm * 64 + (t2 + tt) * 8 + g;
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int col = J64 * DT_N + wn * 32 + u * 8 + q * 2;
+            if (row < n && col < n) {
+              double* p = A + (size_t)row * lda + col;
+              p[0] -= acc[t2 + tt][u][0];
+              if (col + 1 < n) p[1] -= acc[t2 + tt][u][1];
+            }
           }
         }
-        acc[t][u][0] = acc[t][u][1] = 0.0;
       }
+#pragma unroll
+      for (int tt = 0; tt < 2; tt++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[t2 + tt][u][0] = acc[t2 + tt][u][1] = 0.0;
     }
   }
 }

@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "dmma_tile.cuh"
 
@@ -351,17 +352,17 @@ __global__ void band_de_kernel(const double* __restrict__ AB, int n, double* __r
 constexpr int BC_THREADS = 256;
 constexpr int BC_LD = 65;
 constexpr int BC_DONE = 0x3fffffff;
-constexpr int BC_SMEM = (2 * 64 * BC_LD + 64 * 5 + 256) * 8;
+constexpr int BC_SMEM = (2 * 64 * BC_LD + 64 * 8 + 256 * 3 + 8) * 8;
 
 struct HouseSh { double tau, beta; };
 
-// reflector from x[0..len) held in xs (shared): leaves v in vs (v[0] = 1), returns tau/beta through hs.  warp 0 only.
+// reflector from x[0..len) held in xs (shared): leaves v in vs (v[0] = 1, zero beyond len), tau/beta in hs.  warp 0 only.
 __device__ __forceinline__ void bc_make_reflector(const double* xs, int len, double* vs, HouseSh* hs, int lane) {
-  double s = 0.0;
-  for (int i = 1 + lane; i < len; i += 32) s += xs[i] * xs[i];
+  const double x0 = xs[lane], x1 = xs[lane + 32];
+  double s = (lane >= 1 && lane < len ? x0 * x0 : 0.0) + (lane + 32 < len ? x1 * x1 : 0.0);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const double alpha = xs[0];
+  const double alpha = __shfl_sync(0xffffffffu, x0, 0);
   double tau = 0.0, beta = alpha, scal = 0.0;
   if (s != 0.0) {
     const double nrm = sqrt(alpha * alpha + s);
@@ -369,52 +370,45 @@ __device__ __forceinline__ void bc_make_reflector(const double* xs, int len, dou
     tau = (beta - alpha) / beta;
     scal = 1.0 / (alpha - beta);
   }
-  __syncwarp();
-  for (int i = lane; i < 64; i += 32) vs[i] = i == 0 ? 1.0 : (i < len ? xs[i] * scal : 0.0);
+  vs[lane] = lane == 0 ? 1.0 : (lane < len ? x0 * scal : 0.0);
+  vs[lane + 32] = lane + 32 < len ? x1 * scal : 0.0;
   if (lane == 0) { hs->tau = tau; hs->beta = beta; }
 }
 
-// D (len x len symmetric, full in shared, ld BC_LD, D[c][i]) <- H D H with H = I - tau v v^T
-__device__ __forceinline__ void bc_two_sided(double* Ds, int len, const double* vs, double tau, double* red, double* ps, double* ws,
-                                             int tid) {
-  const int i = tid & 63, part = tid >> 6;
-  double acc = 0.0;
-  if (i < len)
-    for (int cc = part * 16; cc < part * 16 + 16; cc++) acc += Ds[cc * BC_LD + i] * vs[cc];   // vs is zero beyond len, Ds too
-  red[part * 64 + i] = acc;
-  __syncthreads();
-  if (tid < 64) ps[tid] = tau * (red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid]);
-  __syncthreads();
-  if (tid < 32) {
-    double s = ps[tid] * vs[tid] + ps[tid + 32] * vs[tid + 32];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const double al = -0.5 * tau * s;
-    ws[tid] = ps[tid] + al * vs[tid];
-    ws[tid + 32] = ps[tid + 32] + al * vs[tid + 32];
-  }
-  __syncthreads();
-  if (i < len) {
-    const double vi = vs[i], wi = ws[i];
-    for (int cc = part * 16; cc < part * 16 + 16; cc++) Ds[cc * BC_LD + i] -= vi * ws[cc] + wi * vs[cc];
-  }
-  __syncthreads();
-}
+#ifdef EB_BC_PROFILE
+__device__ unsigned long long g_bc_prof[8];
+#define BC_TICK(slot) do { if (tid == 0 && blockIdx.x == 1) { const long long t_ = clock64(); g_bc_prof[slot] += t_ - t_prev; t_prev = t_; } } while (0)
+#else
+#define BC_TICK(slot) do { } while (0)
+#endif
 
-__global__ void __launch_bounds__(BC_THREADS) bulge_chase_kernel(double* __restrict__ AB, int n, int* __restrict__ prog, int* __restrict__ err) {
+// One CTA per sweep (column s of the band is reduced to tridiagonal form and its bulge chased off the end); sweep s may
+// run block k once sweep s-1 has finished block k+1.  Thread (i = tid & 63, part = tid >> 6) owns row i, columns
+// part*16 .. part*16+15 of the current 64 x 64 off-diagonal block B and diagonal block D in REGISTERS (one L2 round trip
+// per step); shared memory holds the copies the cross-thread reductions need.  Per step: B <- H2 (B H1) fused into one
+// update (w = tau1 B v1 gives column 0 of B H1, hence H2, before B is touched), D <- H2 D H2.
+__global__ void __launch_bounds__(BC_THREADS, 2) bulge_chase_kernel(double* __restrict__ AB, int n, int* __restrict__ prog, int* __restrict__ err) {
+#ifdef EB_BC_PROFILE
+  long long t_prev = clock64();
+#endif
   extern __shared__ __align__(16) double bcs[];
-  double* Bs = bcs;                       // [64][BC_LD]
-  double* Ds = bcs + 64 * BC_LD;          // [64][BC_LD]
-  double* v1 = Ds + 64 * BC_LD;
-  double* v2 = v1 + 64;
-  double* xs = v2 + 64;
-  double* red = xs + 64;                  // [256]
-  double* ps = red + 256;
-  double* ws = ps + 64;
-  __shared__ HouseSh hs_s;
+  double* Bs = bcs;                       // [64][BC_LD]  Bs[c][i]
+  double* Ds = bcs + 64 * BC_LD;          // [64][BC_LD]  full symmetric
+  double* va = Ds + 64 * BC_LD;           // reflector ping
+  double* vb = va + 64;                   // reflector pong
+  double* xs = vb + 64;
+  double* wv = xs + 64;                   // tau1 * B v1
+  double* us = wv + 64;                   // u[c]
+  double* ps = us + 64;                   // p[i]
+  double* w2 = ps + 64;                   // two-sided w
+  double* spare = w2 + 64;
+  double* red = spare + 64;               // [256]
+  double* redU = red + 256;               // [256]
+  double* redP = redU + 256;              // [256]
+  double* red2 = redP + 256;              // [4]
+  __shared__ HouseSh hs;
   __shared__ int abort_flag;
-  HouseSh& hs = hs_s;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, i = tid & 63, part = tid >> 6;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, i = tid & 63, part = tid >> 6, c0 = part * 16;
   constexpr int LDAB = 2 * BW;
   if (tid == 0) abort_flag = 0;
   __syncthreads();
@@ -436,19 +430,30 @@ __global__ void __launch_bounds__(BC_THREADS) bulge_chase_kernel(double* __restr
     __syncthreads();                       // every thread's band stores precede the barrier ...
     if (tid == 0) { __threadfence(); st_release(prog + s, val); }   // ... and are published cumulatively by one fence + release
   };
+  // two-sided update pieces shared by block 0 and the chase steps (D rows held in dreg; v, tau given)
+  double breg[16], dreg[16];
 
   for (int s = blockIdx.x; s < n - 2; s += gridDim.x) {
-    // ---- block 0: annihilate column s below the sub-diagonal
+    // ---------------------------------------------------------------- block 0: annihilate column s below the sub-diagonal
     wait_for(s - 1, 2);
     if (abort_flag) return;
     int r0 = s + 1, la = min(BW, n - r0);
-    if (tid < 64) xs[tid] = tid < la ? __ldcg(&AB[(size_t)s * LDAB + 1 + tid]) : 0.0;
-    // diagonal block rows/cols r0..r0+la-1 -> full symmetric in Ds[c][i]
-    for (int cc = part; cc < 64; cc += 4) {
-      if (i >= cc) {
-        const double v = (cc < la && i < la) ? __ldcg(&AB[(size_t)(r0 + cc) * LDAB + (i - cc)]) : 0.0;
-        Ds[cc * BC_LD + i] = v;
-        Ds[i * BC_LD + cc] = v;
+    double* v1 = va; double* v2 = vb;
+    {
+      const double x = (tid < 64 && tid < la) ? __ldcg(&AB[(size_t)s * LDAB + 1 + tid]) : 0.0;
+#pragma unroll
+      for (int it = 0; it < 16; it++) {
+        const int cc = c0 + it;
+        const bool okd = i >= cc && i < la;
+        const double td = __ldcg(&AB[okd ? (size_t)(r0 + cc) * LDAB + (i - cc) : (size_t)r0 * LDAB]);
+        dreg[it] = okd ? td : 0.0;
+      }
+      asm volatile("" ::: "memory");
+      if (tid < 64) xs[tid] = x;
+#pragma unroll
+      for (int it = 0; it < 16; it++) {
+        const int cc = c0 + it;
+        if (i >= cc) { Ds[cc * BC_LD + i] = dreg[it]; Ds[i * BC_LD + cc] = dreg[it]; }
       }
     }
     __syncthreads();
@@ -456,68 +461,131 @@ __global__ void __launch_bounds__(BC_THREADS) bulge_chase_kernel(double* __restr
     __syncthreads();
     double tau = hs.tau;
     if (tid < la) __stcg(&AB[(size_t)s * LDAB + 1 + tid], tid == 0 ? hs.beta : 0.0);
-    bc_two_sided(Ds, la, v1, tau, red, ps, ws, tid);
-    for (int cc = part; cc < la; cc += 4)
-      if (i >= cc && i < la) __stcg(&AB[(size_t)(r0 + cc) * LDAB + (i - cc)], Ds[cc * BC_LD + i]);
+    {
+      double pr = 0.0;
+#pragma unroll
+      for (int it = 0; it < 16; it++) { dreg[it] = Ds[(c0 + it) * BC_LD + i]; pr += dreg[it] * v1[c0 + it]; }
+      redP[part * 64 + i] = pr;
+      __syncthreads();
+      if (tid < 64) ps[tid] = tau * (redP[tid] + redP[64 + tid] + redP[128 + tid] + redP[192 + tid]);
+      __syncthreads();
+      if (warp == 0) {
+        double sv = ps[lane] * v1[lane] + ps[lane + 32] * v1[lane + 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        const double al = -0.5 * tau * sv;
+        w2[lane] = ps[lane] + al * v1[lane];
+        w2[lane + 32] = ps[lane + 32] + al * v1[lane + 32];
+      }
+      __syncthreads();
+      const double vi = v1[i], wi = w2[i];
+#pragma unroll
+      for (int it = 0; it < 16; it++) {
+        const int cc = c0 + it;
+        if (i >= cc && i < la) __stcg(&AB[(size_t)(r0 + cc) * LDAB + (i - cc)], dreg[it] - (vi * w2[cc] + wi * v1[cc]));
+      }
+    }
     publish(s, 1);
 
-    // ---- chase the bulge down the band
-    double* vprev = v1; double* vnext = v2;
+    // ---------------------------------------------------------------- chase the bulge down the band
     for (int k = 1;; k++) {
       const int r1 = r0 + la;
       const int lb = min(BW, n - r1);
       if (lb <= 0) break;
+      BC_TICK(0);
       wait_for(s - 1, k + 2);
       if (abort_flag) return;
-      // B: rows r1..r1+lb-1, cols r0..r0+la-1  -> Bs[c][i];  D: rows/cols r1..r1+lb-1
-      for (int cc = part; cc < 64; cc += 4) {
-        double vb = 0.0;
-        if (cc < la && i < lb) vb = __ldcg(&AB[(size_t)(r0 + cc) * LDAB + (la + i - cc)]);
-        Bs[cc * BC_LD + i] = vb;
-        if (i >= cc) {
-          const double vd = (cc < lb && i < lb) ? __ldcg(&AB[(size_t)(r1 + cc) * LDAB + (i - cc)]) : 0.0;
-          Ds[cc * BC_LD + i] = vd;
-          Ds[i * BC_LD + cc] = vd;
+      BC_TICK(1);
+      // B: rows r1..r1+lb-1, cols r0..r0+la-1 ;  D: rows/cols r1..r1+lb-1 (lower part loaded, mirrored through shared memory)
+#pragma unroll
+      for (int it = 0; it < 16; it++) {
+        const int cc = c0 + it;
+        // unconditional loads from a clamped (always valid) address + select: straight-line code, all 32 loads in flight
+        const bool okb = cc < la && i < lb, okd = i >= cc && i < lb;
+        const double tb = __ldcg(&AB[okb ? (size_t)(r0 + cc) * LDAB + (la + i - cc) : (size_t)r0 * LDAB]);
+        const double td = __ldcg(&AB[okd ? (size_t)(r1 + cc) * LDAB + (i - cc) : (size_t)r0 * LDAB]);
+        breg[it] = okb ? tb : 0.0;
+        dreg[it] = okd ? td : 0.0;
+      }
+      asm volatile("" ::: "memory");      // all 32 loads are issued before the first use (one L2 round trip, not 32)
+      BC_TICK(2);
+      {
+        double acc = 0.0;
+#pragma unroll
+        for (int it = 0; it < 16; it++) {
+          const int cc = c0 + it;
+          Bs[cc * BC_LD + i] = breg[it];
+          if (i >= cc) { Ds[cc * BC_LD + i] = dreg[it]; Ds[i * BC_LD + cc] = dreg[it]; }
+          acc += breg[it] * v1[cc];
+        }
+        red[part * 64 + i] = acc;
+      }
+      BC_TICK(3);
+      __syncthreads();                                                       // (1)
+      BC_TICK(4);
+      if (tid < 64) {
+        const double w = tau * (red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid]);
+        wv[tid] = w;
+        xs[tid] = Bs[tid] - w;                                               // column 0 of B H1 (v1[0] = 1)
+      }
+      __syncthreads();                                                       // (2)
+      if (warp == 0) bc_make_reflector(xs, lb, v2, &hs, lane);
+      __syncthreads();                                                       // (3)
+      const double tau2 = hs.tau;
+      {
+        // u_raw[c = i] over rows c0..c0+15, gamma = v2 . wv, p_raw[i] over columns c0..c0+15
+        double ur = 0.0, gp = 0.0, pr = 0.0;
+#pragma unroll
+        for (int it = 0; it < 16; it++) {
+          const int r = c0 + it;
+          const double v2r = v2[r];
+          ur += v2r * Bs[i * BC_LD + r];
+          gp += v2r * wv[r];
+          dreg[it] = Ds[r * BC_LD + i];
+          pr += dreg[it] * v2r;
+        }
+        redU[part * 64 + i] = ur;
+        redP[part * 64 + i] = pr;
+        if (i == 0) red2[part] = gp;
+      }
+      __syncthreads();                                                       // (4)
+      if (tid < 64) {
+        const double gamma = red2[0] + red2[1] + red2[2] + red2[3];
+        us[tid] = tau2 * ((redU[tid] + redU[64 + tid] + redU[128 + tid] + redU[192 + tid]) - gamma * v1[tid]);
+      } else if (tid < 128) {
+        const int j = tid - 64;
+        ps[j] = tau2 * (redP[j] + redP[64 + j] + redP[128 + j] + redP[192 + j]);
+      }
+      __syncthreads();                                                       // (5)
+      if (warp == 0) {
+        double sv = ps[lane] * v2[lane] + ps[lane + 32] * v2[lane + 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        const double al = -0.5 * tau2 * sv;
+        w2[lane] = ps[lane] + al * v2[lane];
+        w2[lane + 32] = ps[lane + 32] + al * v2[lane + 32];
+      }
+      __syncthreads();                                                       // (6)
+      BC_TICK(5);
+      {
+        const double wvi = wv[i], v2i = v2[i], w2i = w2[i];
+        const double beta2 = hs.beta;
+#pragma unroll
+        for (int it = 0; it < 16; it++) {
+          const int cc = c0 + it;
+          double bn = breg[it] - (wvi * v1[cc] + v2i * us[cc]);
+          if (cc == 0) bn = i == 0 ? beta2 : 0.0;                            // column 0 is (beta, 0, ..., 0)
+          if (cc < la && i < lb) __stcg(&AB[(size_t)(r0 + cc) * LDAB + (la + i - cc)], bn);
+          if (i >= cc && i < lb) __stcg(&AB[(size_t)(r1 + cc) * LDAB + (i - cc)], dreg[it] - (v2i * w2[cc] + w2i * v2[cc]));
         }
       }
-      __syncthreads();
-      // right-apply previous reflector: B <- B (I - tau v v^T)
-      {
-        double acc = 0.0;
-        for (int cc = part * 16; cc < part * 16 + 16; cc++) acc += Bs[cc * BC_LD + i] * vprev[cc];
-        red[part * 64 + i] = acc;
-        __syncthreads();
-        const double wi = tau * (red[i] + red[64 + i] + red[128 + i] + red[192 + i]);
-        for (int cc = part * 16; cc < part * 16 + 16; cc++) Bs[cc * BC_LD + i] -= wi * vprev[cc];
-        __syncthreads();
-      }
-      // new reflector from column 0 of B
-      if (tid < 64) xs[tid] = Bs[tid];
-      __syncthreads();
-      if (warp == 0) bc_make_reflector(xs, lb, vnext, &hs, lane);
-      __syncthreads();
-      const double tau2 = hs.tau;
-      // left-apply: B <- (I - tau2 v2 v2^T) B ; thread (c = i, part over rows)
-      {
-        double acc = 0.0;
-        for (int r = part * 16; r < part * 16 + 16; r++) acc += vnext[r] * Bs[i * BC_LD + r];
-        red[part * 64 + i] = acc;
-        __syncthreads();
-        if (tid < 64) ps[tid] = tau2 * (red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid]);   // u[c]
-        __syncthreads();
-        const double vi = vnext[i];
-        for (int cc = part * 16; cc < part * 16 + 16; cc++) Bs[cc * BC_LD + i] -= vi * ps[cc];
-        __syncthreads();
-      }
-      if (tid < 64) Bs[tid] = tid == 0 ? hs.beta : 0.0;           // column 0 is (beta, 0, ..., 0)
-      bc_two_sided(Ds, lb, vnext, tau2, red, ps, ws, tid);         // (starts with a barrier-protected phase; Bs col 0 write is ordered by its syncs)
-      for (int cc = part; cc < 64; cc += 4) {
-        if (cc < la && i < lb) __stcg(&AB[(size_t)(r0 + cc) * LDAB + (la + i - cc)], Bs[cc * BC_LD + i]);
-        if (cc < lb && i >= cc && i < lb) __stcg(&AB[(size_t)(r1 + cc) * LDAB + (i - cc)], Ds[cc * BC_LD + i]);
-      }
-      publish(s, k + 1);
+      publish(s, k + 1);                                                     // (7)
+      BC_TICK(6);
+#ifdef EB_BC_PROFILE
+      if (tid == 0 && blockIdx.x == 1) g_bc_prof[7] += 1;
+#endif
       r0 = r1; la = lb; tau = tau2;
-      double* t = vprev; vprev = vnext; vnext = t;
+      double* t = v1; v1 = v2; v2 = t;
     }
     publish(s, BC_DONE);
   }
@@ -806,6 +874,18 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
     void* args[] = {&ab, &nn, &prog, &err};
     if ((rc = coop_launch(c, (const void*)bulge_chase_kernel, dim3(grid), dim3(BC_THREADS), args, BC_SMEM))) return rc;
   }
+#ifdef EB_BC_PROFILE
+  {
+    unsigned long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_bc_prof, sizeof(h));
+    const double k = h[7] ? (double)h[7] : 1.0;
+    fprintf(stderr, "[bc profile] steps %llu cycles/step: other %.0f wait %.0f load-issue %.0f load-done+smem %.0f sync1 %.0f compute %.0f store+publish %.0f\n", h[7],
+            h[0] / k, h[1] / k, h[2] / k, h[3] / k, h[4] / k, h[5] / k, h[6] / k);
+    memset(h, 0, sizeof(h));
+    cudaMemcpyToSymbol(g_bc_prof, h, sizeof(h));
+  }
+#endif
   band_de_kernel<<<(n + 255) / 256, 256, 0, st>>>(w.AB, n, d, e);
   EB_CHECK_LAUNCH(c);
   int herr = 0;
