@@ -45,7 +45,7 @@ EXPORTS = [
     "eb_reset_launch_count", "eb_upload_packed", "eb_upload_packed_rows", "eb_adopt_packed_device", "eb_synth_packed_device",
     "eb_set_rows", "eb_snp_counts", "eb_indiv_valid_counts", "eb_grm", "eb_grm_partial", "eb_grm_device_ptr", "eb_grm_finish",
     "eb_eig", "eb_eigvecs", "eb_ridoutlier", "eb_pca_full", "eb_fpca", "eb_gauss_matrix", "eb_project", "eb_get_timings",
-    "eb_microbench_fp64", "eb_set_option", "eb_debug_tridiag",
+    "eb_microbench_fp64", "eb_set_option", "eb_debug_tridiag", "eb_lsqproj", "eb_evec_coords",
 ]
 
 _lib = None
@@ -245,6 +245,23 @@ class Context:
         ff = np.empty((k, self.nsnp)); fx = np.empty((k, self.nrows)); sc = np.empty(k)
         _chk(lib().eb_project(self.h, _p(evecs), C.c_int(k), _p(ff), _p(fx), _p(sc)))
         return ff, fx, sc
+
+    def lsqproj(self, ffvecs, fxscal, indiv=None):
+        ffvecs = np.ascontiguousarray(ffvecs, np.float64); k = ffvecs.shape[0]
+        fxscal = np.ascontiguousarray(fxscal, np.float64)
+        lst = np.arange(self.numindivs, dtype=np.int32) if indiv is None else np.ascontiguousarray(indiv, np.int32)
+        nl = len(lst)
+        a = np.empty((k, nl)); b = np.empty((k, nl)); nv = np.empty(nl, np.int32); ok = np.empty(nl, np.uint8)
+        _chk(lib().eb_lsqproj(self.h, _p(lst), C.c_int(nl), _p(ffvecs), _p(fxscal), C.c_int(k), _p(a), _p(b), _p(nv), _p(ok)))
+        return a, b, nv, ok
+
+    def evec_coords(self, evecs, indiv=None):
+        evecs = np.ascontiguousarray(evecs, np.float64); k = evecs.shape[0]
+        lst = np.arange(self.numindivs, dtype=np.int32) if indiv is None else np.ascontiguousarray(indiv, np.int32)
+        nl = len(lst)
+        co = np.empty((k, nl)); es = np.empty(k); ok = np.empty(nl, np.uint8)
+        _chk(lib().eb_evec_coords(self.h, _p(evecs), C.c_int(k), _p(lst), C.c_int(nl), _p(co), _p(es), _p(ok)))
+        return co, es, ok
 
     # ---- measurement
     def timings(self):

@@ -452,6 +452,52 @@ int eb_project(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, doub
   return project_run(c, evecs, numeigs, ffvecs, fxvecs, fxscal);
 }
 
+int eb_lsqproj(eb_ctx* c, const int* indiv, int nindiv, const double* ffvecs, const double* fxscal, int numeigs, double* acoeffs,
+               double* bcoeffs, int* nvalid, uint8_t* ok) {
+  int rc;
+  if ((rc = need_rows(c, "eb_lsqproj"))) return rc;
+  if (!c->grm_valid) { set_error("eb_lsqproj: run eb_grm first (needs the per-SNP normalisation)"); return EB_ERR_STATE; }
+  if (!ffvecs || !fxscal || nindiv <= 0) { set_error("eb_lsqproj: bad argument"); return EB_ERR_ARG; }
+  std::vector<int> all;
+  if (!indiv) { all.resize(nindiv); for (int i = 0; i < nindiv; i++) all[i] = i; indiv = all.data(); }
+  return lsqproj_run(c, indiv, nindiv, ffvecs, fxscal, numeigs, acoeffs, bcoeffs, nvalid, ok);
+}
+
+// smartpca.c:1440-1564: setfvecs -> SNP loadings -> sample projections -> lsqproj -> seteigscale -> scaled coordinates
+int eb_evec_coords(eb_ctx* c, const double* evecs, int numeigs, const int* indiv, int nindiv, double* coords, double* eigscale, uint8_t* ok) {
+  int rc;
+  if ((rc = need_rows(c, "eb_evec_coords"))) return rc;
+  if (!evecs || !coords || nindiv <= 0) { set_error("eb_evec_coords: bad argument"); return EB_ERR_ARG; }
+  std::vector<int> all;
+  if (!indiv) { all.resize(nindiv); for (int i = 0; i < nindiv; i++) all[i] = i; indiv = all.data(); }
+  // position of every PCA row inside the list (sqz, smartpca.c:3664-3684, needs all of them)
+  std::vector<int> pos(c->numindivs, -1);
+  for (int i = 0; i < nindiv; i++) {
+    if (indiv[i] < 0 || indiv[i] >= c->numindivs) { set_error("eb_evec_coords: individual index out of range"); return EB_ERR_ARG; }
+    pos[indiv[i]] = i;
+  }
+  for (int r = 0; r < c->nrows; r++)
+    if (pos[c->xindex_h[r]] < 0) { set_error("eb_evec_coords: PCA row %d (individual %d) is not in the output list", r, c->xindex_h[r]); return EB_ERR_ARG; }
+  const int64_t m = c->nsnp;
+  std::vector<double> ff((size_t)numeigs * m), sc(numeigs), a((size_t)numeigs * nindiv), b((size_t)numeigs * nindiv);
+  std::vector<uint8_t> okv(nindiv);
+  if ((rc = eb_project(c, evecs, numeigs, ff.data(), nullptr, sc.data()))) return rc;
+  if ((rc = eb_lsqproj(c, indiv, nindiv, ff.data(), sc.data(), numeigs, a.data(), b.data(), nullptr, okv.data()))) return rc;
+  for (int j = 0; j < numeigs; j++) {
+    double ab = 0.0, aa = 0.0;
+    for (int r = 0; r < c->nrows; r++) {
+      const int q = pos[c->xindex_h[r]];
+      ab += a[(size_t)j * nindiv + q] * b[(size_t)j * nindiv + q];
+      aa += a[(size_t)j * nindiv + q] * a[(size_t)j * nindiv + q];
+    }
+    const double es = ab / aa;
+    if (eigscale) eigscale[j] = es;
+    for (int q = 0; q < nindiv; q++) coords[(size_t)j * nindiv + q] = a[(size_t)j * nindiv + q] * es;
+  }
+  if (ok) memcpy(ok, okv.data(), nindiv);
+  return 0;
+}
+
 int eb_get_timings(eb_ctx* c, eb_timings* t) {
   if (!c || !t) return EB_ERR_ARG;
   *t = c->tm; t->nsplit = c->nsplit;

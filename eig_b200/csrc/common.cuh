@@ -112,6 +112,7 @@ struct eb_ctx {
 namespace eb {
 // pack_kernels.cu
 int launch_gather(eb_ctx* c);
+int launch_gather_into(eb_ctx* c, const int* list_d, int nlist, uint8_t* dst, int64_t wpitch);
 int launch_stats(eb_ctx* c, const eb_grm_opts* o);
 int launch_indiv_counts(eb_ctx* c, const uint8_t* keep_d, int* out_d);
 int launch_synth(eb_ctx* c, uint8_t* dst, int64_t nsnp, int64_t pitch, int numindivs, uint64_t seed, int64_t s0,
@@ -129,4 +130,6 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
 // fpca_kernels.cu
 int fpca_run(eb_ctx* c, int fancynorm, int altnormstyle, size_t K, size_t L, size_t I, long seed, double* eval, double* evec);
 int project_run(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, double* fxvecs, double* fxscal);
+int lsqproj_run(eb_ctx* c, const int* indiv, int nlist, const double* ffvecs, const double* fxscal, int k, double* acoeffs, double* bcoeffs,
+                int* nvalid, uint8_t* ok);
 }  // namespace eb

@@ -138,10 +138,15 @@ packed_gemm_kernel(const uint8_t* __restrict__ work, int64_t wpitch, const doubl
   }
 }
 
+// view of a 2-bit working matrix [mpad][npad/4] (the PCA rows by default; lsqproj builds one over all listed individuals)
+struct PackedView { const uint8_t* work; int64_t wpitch; int npad; };
+
 template <int MODE>
 static int launch_packed_gemm(eb_ctx* c, const double* table, const double* In_t, int64_t ld_in, double* Out_t, int64_t ld_out,
-                              int ncols, double oscale) {
-  const int64_t rows = MODE == MODE_XTB ? c->npad : c->mpad;
+                              int ncols, double oscale, const PackedView* view = nullptr) {
+  const PackedView dflt = {c->work.p, c->wpitch, c->npad};
+  const PackedView pv = view ? *view : dflt;
+  const int64_t rows = MODE == MODE_XTB ? pv.npad : c->mpad;
   const unsigned gx = (unsigned)((rows + PG_ROWS - 1) / PG_ROWS);
   int done = 0;
   while (done < ncols) {
@@ -156,7 +161,7 @@ static int launch_packed_gemm(eb_ctx* c, const double* table, const double* In_t
     const size_t smem = sizeof(double) * 2 * (NB_ * 8) * PG_LD + 2 * (MODE == MODE_XTB ? PG_KT * 64 : PG_ROWS * 20) +              \
                         sizeof(double) * (MODE == MODE_XTB ? 2 * PG_KT * 4 : PG_ROWS * 4);                                        \
     EB_CUDA(cudaFuncSetAttribute(packed_gemm_kernel<MODE, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-    packed_gemm_kernel<MODE, NB_><<<grid, 256, smem, c->stream>>>(c->work.p, c->wpitch, table, c->mpad, c->npad, in, ld_in, out,  \
+    packed_gemm_kernel<MODE, NB_><<<grid, 256, smem, c->stream>>>(pv.work, pv.wpitch, table, c->mpad, pv.npad, in, ld_in, out,    \
                                                                  ld_out, take, oscale);                                           \
   } break;
     switch (nblk) {
@@ -393,6 +398,109 @@ int project_run(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, dou
   if (fxvecs) EB_CUDA(cudaMemcpy2DAsync(fxvecs, sizeof(double) * n, FXt.p, sizeof(double) * npad, sizeof(double) * n, numeigs, cudaMemcpyDeviceToHost, c->stream));
   EB_CUDA(cudaStreamSynchronize(c->stream));
   if (fxscal) for (int j = 0; j < numeigs; j++) fxscal[j] = 1.0 / sqrt(s[j]);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ lsqproj (smartpca.c:4606-4757)
+// mask table: 1 for an observed genotype of a used SNP, else 0 (rows of the normal equations, smartpca.c:4695-4706)
+__global__ void mask_table_kernel(int64_t nsnp, int64_t mpad, const uint8_t* __restrict__ used, double* __restrict__ table) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= mpad) return;
+  const double v = (s < nsnp && used[s]) ? 1.0 : 0.0;
+  reinterpret_cast<double4*>(table)[s] = make_double4(v, v, v, 0.0);
+}
+// E[j][s] = fxscal[j] * ffvecs[j][s] (emat, smartpca.c:4702), zero in the pad
+__global__ void lsq_scale_kernel(const double* __restrict__ FFt, int64_t ld, int64_t nsnp, int64_t mpad, const double* __restrict__ fxscal,
+                                 double* __restrict__ Et) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y;
+  if (s >= mpad) return;
+  Et[(size_t)j * ld + s] = s < nsnp ? fxscal[j] * FFt[(size_t)j * ld + s] : 0.0;
+}
+// pair rows: Pt[pair(a,b)][s] = E[a][s] E[b][s] for a <= b, plus one all-ones row (-> number of valid SNPs per individual)
+__global__ void lsq_pairs_kernel(const double* __restrict__ Et, int64_t ld, int64_t nsnp, int64_t mpad, int k, double* __restrict__ Pt) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= mpad) return;
+  int pr = 0;
+  for (int a = 0; a < k; a++) {
+    const double ea = Et[(size_t)a * ld + s];
+    for (int b = a; b < k; b++) Pt[(size_t)(pr++) * ld + s] = ea * Et[(size_t)b * ld + s];
+  }
+  Pt[(size_t)pr * ld + s] = s < nsnp ? 1.0 : 0.0;
+}
+// one thread per individual: normal equations -> choldc / cholsl in the reference's operation order (linsubs.c:331-393)
+constexpr int LSQ_KMAX = 16;
+__global__ void __launch_bounds__(128) lsq_solve_kernel(const double* __restrict__ Nt, const double* __restrict__ Rt, int64_t ld, int nlist, int k,
+                                                        double* __restrict__ At, int* __restrict__ nvalid, uint8_t* __restrict__ ok) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nlist) return;
+  double a[LSQ_KMAX * LSQ_KMAX], p[LSQ_KMAX], x[LSQ_KMAX];
+  int pr = 0;
+  for (int i = 0; i < k; i++)
+    for (int j = i; j < k; j++) { const double v = Nt[(size_t)(pr++) * ld + q]; a[i * k + j] = v; a[j * k + i] = v; }
+  const int kk = (int)(Nt[(size_t)pr * ld + q] + 0.5);
+  nvalid[q] = kk;
+  bool good = kk > k;
+  if (good) {
+    for (int i = 0; i < k && good; i++)
+      for (int j = i; j < k; j++) {
+        double sum = a[i * k + j];
+        for (int m = i - 1; m >= 0; m--) sum -= a[i * k + m] * a[j * k + m];
+        if (i == j) { if (sum <= 0.0) { good = false; break; } p[i] = sqrt(sum); }
+        else a[j * k + i] = sum / p[i];
+      }
+  }
+  if (good) {
+    for (int i = 0; i < k; i++) { double sum = Rt[(size_t)i * ld + q]; for (int m = i - 1; m >= 0; m--) sum -= a[i * k + m] * x[m]; x[i] = sum / p[i]; }
+    for (int i = k - 1; i >= 0; i--) { double sum = x[i]; for (int m = i + 1; m < k; m++) sum -= a[m * k + i] * x[m]; x[i] = sum / p[i]; }
+  }
+  for (int i = 0; i < k; i++) At[(size_t)i * ld + q] = good ? x[i] : 0.0;
+  ok[q] = good ? 1 : 0;
+}
+
+int lsqproj_run(eb_ctx* c, const int* indiv, int nlist, const double* ffvecs, const double* fxscal, int k, double* acoeffs, double* bcoeffs,
+                int* nvalid, uint8_t* ok) {
+  if (k < 1 || k > LSQ_KMAX) { set_error("eb_lsqproj: numeigs must be in 1..%d", LSQ_KMAX); return EB_ERR_ARG; }
+  int rc;
+  const int64_t m = c->nsnp, mpad = c->mpad;
+  const int npad2 = (nlist + 255) / 256 * 256;
+  const int64_t wp2 = npad2 / 4;
+  const int npairs = k * (k + 1) / 2 + 1;
+  DevBuf<uint8_t> work2, ok_d;
+  DevBuf<int> list_d, nv_d;
+  DevBuf<double> FFt, Et, Pt, ftab, mtab, Rt, Nt, At, sc_d;
+  if ((rc = work2.ensure((size_t)mpad * wp2)) || (rc = list_d.ensure(nlist)) || (rc = FFt.ensure((size_t)k * mpad)) || (rc = Et.ensure((size_t)k * mpad)) ||
+      (rc = Pt.ensure((size_t)npairs * mpad)) || (rc = ftab.ensure((size_t)mpad * 4)) || (rc = mtab.ensure((size_t)mpad * 4)) ||
+      (rc = Rt.ensure((size_t)k * npad2)) || (rc = Nt.ensure((size_t)npairs * npad2)) || (rc = At.ensure((size_t)k * npad2)) ||
+      (rc = sc_d.ensure(k)) || (rc = nv_d.ensure(npad2)) || (rc = ok_d.ensure(npad2)))
+    return rc;
+  for (int i = 0; i < nlist; i++)
+    if (indiv[i] < 0 || indiv[i] >= c->numindivs) { set_error("eb_lsqproj: individual index %d out of range", indiv[i]); return EB_ERR_ARG; }
+  EB_CUDA(cudaMemcpyAsync(list_d.p, indiv, sizeof(int) * nlist, cudaMemcpyHostToDevice, c->stream));
+  EB_CUDA(cudaMemsetAsync(FFt.p, 0, sizeof(double) * (size_t)k * mpad, c->stream));
+  EB_CUDA(cudaMemcpy2DAsync(FFt.p, sizeof(double) * mpad, ffvecs, sizeof(double) * m, sizeof(double) * m, k, cudaMemcpyHostToDevice, c->stream));
+  EB_CUDA(cudaMemcpyAsync(sc_d.p, fxscal, sizeof(double) * k, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = launch_gather_into(c, list_d.p, nlist, work2.p, wp2))) return rc;
+  const unsigned gm = (unsigned)((mpad + 255) / 256);
+  fix_table_kernel<<<gm, 256, 0, c->stream>>>(m, mpad, c->xmean_d.p, c->xfancy_d.p, c->used_d.p, ftab.p);
+  EB_CHECK_LAUNCH(c);
+  mask_table_kernel<<<gm, 256, 0, c->stream>>>(m, mpad, c->used_d.p, mtab.p);
+  EB_CHECK_LAUNCH(c);
+  lsq_scale_kernel<<<dim3(gm, k), 256, 0, c->stream>>>(FFt.p, mpad, m, mpad, sc_d.p, Et.p);
+  EB_CHECK_LAUNCH(c);
+  lsq_pairs_kernel<<<gm, 256, 0, c->stream>>>(Et.p, mpad, m, mpad, k, Pt.p);
+  EB_CHECK_LAUNCH(c);
+  const PackedView pv = {work2.p, wp2, npad2};
+  // rr[j][q] = sum_s x_qs e_sj (also bcoeffs, smartpca.c:4743-4746);  co[(a,b)][q] = sum_s m_qs e_sa e_sb
+  if ((rc = launch_packed_gemm<MODE_XTB>(c, ftab.p, Et.p, mpad, Rt.p, npad2, k, 1.0, &pv))) return rc;
+  if ((rc = launch_packed_gemm<MODE_XTB>(c, mtab.p, Pt.p, mpad, Nt.p, npad2, npairs, 1.0, &pv))) return rc;
+  lsq_solve_kernel<<<(nlist + 127) / 128, 128, 0, c->stream>>>(Nt.p, Rt.p, npad2, nlist, k, At.p, nv_d.p, ok_d.p);
+  EB_CHECK_LAUNCH(c);
+  if (acoeffs) EB_CUDA(cudaMemcpy2DAsync(acoeffs, sizeof(double) * nlist, At.p, sizeof(double) * npad2, sizeof(double) * nlist, k, cudaMemcpyDeviceToHost, c->stream));
+  if (bcoeffs) EB_CUDA(cudaMemcpy2DAsync(bcoeffs, sizeof(double) * nlist, Rt.p, sizeof(double) * npad2, sizeof(double) * nlist, k, cudaMemcpyDeviceToHost, c->stream));
+  if (nvalid) EB_CUDA(cudaMemcpyAsync(nvalid, nv_d.p, sizeof(int) * nlist, cudaMemcpyDeviceToHost, c->stream));
+  if (ok) EB_CUDA(cudaMemcpyAsync(ok, ok_d.p, nlist, cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

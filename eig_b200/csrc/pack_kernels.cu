@@ -50,6 +50,15 @@ int launch_gather(eb_ctx* c) {
   return 0;
 }
 
+// gather an arbitrary individual list (device array) into a caller-provided working matrix [mpad][wpitch]
+int launch_gather_into(eb_ctx* c, const int* list_d, int nlist, uint8_t* dst, int64_t wpitch) {
+  const int wordsPerRow = (int)(wpitch >> 2);
+  dim3 block(256), grid((wordsPerRow + 255) / 256, (unsigned)std::min<int64_t>(c->mpad, 65535));
+  gather_rows_kernel<<<grid, block, 0, c->stream>>>(c->raw, c->raw_pitch, c->nsnp, c->mpad, list_d, nlist, dst, wpitch);
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- stats
 __device__ __forceinline__ void count_word(uint32_t x, int& n1, int& n2, int& n3) {
   const uint32_t lo = x & 0x55555555u, hi = (x >> 1) & 0x55555555u;

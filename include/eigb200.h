@@ -149,6 +149,19 @@ void eb_gauss_matrix (long seed, size_t n, size_t L, double *out);
 int eb_project (eb_ctx *, const double *evecs, int numeigs, double *ffvecs /* [numeigs][nsnp] */ ,
                 double *fxvecs /* [numeigs][nrows] */ , double *fxscal /* [numeigs] */ );
 
+/* lsqproj(), smartpca.c:4606-4757 (regressit, regsubs.c:8-77; solvit/choldc/cholsl, nicksrc/linsubs.c:296-393):
+ * least-squares coordinates of every listed individual on the SNP loadings, using only its observed genotypes.
+ * indiv[nindiv] ascending indices into 0..numindivs-1 (NULL = 0..nindiv-1): the reference walks all non-ignored
+ * individuals, PCA rows or not (projected populations).  acoeffs/bcoeffs [numeigs][nindiv] (smartpca.c:4713,4745);
+ * nvalid = rows of the individual's regression; ok = 0 where the reference ignores the individual
+ * ("insufficient data", nvalid <= numeigs) -- its coefficients are 0.  Uses xmean/xfancy/used of the last eb_grm. */
+int eb_lsqproj (eb_ctx *, const int *indiv, int nindiv, const double *ffvecs /* [numeigs][nsnp] */ , const double *fxscal,
+                int numeigs, double *acoeffs, double *bcoeffs, int *nvalid, uint8_t * ok);
+/* the .evec values: the whole sequence smartpca.c:1440-1564 (setfvecs, loadings, projections, lsqproj, seteigscale,
+ * acoeffs * eigscale).  coords [numeigs][nindiv]; every PCA row must be in the list. */
+int eb_evec_coords (eb_ctx *, const double *evecs /* [numeigs][nrows] */ , int numeigs, const int *indiv, int nindiv,
+                    double *coords, double *eigscale /* [numeigs] or NULL */ , uint8_t * ok /* [nindiv] or NULL */ );
+
 /* -------- measurement helpers -------- */
 /* last pass timings measured with CUDA events on the library's stream (milliseconds) */
 typedef struct {

@@ -206,3 +206,59 @@ def ref_fpca(packed, numindivs, K, L, I, seed, xindex=None, fancynorm=1, altnorm
                     C.c_long(K), C.c_long(L), C.c_long(I), C.c_long(seed),
                     ev.ctypes.data_as(C.c_void_p), vec.ctypes.data_as(C.c_void_p), secs.ctypes.data_as(C.c_void_p))
     return ev, vec, float(secs[0])
+
+
+def port_lsqproj(packed, indiv, used, xmean, xfancy, ffvecs, fxscal):
+    """oracle port of lsqproj (smartpca.c:4606-4757): acoeffs, bcoeffs [k][nlist], nvalid, ok"""
+    nsnp, rlen = packed.shape
+    indiv = np.ascontiguousarray(indiv, np.int32); nl = len(indiv)
+    ffvecs = np.ascontiguousarray(ffvecs, np.float64); k = ffvecs.shape[0]
+    a = np.empty((k, nl)); b = np.empty((k, nl)); nv = np.empty(nl, np.int32); ok = np.empty(nl, np.uint8)
+    port().orc_lsqproj(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen), indiv.ctypes.data_as(C.c_void_p), C.c_int(nl),
+                       np.ascontiguousarray(used, np.uint8).ctypes.data_as(C.c_void_p), np.ascontiguousarray(xmean).ctypes.data_as(C.c_void_p),
+                       np.ascontiguousarray(xfancy).ctypes.data_as(C.c_void_p), ffvecs.ctypes.data_as(C.c_void_p),
+                       np.ascontiguousarray(fxscal).ctypes.data_as(C.c_void_p), C.c_int(k),
+                       a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), nv.ctypes.data_as(C.c_void_p), ok.ctypes.data_as(C.c_void_p))
+    return a, b, nv, ok
+
+
+def port_seteigscale(acoeffs, bcoeffs, rowpos):
+    acoeffs = np.ascontiguousarray(acoeffs); bcoeffs = np.ascontiguousarray(bcoeffs); k, nl = acoeffs.shape
+    rowpos = np.ascontiguousarray(rowpos, np.int32); out = np.empty(k)
+    port().orc_seteigscale(acoeffs.ctypes.data_as(C.c_void_p), bcoeffs.ctypes.data_as(C.c_void_p), C.c_int(nl),
+                           rowpos.ctypes.data_as(C.c_void_p), C.c_int(len(rowpos)), C.c_int(k), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def port_evec_coords(packed, numindivs, used, xmean, xfancy, evecs, xindex=None, indiv_ignore=None):
+    """the whole .evec value pipeline with the port: project -> lsqproj over all non-ignored individuals -> eigscale.
+    Returns coords [k][numindivs] (zero rows for ignored / insufficient individuals), eigscale, ok[numindivs]"""
+    xi = _xi(xindex, numindivs)
+    ff, fx, sc = port_project(packed, numindivs, used, xmean, xfancy, evecs, xindex=xi)
+    keep = np.ones(numindivs, bool) if indiv_ignore is None else ~np.asarray(indiv_ignore, bool)
+    lst = np.flatnonzero(keep).astype(np.int32)
+    a, b, nv, ok = port_lsqproj(packed, lst, used, xmean, xfancy, ff, sc)
+    pos = -np.ones(numindivs, np.int64); pos[lst] = np.arange(len(lst))
+    es = port_seteigscale(a, b, pos[xi])
+    k = a.shape[0]
+    coords = np.zeros((k, numindivs)); coords[:, lst] = a * es[:, None]
+    okf = np.zeros(numindivs, np.uint8); okf[lst] = ok
+    return coords, es, okf, ff, sc
+
+
+def ref_evec_coords(packed, numindivs, used, xmean, xfancy, evecs, xindex=None, indiv_ignore=None, fancynorm=1, altnormstyle=1):
+    """the unmodified reference's own post-eigen sequence (smartpca.c:1440-1564), run in a forked child"""
+    nsnp, rlen = packed.shape; xi = _xi(xindex, numindivs); n = len(xi)
+    evecs = np.ascontiguousarray(evecs, np.float64); k = evecs.shape[0]
+    a = np.zeros((k, numindivs)); b = np.zeros((k, numindivs)); es = np.zeros(k); ff = np.zeros((k, nsnp)); sc = np.zeros(k)
+    ign = np.zeros(numindivs, np.uint8)
+    ig_in = None if indiv_ignore is None else np.ascontiguousarray(indiv_ignore, np.uint8)
+    rc = ref().refh_evec_coords(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen), C.c_int(numindivs),
+                                xi.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(fancynorm), C.c_int(altnormstyle),
+                                np.ascontiguousarray(used, np.uint8).ctypes.data_as(C.c_void_p),
+                                np.ascontiguousarray(xmean).ctypes.data_as(C.c_void_p), np.ascontiguousarray(xfancy).ctypes.data_as(C.c_void_p),
+                                evecs.ctypes.data_as(C.c_void_p), C.c_int(k), None if ig_in is None else ig_in.ctypes.data_as(C.c_void_p),
+                                a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), es.ctypes.data_as(C.c_void_p),
+                                ff.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p), ign.ctypes.data_as(C.c_void_p))
+    assert rc == 0, rc
+    return dict(coords=a, bcoeffs=b, eigscale=es, ffvecs=ff, fxscal=sc, ignored=ign)

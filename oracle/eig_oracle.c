@@ -442,3 +442,88 @@ void orc_project (const uint8_t * packed, long ncols, long rlen, const int *xind
   }
   for (int j = 0; j < numeigs; j++) fxscal[j] = 1.0 / sqrt (fxscal[j]);
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * lsqproj + seteigscale: the .evec coordinates (restates smartpca.c:4606-4757, regsubs.c:8-77 regressit,
+ * nicksrc/linsubs.c:296-393 solvit/choldc/cholsl, smartpca.c:4758-4781 seteigscale, smartpca.c:1553-1564).
+ * indiv[nlist]: the non-ignored individuals (the reference walks all of indivmarkers, smartpca.c:4651).
+ * For individual q: rows kk over SNPs with used[s] and a valid genotype; emat[kk][j] = fxscal[j]*ffvecs[j][s],
+ * rhs[kk] = g*xfancy[s]-xmean[s]; normal equations + Cholesky; bcoeffs[j] = fxscal[j]*sum_s xrow[s]*ffvecs[j][s]
+ * (missing -> 0).  An individual with kk <= numeigs (or a non positive definite normal matrix) gets ok = 0 and
+ * zero coefficients.  nvalid[q] = kk. */
+static int orc_choldc (double *a, int n, double *p)
+{
+  for (int i = 0; i < n; i++) p[i] = 0;
+  for (int i = 0; i < n; i++)
+    for (int j = i; j < n; j++) {
+      double sum = a[i * n + j];
+      for (int k = i - 1; k >= 0; k--) sum -= a[i * n + k] * a[j * n + k];
+      if (i == j) { if (sum <= 0.0) return -1; p[i] = sqrt (sum); }
+      else a[j * n + i] = sum / p[i];
+    }
+  return 1;
+}
+static void orc_cholsl (const double *a, int n, const double *p, const double *b, double *x)
+{
+  for (int i = 0; i < n; i++) { double sum = b[i]; for (int k = i - 1; k >= 0; k--) sum -= a[i * n + k] * x[k]; x[i] = sum / p[i]; }
+  for (int i = n - 1; i >= 0; i--) { double sum = x[i]; for (int k = i + 1; k < n; k++) sum -= a[k * n + i] * x[k]; x[i] = sum / p[i]; }
+}
+
+void orc_lsqproj (const uint8_t * packed, long ncols, long rlen, const int *indiv, int nlist,
+                  const uint8_t * used, const double *xmean, const double *xfancy,
+                  const double *ffvecs /* [numeigs][ncols] */ , const double *fxscal, int numeigs,
+                  double *acoeffs /* [numeigs][nlist] */ , double *bcoeffs /* [numeigs][nlist] */ , int *nvalid, uint8_t * ok)
+{
+  const int n = numeigs;
+  double *co = (double *) malloc (sizeof (double) * n * n), *rr = (double *) malloc (sizeof (double) * n),
+    *p = (double *) malloc (sizeof (double) * n), *ans = (double *) malloc (sizeof (double) * n), *e = (double *) malloc (sizeof (double) * n);
+  for (int q = 0; q < nlist; q++) {
+    memset (co, 0, sizeof (double) * n * n); memset (rr, 0, sizeof (double) * n);
+    int kk = 0;
+    for (int j = 0; j < n; j++) bcoeffs[(size_t) j * nlist + q] = 0;
+    for (long s = 0; s < ncols; s++) {
+      if (!used[s]) continue;
+      const int g = gt (packed + s * rlen, indiv[q]);
+      if (g < 0) continue;
+      const double x = g * xfancy[s] - xmean[s];
+      for (int j = 0; j < n; j++) e[j] = fxscal[j] * ffvecs[(size_t) j * ncols + s];
+      for (int j = 0; j < n; j++) {
+        rr[j] += e[j] * x;
+        for (int k = j; k < n; k++) co[j * n + k] = co[k * n + j] += e[j] * e[k];
+      }
+      ++kk;
+    }
+    nvalid[q] = kk; ok[q] = 0;
+    for (int j = 0; j < n; j++) acoeffs[(size_t) j * nlist + q] = 0;
+    /* bcoeffs: fxscal[j] * vdot(xrow, ffvecs_j) over all SNPs with missing -> 0 == rr up to summation order */
+    for (int j = 0; j < n; j++) {
+      double y = 0;
+      for (long s = 0; s < ncols; s++) {
+        if (!used[s]) continue;
+        const int g = gt (packed + s * rlen, indiv[q]);
+        if (g >= 0) y += (g * xfancy[s] - xmean[s]) * ffvecs[(size_t) j * ncols + s];
+      }
+      bcoeffs[(size_t) j * nlist + q] = fxscal[j] * y;
+    }
+    if (kk <= n) continue;
+    if (orc_choldc (co, n, p) < 0) continue;
+    orc_cholsl (co, n, p, rr, ans);
+    for (int j = 0; j < n; j++) acoeffs[(size_t) j * nlist + q] = ans[j];
+    ok[q] = 1;
+  }
+  free (co); free (rr); free (p); free (ans); free (e);
+}
+
+/* seteigscale (smartpca.c:4758-4781): eigscale[j] = <a_j, b_j> / <a_j, a_j> over the PCA rows; rowpos[k] = position of
+ * PCA row k inside the list the coefficients are stored for. */
+void orc_seteigscale (const double *acoeffs, const double *bcoeffs, int nlist, const int *rowpos, int nrows, int numeigs, double *eigscale)
+{
+  for (int j = 0; j < numeigs; j++) {
+    double ab = 0, aa = 0;
+    for (int k = 0; k < nrows; k++) {
+      const double a = acoeffs[(size_t) j * nlist + rowpos[k]], b = bcoeffs[(size_t) j * nlist + rowpos[k]];
+      ab += a * b; aa += a * a;
+    }
+    eigscale[j] = ab / aa;
+  }
+}

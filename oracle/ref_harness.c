@@ -128,3 +128,68 @@ void refh_gauss (long seed_in, long n, long L, double *out)
 
 unsigned long refh_mt_first (unsigned long s) { gsl_rng *r; unsigned long v; gsl_rng_default_seed = s; r = gsl_rng_alloc (gsl_rng_default); v = gsl_rng_get (r); gsl_rng_free (r); return v; }
 void refh_openblas_threads (int n) { extern void openblas_set_num_threads (int); openblas_set_num_threads (n); }
+
+/* .evec coordinates: the reference's own post-eigen sequence, smartpca.c:1440-1564 (setfvecs, getcolxf loadings,
+ * loadxdataind/fixxrow sample projections, lsqproj, seteigscale, mulmat) on flat inputs.  lsqproj keeps file-static
+ * work arrays sized by its first call (smartpca.c:4614,4630-4636), so every invocation runs in a forked child and
+ * hands its results back through shared anonymous mappings.
+ * acoeffs_o / bcoeffs_o: [k][nind] (all individuals; rows of ignored individuals stay 0), ignored_o[nind]. */
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
+int refh_evec_coords (const unsigned char *packed, long nsnp, long rl, int nind, const int *xindex_in, int nrows,
+                      int fancy, int altnorm, const unsigned char *used, const double *xmean_in, const double *xfancy_in,
+                      const double *evecs_in, int k, const unsigned char *indiv_ignore,
+                      double *acoeffs_o, double *bcoeffs_o, double *eigscale_o, double *ffvecs_o, double *fxscal_o, unsigned char *ignored_o)
+{
+  size_t na = sizeof (double) * (size_t) k * nind, nf = sizeof (double) * (size_t) k * nsnp;
+  size_t tot = 2 * na + nf + sizeof (double) * 2 * k + nind;
+  unsigned char *sh = mmap (NULL, tot, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+  if (sh == MAP_FAILED) return -1;
+  pid_t pid = fork ();
+  if (pid < 0) return -2;
+  if (pid == 0) {
+    long i; int j, kk_; double y;
+    double *acoeffs = (double *) sh, *bcoeffs = (double *) (sh + na), *ffv = (double *) (sh + 2 * na), *esc = (double *) (sh + 2 * na + nf),
+      *fxs = esc + k; unsigned char *ign = sh + 2 * na + nf + sizeof (double) * 2 * k;
+    double *fvecs, *fxvecs, *cc, *xrow, *eigscmat; int *xidx, *xt;
+    fclose (stdout); stdout = fopen ("/dev/null", "w");
+    hbuild (packed, nsnp, rl, nind);
+    fancynorm = fancy; altnormstyle = altnorm; usepopsformissing = NO; regmode = YES; plotmode = NO; printcover = NO;
+    numeigs = k; numindivs = nind;
+    for (i = 0; i < nsnp; i++) hsnps[i].ignore = used[i] ? NO : YES;
+    for (i = 0; i < nind; i++) { hind[i].idnum = (int) i; hind[i].ignore = indiv_ignore && indiv_ignore[i] ? YES : NO; }
+    ZALLOC (xmean, nsnp, double); ZALLOC (xfancy, nsnp, double);
+    memcpy (xmean, xmean_in, sizeof (double) * nsnp); memcpy (xfancy, xfancy_in, sizeof (double) * nsnp);
+    ZALLOC (xidx, nrows, int); memcpy (xidx, xindex_in, sizeof (int) * nrows);
+    ZALLOC (xt, nind, int);
+    ZALLOC (fvecs, (long) nrows * k, double); ZALLOC (fxvecs, (long) nrows * k, double); ZALLOC (cc, nrows > 3 ? nrows : 3, double);
+    ZALLOC (xrow, nsnp, double);
+    setfvecs (fvecs, (double *) evecs_in, nrows, k);
+    for (i = 0; i < nsnp; i++) {
+      getcolxf (cc, hsnpp[i], xidx, nrows, (int) i, NULL, NULL);
+      for (j = 0; j < k; j++) for (kk_ = 0; kk_ < nrows; kk_++) ffv[j * nsnp + i] += fvecs[j * nrows + kk_] * cc[kk_];
+    }
+    for (i = 0; i < nrows; i++) {
+      loadxdataind (xrow, hsnpp, xidx[i], (int) nsnp);
+      fixxrow (xrow, xmean, xfancy, (int) nsnp);
+      for (j = 0; j < k; j++) { y = fxvecs[j * nrows + i] = vdot (xrow, ffv + j * nsnp, (int) nsnp); fxs[j] += y * y; }
+    }
+    for (j = 0; j < k; j++) fxs[j] = 1.0 / sqrt (fxs[j]);
+    lsqproj (-99, hsnpp, (int) nsnp, hindp, nind, fxs, ffv, acoeffs, bcoeffs, xt, 1);
+    seteigscale (esc, acoeffs, bcoeffs, xidx, nrows, k);
+    ZALLOC (eigscmat, k * k, double);
+    setdiag (eigscmat, esc, k);
+    mulmat (acoeffs, eigscmat, acoeffs, k, k, nind);
+    for (i = 0; i < nind; i++) ign[i] = hind[i].ignore ? 1 : 0;
+    _exit (0);
+  }
+  int status = 0;
+  waitpid (pid, &status, 0);
+  if (!WIFEXITED (status) || WEXITSTATUS (status) != 0) { munmap (sh, tot); return -3; }
+  memcpy (acoeffs_o, sh, na); memcpy (bcoeffs_o, sh + na, na); memcpy (ffvecs_o, sh + 2 * na, nf);
+  memcpy (eigscale_o, sh + 2 * na + nf, sizeof (double) * k); memcpy (fxscal_o, sh + 2 * na + nf + sizeof (double) * k, sizeof (double) * k);
+  memcpy (ignored_o, sh + 2 * na + nf + sizeof (double) * 2 * k, nind);
+  munmap (sh, tot);
+  return 0;
+}

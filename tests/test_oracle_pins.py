@@ -155,3 +155,23 @@ def test_committed_reference_vectors():
     ev, u = ob.port_fpca(P, int(z["nind"]), K=3, L=6, I=2, seed=int(z["gseed"]), xindex=xi, altnormstyle=int(z["altnormstyle"]))
     assert (np.abs(ev - z["fpca_eval"]) / z["fpca_eval"]).max() < 1e-10
     assert np.abs(np.abs((u * z["fpca_evec"]).sum(0)) - 1).max() < 1e-10
+
+
+def test_port_lsqproj_against_reference():
+    """pin of orc_lsqproj / orc_seteigscale: the unmodified reference's post-eigen sequence (smartpca.c:1440-1564)"""
+    if ob.ref() is None:
+        pytest.skip("oracle/_ref not built")
+    from eig_b200 import synth
+    nsnp, nind, k = 2000, 90, 4
+    g = synth.genotypes(3, nsnp, nind, missing=0.15, npops=3, delta=0.3)
+    g[:, 7] = -1; g[3:, 11] = -1
+    P = synth.pack(g)
+    xi = np.array([i for i in range(nind) if i % 4 != 1 and i not in (7, 11)], dtype=np.int32)
+    o = ob.ref_grm(P, nind, xindex=xi)
+    lam, vec = ob.ref_eigvecs(o["XTX"] / o["y"])
+    r = ob.ref_evec_coords(P, nind, o["used"], o["xmean"], o["xfancy"], vec[:k], xindex=xi)
+    c, es, ok, ff, sc = ob.port_evec_coords(P, nind, o["used"], o["xmean"], o["xfancy"], vec[:k], xindex=xi)
+    assert np.array_equal(r["ignored"], 1 - ok) and set(np.flatnonzero(ok == 0)) == {7, 11}
+    assert np.abs(ff - r["ffvecs"]).max() < 1e-11 and np.abs(sc - r["fxscal"]).max() < 1e-15
+    assert np.abs(es - r["eigscale"]).max() <= 1e-12 * np.abs(es).max()
+    assert np.abs(c - r["coords"]).max() < 1e-13
