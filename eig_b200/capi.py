@@ -45,7 +45,7 @@ EXPORTS = [
     "eb_reset_launch_count", "eb_upload_packed", "eb_upload_packed_rows", "eb_adopt_packed_device", "eb_synth_packed_device",
     "eb_set_rows", "eb_snp_counts", "eb_indiv_valid_counts", "eb_grm", "eb_grm_partial", "eb_grm_device_ptr", "eb_grm_finish",
     "eb_eig", "eb_eigvecs", "eb_ridoutlier", "eb_pca_full", "eb_fpca", "eb_gauss_matrix", "eb_project", "eb_get_timings",
-    "eb_microbench_fp64", "eb_set_option", "eb_debug_tridiag", "eb_lsqproj", "eb_evec_coords",
+    "eb_microbench_fp64", "eb_set_option", "eb_debug_tridiag", "eb_lsqproj", "eb_evec_coords", "eb_grm_dense_begin", "eb_grm_dense_add", "eb_grm_dense_end", "eigvecs", "eigvals",
 ]
 
 _lib = None
@@ -188,6 +188,19 @@ class Context:
         y = C.c_double(0)
         xtx = np.empty((self.nrows, self.nrows)) if want_xtx else None
         _chk(lib().eb_grm_finish(self.h, C.byref(y), _p(xtx)))
+        return y.value, xtx
+
+    def grm_dense(self, tblocks, nrows, want_xtx=False):
+        """dense path: tblocks = iterable of [nblock][nrows] FP64 blocks of normalised columns"""
+        _chk(lib().eb_grm_dense_begin(self.h, C.c_int(nrows)))
+        self.nrows = nrows
+        for tb in tblocks:
+            tb = np.ascontiguousarray(tb, np.float64)
+            assert tb.shape[1] == nrows
+            _chk(lib().eb_grm_dense_add(self.h, _p(tb), C.c_int(tb.shape[0])))
+        y = C.c_double(0)
+        xtx = np.empty((nrows, nrows)) if want_xtx else None
+        _chk(lib().eb_grm_dense_end(self.h, C.byref(y), _p(xtx)))
         return y.value, xtx
 
     # ---- eigen

@@ -280,6 +280,59 @@ int eb_grm(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* nmiss, uin
   return eb_grm_finish(c, y_out, XTX_host);
 }
 
+// ---- dense path: getcolxz + domult_increment_normal (smartpca.c:3129-3216, 3531-3561), used by the reference when
+// usepopsformissing / ldregress make the columns arbitrary FP64 values.  The host keeps producing the normalised
+// columns (tblock rows); the library accumulates XTX += sum_s x_s x_s^T on the FP64 tensor cores.
+int eb_grm_dense_begin(eb_ctx* c, int nrows) {
+  if (!c || nrows < 2) { set_error("eb_grm_dense_begin: bad argument"); return EB_ERR_ARG; }
+  EB_CUDA(cudaSetDevice(c->device));
+  c->nrows = nrows;
+  c->npad = (nrows + TILE - 1) / TILE * TILE;
+  c->rows_set = false;      // no packed working matrix behind this GRM
+  c->grm_valid = false;
+  int rc;
+  const size_t plane = (size_t)c->npad * c->npad;
+  if ((rc = c->partial.ensure(plane)) || (rc = c->xtx.ensure(plane)) || (rc = c->trace_d.ensure(1)) ||
+      (rc = c->dense_blk.ensure((size_t)1024 * c->npad)))
+    return rc;
+  EB_CUDA(cudaMemsetAsync(c->partial.p, 0, sizeof(double) * plane, c->stream));
+  c->dense_open = true;
+  c->nsplit = 1;
+  return 0;
+}
+
+int eb_grm_dense_add(eb_ctx* c, const double* tblock, int nblock) {
+  if (!c || !c->dense_open) { set_error("eb_grm_dense_add: call eb_grm_dense_begin first"); return EB_ERR_STATE; }
+  if (!tblock || nblock < 0) { set_error("eb_grm_dense_add: bad argument"); return EB_ERR_ARG; }
+  EB_CUDA(cudaSetDevice(c->device));
+  int rc;
+  // the reference refuses columns that are not centred (domult_increment_normal's ycheck, smartpca.c:3545-3549)
+  for (int b = 0; b < nblock; b++) {
+    double s = 0.0;
+    for (int i = 0; i < c->nrows; i++) s += tblock[(size_t)b * c->nrows + i];
+    if (fabs(s) > .00001) { set_error("bad ycheck"); return EB_ERR_NUMERIC; }
+  }
+  for (int done = 0; done < nblock; done += 1024) {
+    const int nb = std::min(1024, nblock - done), kr = (nb + 31) / 32 * 32;
+    EB_CUDA(cudaMemsetAsync(c->dense_blk.p, 0, sizeof(double) * (size_t)kr * c->npad, c->stream));
+    EB_CUDA(cudaMemcpy2DAsync(c->dense_blk.p, sizeof(double) * c->npad, tblock + (size_t)done * c->nrows, sizeof(double) * c->nrows,
+                              sizeof(double) * c->nrows, nb, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = launch_syrk_lower_add(c, c->partial.p, c->npad, c->npad, c->dense_blk.p, c->npad, kr))) return rc;
+    EB_CUDA(cudaStreamSynchronize(c->stream));      // the caller may reuse tblock
+  }
+  return 0;
+}
+
+int eb_grm_dense_end(eb_ctx* c, double* y_out, double* XTX_host) {
+  if (!c || !c->dense_open) { set_error("eb_grm_dense_end: call eb_grm_dense_begin first"); return EB_ERR_STATE; }
+  EB_CUDA(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = grm_dense_finalize(c))) return rc;
+  c->dense_open = false;
+  c->grm_valid = true;
+  return eb_grm_finish(c, y_out, XTX_host);
+}
+
 int eb_eig(eb_ctx* c, int nvec, double* lambda, double* evecs) {
   if (!c || !c->grm_valid || c->y <= 0.0) { set_error("eb_eig: no normalised GRM resident (call eb_grm first)"); return EB_ERR_STATE; }
   EB_CUDA(cudaSetDevice(c->device));
@@ -314,6 +367,28 @@ int eb_debug_tridiag(eb_ctx* c, const double* mat, int n, double* d, double* e, 
   EB_CUDA(cudaMemcpyAsync(e, de.p + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
   EB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+// ---- drop-in symbols with the reference's own names and contract (include/eigsubs.h:6-7; eigsubs.c:21,39): mat row-major
+// n x n, preserved; eigenvalues descending; evecs row i = eigenvector i; failure = message on stderr + exit(1) like
+// eigx.c:109-116.  They run on a process-wide context on the current device.
+static eb_ctx* g_dropin_ctx = nullptr;
+static eb_ctx* dropin_ctx() {
+  if (!g_dropin_ctx) g_dropin_ctx = eb_create(-1);
+  if (!g_dropin_ctx) { fprintf(stderr, "eigvecs (libeigb200): %s\n", eb_last_error()); exit(1); }
+  return g_dropin_ctx;
+}
+void eigvecs(double* mat, double* evals, double* evecs, int n) {
+  eb_ctx* c = dropin_ctx();
+  // all n vectors for the sizes the remaining callers use (2 x 2 ellipses, smartpca.c:1751; mkorth); beyond that the
+  // leading block only -- what smartpca.c:4087,4298 consume -- and zeros for the rest
+  const int nvec = n <= 2048 ? n : 40;
+  if (n > 2048) memset(evecs, 0, sizeof(double) * (size_t)n * n);
+  if (eb_eigvecs(c, mat, evals, evecs, n, nvec) != 0) { fprintf(stderr, "eigvecs (libeigb200): %s\n", eb_last_error()); exit(1); }
+}
+void eigvals(double* mat, double* evals, int n) {
+  eb_ctx* c = dropin_ctx();
+  if (eb_eigvecs(c, mat, evals, nullptr, n, 0) != 0) { fprintf(stderr, "eigvals (libeigb200): %s\n", eb_last_error()); exit(1); }
 }
 
 int eb_set_option(eb_ctx* c, const char* key, int value) {

@@ -89,6 +89,8 @@ struct eb_ctx {
   eb::DevBuf<double> xtx;         // npad * npad, full symmetric, UNNORMALISED
   eb::DevBuf<double> trace_d;     // 1
   eb::DevBuf<int> workctr_d;      // 1
+  eb::DevBuf<double> dense_blk;   // dense path staging: [1024][npad]
+  bool dense_open = false;
   int nsplit = 1;
   bool grm_valid = false;
   double y = 0.0;                 // trace/(nrows-1)
@@ -124,6 +126,10 @@ int microbench_fp64(eb_ctx* c, double* dmma, double* dfma);
 // eig_kernels.cu
 int eig_resident(eb_ctx* c, const double* A_d, int64_t lda, int n, double scale, int nvec, double* lambda_h, double* evecs_h);
 bool eig_uses_two_stage(const eb_ctx* c, int n, int nvec);
+// eig2_gemm.cu
+int launch_syrk_lower_add(eb_ctx* c, double* A, int64_t lda, int n, const double* T, int64_t ldt, int krows);
+// grm_kernel.cu (dense path)
+int grm_dense_finalize(eb_ctx* c);
 // eig2_kernels.cu
 int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, double* e);
 int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* theta_h, double* vec_d, int* iters_out, int* matvecs_out);

@@ -143,7 +143,7 @@ __device__ __forceinline__ void syr2k_item(int item, int t0, int& I, int& J64) {
 
 __global__ void __launch_bounds__(DT_THREADS, 2)
 syr2k_lower_kernel(const __grid_constant__ CUtensorMap mapVZ_km, const __grid_constant__ CUtensorMap mapVZ_kn,
-                   double* __restrict__ A, int64_t lda, int n, int t0, int nitems) {
+                   double* __restrict__ A, int64_t lda, int n, int t0, int nitems, int nkc, int boff, int krows, double sgn) {
   extern __shared__ __align__(128) uint8_t dt_raw[];
   const DtSmem sm = dt_setup(dt_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -153,11 +153,13 @@ syr2k_lower_kernel(const __grid_constant__ CUtensorMap mapVZ_km, const __grid_co
       uint32_t stage = 0, phase = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         int I, J64; syr2k_item(item, t0, I, J64);
-        for (int kc = 0; kc < 4; kc++) {
+        for (int kc = 0; kc < nkc; kc++) {
           dt_mbar_wait(sm.empty + stage, phase ^ 1);
           dt_mbar_expect_tx(sm.full + stage, DT_A_KM_BYTES + DT_B_KN_BYTES);
           dt_tma_2d(sm.A(stage), &mapVZ_km, I * DT_M, kc * DT_KC, sm.full + stage);
-          dt_tma_2d(sm.B(stage), &mapVZ_kn, J64 * DT_N, (kc * DT_KC + 64) & 127, sm.full + stage);
+          int brow = kc * DT_KC + boff;
+          if (brow >= krows) brow -= krows;
+          dt_tma_2d(sm.B(stage), &mapVZ_kn, J64 * DT_N, brow, sm.full + stage);
           if (++stage == DT_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -174,7 +176,7 @@ syr2k_lower_kernel(const __grid_constant__ CUtensorMap mapVZ_km, const __grid_co
   uint32_t stage = 0, phase = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     int I, J64; syr2k_item(item, t0, I, J64);
-    for (int kc = 0; kc < 4; kc++) {
+    for (int kc = 0; kc < nkc; kc++) {
       dt_mbar_wait(sm.full + stage, phase);
       dt_stage_mma<true, true>(sm.A(stage), sm.B(stage), acc, wm, wn, g, q);
       __syncwarp();
@@ -197,7 +199,7 @@ syr2k_lower_kernel(const __grid_constant__ CUtensorMap mapVZ_km, const __grid_co
         for (int tt = 0; tt < 2; tt++)
 #pragma unroll
           for (int u = 0; u < 4; u++) {
-            v[tt][u].x -= acc[t2 + tt][u][0]; v[tt][u].y -= acc[t2 + tt][u][1];
+            v[tt][u].x += sgn * acc[t2 + tt][u][0]; v[tt][u].y += sgn * acc[t2 + tt][u][1];
             *reinterpret_cast<double2*>(A + (size_t)(I * DT_M + wm * 64 + (t2 + tt) * 8 + g) * lda + J64 * DT_N + wn * 32 + u * 8 + q * 2) = v[tt][u];
           }
       } else {
@@ -209,8 +211,8 @@ syr2k_lower_kernel(const __grid_constant__ CUtensorMap mapVZ_km, const __grid_co
             const int col = J64 * DT_N + wn * 32 + u * 8 + q * 2;
             if (row < n && col < n) {
               double* p = A + (size_t)row * lda + col;
-              p[0] -= acc[t2 + tt][u][0];
-              if (col + 1 < n) p[1] -= acc[t2 + tt][u][1];
+              p[0] += sgn * acc[t2 + tt][u][0];
+              if (col + 1 < n) p[1] += sgn * acc[t2 + tt][u][1];
             }
           }
         }
@@ -273,7 +275,22 @@ int launch_syr2k_lower(eb_ctx* c, double* A, int64_t lda, int n, int t0, const d
   if (nt <= 0) return 0;
   const int nitems = nt * (nt + 1);
   const int grid = std::min(nitems, dt_resident_ctas(c));
-  syr2k_lower_kernel<<<grid, DT_THREADS, DT_SMEM, c->stream>>>(km, kn, A, lda, n, t0, nitems);
+  syr2k_lower_kernel<<<grid, DT_THREADS, DT_SMEM, c->stream>>>(km, kn, A, lda, n, t0, nitems, 4, 64, 128, -1.0);
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
+// A (lower 128x64 tiles, n x n, lda) += T^T T with T = [krows][n] (ldt), krows a multiple of 32 (zero rows as padding):
+// the dense-block accumulation that replaces domult_increment_normal (smartpca.c:3531-3561).
+int launch_syrk_lower_add(eb_ctx* c, double* A, int64_t lda, int n, const double* T, int64_t ldt, int krows) {
+  CUtensorMap km, kn;
+  int rc;
+  if ((rc = make_f64_tensormap(&km, T, krows, n, ldt, DT_LD_M, DT_KC))) return rc;
+  if ((rc = make_f64_tensormap(&kn, T, krows, n, ldt, DT_LD_N, DT_KC))) return rc;
+  const int nt = (n + DT_M - 1) / DT_M;
+  const int nitems = nt * (nt + 1);
+  const int grid = std::min(nitems, dt_resident_ctas(c));
+  syr2k_lower_kernel<<<grid, DT_THREADS, DT_SMEM, c->stream>>>(km, kn, A, lda, n, 0, nitems, krows / DT_KC, 0, krows, 1.0);
   EB_CHECK_LAUNCH(c);
   return 0;
 }

@@ -375,6 +375,14 @@ int grm_accumulate(eb_ctx* c) {
   return 0;
 }
 
+// dense path: lower-tile accumulator (c->partial, one plane) -> full symmetric xtx
+int grm_dense_finalize(eb_ctx* c) {
+  const int T32 = c->npad / 32;
+  grm_finalize_kernel<<<T32 * (T32 + 1) / 2, 256, 0, c->stream>>>(c->partial.p, 1, c->npad, c->xtx.p);
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- FP64 microbenchmarks
 __global__ void __launch_bounds__(256) dmma_bench_kernel(double* out, int iters) {
   double acc[16][2];

@@ -85,6 +85,15 @@ typedef struct {
 int eb_grm (eb_ctx *, const eb_grm_opts * opts, int *c0, int *c1, int *nmiss, uint8_t * used,
             double *xmean, double *xfancy, double *y_out, int64_t * nused_out, double *XTX_host);
 
+/* dense path: getcolxz + domult_increment_normal + block_increment_normal (smartpca.c:3129-3216, 3531-3561, 3498-3528),
+ * which the reference takes when usepopsformissing / ldregress make the normalised columns arbitrary FP64 values
+ * (smartpca.c:995-1014).  The host keeps producing tblock (nblock rows of nrows doubles, smartpca.c:1198-1218); each call
+ * adds sum_s x_s x_s^T to the resident accumulator; _end mirrors (symit2), takes the trace and leaves the GRM resident
+ * for eb_eig exactly like eb_grm. */
+int eb_grm_dense_begin (eb_ctx *, int nrows);
+int eb_grm_dense_add (eb_ctx *, const double *tblock /* [nblock][nrows] */ , int nblock);
+int eb_grm_dense_end (eb_ctx *, double *y_out, double *XTX_host /* or NULL */ );
+
 /* multi-GPU (one context per SNP shard): device pointer / leading dimension of the UNNORMALISED partial
  * XTX left by eb_grm_partial, so that the caller's NCCL reduce can run on it in place, and the call that
  * finishes the pass (trace, y) after the reduce. */
@@ -100,6 +109,12 @@ int eb_grm_finish (eb_ctx *, double *y_out, double *XTX_host);
 int eb_eig (eb_ctx *, int nvec, double *lambda, double *evecs);
 /* standalone drop-in with the reference's contract (mat row-major n*n, preserved): include/eigsubs.h:6-7 */
 int eb_eigvecs (eb_ctx *, const double *mat, double *evals, double *evecs, int n, int nvec);
+
+/* drop-in symbols under the reference's own names (include/eigsubs.h:6-7): same contract as eigsubs.c:21,39 (mat
+ * preserved, eigenvalues descending, row i of evecs = vector i, fatal on failure).  eigvecs fills all n vectors for
+ * n <= 2048 and the leading 40 (zeros elsewhere) beyond -- every reference caller reads at most numeigs of them. */
+void eigvecs (double *mat, double *evals, double *evecs, int n);
+void eigvals (double *mat, double *evals, int n);
 
 /* eigensolver selection: key "eig_method" = 0 auto | 1 one-stage | 2 two-stage + subspace iteration;
  * "two_stage_min" = n at which auto switches to 2.  Returns EB_ERR_ARG for an unknown key. */

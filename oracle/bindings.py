@@ -262,3 +262,19 @@ def ref_evec_coords(packed, numindivs, used, xmean, xfancy, evecs, xindex=None, 
                                 ff.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p), ign.ctypes.data_as(C.c_void_p))
     assert rc == 0, rc
     return dict(coords=a, bcoeffs=b, eigscale=es, ffvecs=ff, fxscal=sc, ignored=ign)
+
+
+def port_dense_grm(tblock):
+    tblock = np.ascontiguousarray(tblock, np.float64); ncols, nrows = tblock.shape
+    out = np.empty((nrows, nrows))
+    port().orc_dense_grm(tblock.ctypes.data_as(C.c_void_p), C.c_long(ncols), C.c_int(nrows), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def ref_dense_grm(tblock, blocksize=1024, nthreads=4):
+    tblock = np.ascontiguousarray(tblock, np.float64); ncols, nrows = tblock.shape
+    out = np.zeros((nrows, nrows))
+    rc = ref().refh_dense_grm(tblock.ctypes.data_as(C.c_void_p), C.c_long(ncols), C.c_int(nrows), C.c_int(blocksize), C.c_int(nthreads),
+                              out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return out

@@ -527,3 +527,15 @@ void orc_seteigscale (const double *acoeffs, const double *bcoeffs, int nlist, c
     eigscale[j] = ab / aa;
   }
 }
+
+/* dense path (restates block_increment_normal, smartpca.c:3498-3528, + symit2): XTX = sum_s x_s x_s^T, SNP by SNP in
+ * the reference's order; tblock_all[ncols][nrows]. */
+void orc_dense_grm (const double *tblock_all, long ncols, int nrows, double *XTX)
+{
+  memset (XTX, 0, sizeof (double) * (size_t) nrows * nrows);
+  for (long s = 0; s < ncols; s++) {
+    const double *x = tblock_all + s * nrows;
+    for (int i = 0; i < nrows; i++) { const double xi = x[i]; for (int j = 0; j <= i; j++) XTX[(size_t) i * nrows + j] += xi * x[j]; }
+  }
+  for (int i = 0; i < nrows; i++) for (int j = 0; j < i; j++) XTX[(size_t) j * nrows + i] = XTX[(size_t) i * nrows + j];
+}

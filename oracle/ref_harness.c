@@ -193,3 +193,23 @@ int refh_evec_coords (const unsigned char *packed, long nsnp, long rl, int nind,
   munmap (sh, tot);
   return 0;
 }
+
+/* dense path: the reference's domult_increment_normal (smartpca.c:3531-3561) over consecutive blocks of `blocksize`
+ * columns, then symit2 (smartpca.c:480-508).  XTX_out: nrows*nrows (packed lower triangle while accumulating). */
+int refh_dense_grm (const double *tblock_all, long ncols, int nrows, int blocksize, int nthreads, double *XTX_out)
+{
+  pthread_t threads[MAX_THREADS]; uint32_t thread_ct; long s; double *tb;
+  thread_ct = nthreads < 1 ? 1 : nthreads; if (thread_ct > MAX_THREADS) thread_ct = MAX_THREADS;
+  if (thread_ct > (uint32_t) nrows * 2) { thread_ct = nrows / 2; if (!thread_ct) thread_ct = 1; }
+  triangle_fill (g_thread_start, nrows, thread_ct, 0, 1, 0, 1);
+  vzero (XTX_out, ((long) nrows * (nrows + 1)) / 2);
+  ZALLOC (tb, (long) blocksize * nrows, double);
+  for (s = 0; s < ncols; s += blocksize) {
+    int nb = (int) MIN ((long) blocksize, ncols - s);
+    memcpy (tb, tblock_all + s * nrows, sizeof (double) * (size_t) nb * nrows);
+    domult_increment_normal (threads, thread_ct, XTX_out, tb, nb, nrows);
+  }
+  symit2 (XTX_out, nrows);
+  free (tb);
+  return 0;
+}
