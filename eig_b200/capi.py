@@ -45,7 +45,8 @@ EXPORTS = [
     "eb_reset_launch_count", "eb_upload_packed", "eb_upload_packed_rows", "eb_adopt_packed_device", "eb_synth_packed_device",
     "eb_set_rows", "eb_snp_counts", "eb_indiv_valid_counts", "eb_grm", "eb_grm_partial", "eb_grm_device_ptr", "eb_grm_finish",
     "eb_eig", "eb_eigvecs", "eb_ridoutlier", "eb_pca_full", "eb_fpca", "eb_gauss_matrix", "eb_project", "eb_get_timings",
-    "eb_microbench_fp64", "eb_set_option", "eb_debug_tridiag", "eb_lsqproj", "eb_evec_coords", "eb_grm_dense_begin", "eb_grm_dense_add", "eb_grm_dense_end", "eigvecs", "eigvals",
+    "eb_microbench_fp64", "eb_set_option", "eb_debug_tridiag", "eb_lsqproj", "eb_evec_coords", "eb_pop_counts", "eb_hash_ids", "eb_packed_file_header", "eb_upload_packed_file",
+    "eb_download_packed", "eb_write_eval", "eb_write_evec", "eb_write_grm", "eb_grm_dense_begin", "eb_grm_dense_add", "eb_grm_dense_end", "eigvecs", "eigvals",
 ]
 
 _lib = None
@@ -92,6 +93,38 @@ def ridoutlier(evecs, neigs, thresh=6.0, outliermode=0):
     return bad[:nb].copy(), vecno, score
 
 
+def _strarr(strings):
+    arr = (C.c_char_p * len(strings))(*[s.encode() for s in strings])
+    return arr
+
+
+def hash_ids(ids):
+    return lib().eb_hash_ids(_strarr(list(ids)), C.c_int(len(ids)))
+
+
+def packed_file_header(path):
+    ni = C.c_int(0); ns = C.c_int(0); ih = C.c_int(0); sh = C.c_int(0); rl = C.c_int64(0); fb = C.c_int64(0)
+    _chk(lib().eb_packed_file_header(path.encode(), C.byref(ni), C.byref(ns), C.byref(ih), C.byref(sh), C.byref(rl), C.byref(fb)))
+    return dict(nind=ni.value, nsnp=ns.value, ihash=ih.value, shash=sh.value, rlen=rl.value, file_bytes=fb.value)
+
+
+def write_eval(path, lam):
+    lam = np.ascontiguousarray(lam, np.float64)
+    _chk(lib().eb_write_eval(path.encode(), _p(lam), C.c_int(len(lam))))
+
+
+def write_evec(path, lam, ids, groups, coords, hiprec=False):
+    coords = np.ascontiguousarray(coords, np.float64); k, n = coords.shape
+    lam = np.ascontiguousarray(lam, np.float64)
+    _chk(lib().eb_write_evec(path.encode(), _p(lam), C.c_int(k), _strarr(list(ids)), _strarr(list(groups)), _p(coords), C.c_int(n),
+                             C.c_int(1 if hiprec else 0)))
+
+
+def write_grm(path, xtx, numsnps):
+    xtx = np.ascontiguousarray(xtx, np.float64)
+    _chk(lib().eb_write_grm(path.encode(), _p(xtx), C.c_int(xtx.shape[0]), C.c_int(numsnps)))
+
+
 class Context:
     """One eb_ctx = one GPU."""
 
@@ -121,6 +154,19 @@ class Context:
         _chk(lib().eb_upload_packed(self.h, _p(packed), C.c_int64(self.nsnp), C.c_int64(rlen), C.c_int(numindivs)))
         _chk(lib().eb_sync(self.h))
 
+    def upload_packed_file(self, path, numindivs, nsnp, ihash=None, shash=None, snp_is_x=None, indiv_is_male=None):
+        chk = ihash is not None and shash is not None
+        sx = None if snp_is_x is None else np.ascontiguousarray(snp_is_x, np.uint8)
+        im = None if indiv_is_male is None else np.ascontiguousarray(indiv_is_male, np.uint8)
+        _chk(lib().eb_upload_packed_file(self.h, path.encode(), C.c_int(numindivs), C.c_int64(nsnp), C.c_int(1 if chk else 0),
+                                         C.c_int(ihash if chk else 0), C.c_int(shash if chk else 0), _p(sx), _p(im)))
+        self.nsnp, self.numindivs = nsnp, numindivs
+
+    def download_packed(self, rlen):
+        out = np.empty((self.nsnp, rlen), np.uint8)
+        _chk(lib().eb_download_packed(self.h, _p(out)))
+        return out
+
     def adopt_packed_device(self, dev_ptr, nsnp, pitch, numindivs):
         self.nsnp, self.numindivs = nsnp, numindivs
         _chk(lib().eb_adopt_packed_device(self.h, C.c_void_p(dev_ptr), C.c_int64(nsnp), C.c_int64(pitch), C.c_int(numindivs)))
@@ -142,6 +188,13 @@ class Context:
         c0 = np.empty(self.nsnp, np.int32); c1 = np.empty(self.nsnp, np.int32); nm = np.empty(self.nsnp, np.int32)
         _chk(lib().eb_snp_counts(self.h, _p(c0), _p(c1), _p(nm)))
         return c0, c1, nm
+
+    def pop_counts(self, xtypes, npops):
+        xt = np.ascontiguousarray(xtypes, np.int32)
+        assert len(xt) == self.nrows
+        out = np.empty((self.nsnp, npops, 3), np.int32)
+        _chk(lib().eb_pop_counts(self.h, _p(xt), C.c_int(npops), _p(out)))
+        return out
 
     def indiv_valid_counts(self, snp_keep=None):
         out = np.empty(self.numindivs, np.int32)

@@ -220,6 +220,39 @@ int eb_indiv_valid_counts(eb_ctx* c, const uint8_t* snp_keep, int* nvalid) {
   return 0;
 }
 
+// per-population genotype-class counts over the current PCA rows (the getrawcol + ddd[k] loops of fstcolyy,
+// qpsubs.c:1205-1281, and of the per-population validity passes)
+int eb_pop_counts(eb_ctx* c, const int* xtypes, int npops, int* counts) {
+  int rc;
+  if ((rc = need_rows(c, "eb_pop_counts"))) return rc;
+  if (!xtypes || !counts || npops <= 0) { set_error("eb_pop_counts: bad argument"); return EB_ERR_ARG; }
+  // population-sorted individual list, each segment padded to a multiple of 16 with -1 (gathered as missing)
+  std::vector<int> cnt(npops, 0), seg(npops + 1, 0);
+  for (int i = 0; i < c->nrows; i++) if (xtypes[i] >= 0 && xtypes[i] < npops) cnt[xtypes[i]]++;
+  for (int k = 0; k < npops; k++) seg[k + 1] = seg[k] + (cnt[k] + 15) / 16;
+  const int nwords = std::max(seg[npops], 1);
+  const int64_t wp3 = ((int64_t)nwords * 4 + 15) / 16 * 16;
+  std::vector<int> list((size_t)wp3 * 4, -1), fill(npops, 0);
+  for (int i = 0; i < c->nrows; i++) {
+    const int k = xtypes[i];
+    if (k < 0 || k >= npops) continue;
+    list[(size_t)seg[k] * 16 + fill[k]++] = c->xindex_h[i];
+  }
+  DevBuf<int> list_d, seg_d, out_d;
+  DevBuf<uint8_t> work3;
+  const size_t nout = (size_t)c->nsnp * npops * 3;
+  if ((rc = list_d.ensure(list.size())) || (rc = seg_d.ensure(npops + 1)) || (rc = out_d.ensure(nout)) ||
+      (rc = work3.ensure((size_t)c->mpad * wp3)))
+    return rc;
+  EB_CUDA(cudaMemcpyAsync(list_d.p, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, c->stream));
+  EB_CUDA(cudaMemcpyAsync(seg_d.p, seg.data(), sizeof(int) * (npops + 1), cudaMemcpyHostToDevice, c->stream));
+  if ((rc = launch_gather_into(c, list_d.p, (int)list.size(), work3.p, wp3))) return rc;
+  if ((rc = launch_pop_counts(c, work3.p, wp3, npops, seg_d.p, out_d.p))) return rc;
+  EB_CUDA(cudaMemcpyAsync(counts, out_d.p, sizeof(int) * nout, cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int eb_grm_partial(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* nmiss, uint8_t* used, double* xmean, double* xfancy,
                    int64_t* nused_out) {
   int rc;

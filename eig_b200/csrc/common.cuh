@@ -116,6 +116,7 @@ namespace eb {
 int launch_gather(eb_ctx* c);
 int launch_gather_into(eb_ctx* c, const int* list_d, int nlist, uint8_t* dst, int64_t wpitch);
 int launch_stats(eb_ctx* c, const eb_grm_opts* o);
+int launch_pop_counts(eb_ctx* c, const uint8_t* work3, int64_t wp3, int npops, const int* seg_word0_d, int* out_d);
 int launch_indiv_counts(eb_ctx* c, const uint8_t* keep_d, int* out_d);
 int launch_synth(eb_ctx* c, uint8_t* dst, int64_t nsnp, int64_t pitch, int numindivs, uint64_t seed, int64_t s0,
                  double missing, int npops, double delta);

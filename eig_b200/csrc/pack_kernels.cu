@@ -136,6 +136,43 @@ __global__ void __launch_bounds__(256) snp_stats_kernel(const uint8_t* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------- per-population counts
+// Working matrix gathered in population-sorted order, every population's segment padded to whole 32-bit words (16
+// individuals, pad = code 3).  One warp per SNP; for each population a popcount sweep over its words.
+// out[(s * npops + k) * 3 + g] = number of members of population k with genotype g at SNP s  (fstcolyy's ddd[k],
+// qpsubs.c:1256-1281: c0 = n1 + 2 n2, c1 = n1 + 2 n0; inbreed mode uses the classes directly).
+__global__ void __launch_bounds__(256) pop_counts_kernel(const uint8_t* __restrict__ work, int64_t wpitch, int64_t nsnp, int npops,
+                                                         const int* __restrict__ seg_word0, int* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t s = warp; s < nsnp; s += nwarps) {
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(work + s * wpitch);
+    for (int k = 0; k < npops; k++) {
+      const int w0 = seg_word0[k], w1 = seg_word0[k + 1];
+      int n1 = 0, n2 = 0, n3 = 0;
+      for (int w = w0 + lane; w < w1; w += 32) count_word(__ldg(row + w), n1, n2, n3);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        n3 += __shfl_xor_sync(0xffffffffu, n3, o);
+      }
+      if (lane == 0) {
+        int* o3 = out + ((size_t)s * npops + k) * 3;
+        o3[0] = (w1 - w0) * 16 - n1 - n2 - n3; o3[1] = n1; o3[2] = n2;
+      }
+    }
+  }
+}
+
+int launch_pop_counts(eb_ctx* c, const uint8_t* work3, int64_t wp3, int npops, const int* seg_word0_d, int* out_d) {
+  const int blocks = c->num_sms * 8;
+  pop_counts_kernel<<<blocks, 256, 0, c->stream>>>(work3, wp3, c->nsnp, npops, seg_word0_d, out_d);
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
 int launch_stats(eb_ctx* c, const eb_grm_opts* o) {
   const int warpsPerBlock = 8;
   int64_t blocks = (c->mpad + warpsPerBlock - 1) / warpsPerBlock;

@@ -53,6 +53,26 @@ int eb_adopt_packed_device (eb_ctx *, const void *dev_packed, int64_t nsnp, int6
 int eb_synth_packed_device (eb_ctx *, void *dev_packed, int64_t nsnp, int64_t pitch, int numindivs,
                             uint64_t seed, int64_t s0, double missing, int npops, double delta);
 
+/* PACKEDANCESTRYMAP genotype file -> device slab: inpack(), mcio.c:2769-2879.  The header record is checked with the
+ * reference's own rules and messages (individual / SNP counts, and the two ID hashes when check_hash != 0: hasharr,
+ * admutils.c:651-682, over the .ind / .snp IDs in file order); the payload streams through pinned staging buffers
+ * (disk read of chunk i+1 overlaps the H2D copy of chunk i); male X heterozygotes become missing on the device
+ * (checkxval, mcio.c:1606-1618) when snp_is_x[nsnp] / indiv_is_male[numindivs] are given (NULL = no X rule). */
+int eb_hash_ids (const char *const *ids, int n);
+int eb_packed_file_header (const char *path, int *nind, int *nsnp, int *ihash, int *shash, int64_t * rlen, int64_t * file_bytes);
+int eb_upload_packed_file (eb_ctx *, const char *path, int numindivs, int64_t nsnp, int check_hash, int ihash, int shash,
+                           const uint8_t * snp_is_x, const uint8_t * indiv_is_male);
+int eb_download_packed (eb_ctx *, uint8_t * out /* [nsnp][rlen] */ );
+
+/* output files with the reference's formats: .eval "%12.6f\n" per eigenvalue (smartpca.c:1425-1431); .evec header
+ * "%20s " "#eigvals:" + "%9.3f " per eigenvalue, then per individual "%20s " ID, "%10.4f  " (hiprec: "%12.6f  ") per
+ * coordinate, "%15s\n" population (smartpca.c:1433-1437, 1574-1591); text GRM "a b nsnp %0.6f" scaled to mean
+ * diagonal 1 (dumpgrm, smartpca.c:3770-3805).  coords [numeigs][nout]. */
+int eb_write_eval (const char *path, const double *lambda, int n);
+int eb_write_evec (const char *path, const double *lambda, int numeigs, const char *const *ids, const char *const *groups,
+                   const double *coords, int nout, int hiprec);
+int eb_write_grm (const char *path, const double *XTX, int nrows, int numsnps);
+
 /* rows used = xindex[0..nrows) ascending into 0..numindivs-1 (loadindx, qpsubs.c:202-219).
  * xindex == NULL selects all individuals.  Re-gathers the working matrix on the device. */
 int eb_set_rows (eb_ctx *, const int *xindex, int nrows);
@@ -64,6 +84,12 @@ int eb_snp_counts (eb_ctx *, int *c0, int *c1, int *nmiss);
 /* per individual (all numindivs) non-missing count over SNPs with snp_keep[s] != 0 (NULL = all):
  * numvalidgtallind, admutils.c:1075-1097 */
 int eb_indiv_valid_counts (eb_ctx *, const uint8_t * snp_keep, int *nvalid);
+
+/* per population k (xtypes[row] in 0..npops-1, other values skipped; xtypes indexed like the current rows) and SNP s:
+ * counts[(s*npops + k)*3 + g] = members with genotype g = 0,1,2.  This is the gather + count loop of fstcolyy
+ * (qpsubs.c:1205-1281: ddd[k] = {n1 + 2 n2, n1 + 2 n0}; inbreed mode uses the classes) that dofstnumx
+ * (qpsubs.c:2488-2736) runs for every SNP, and of the per-population validity passes (smartpca.c:844,870). */
+int eb_pop_counts (eb_ctx *, const int *xtypes, int npops, int *counts);
 
 /* -------- GRM accumulation: the region smartpca.c:1088-1236 -------- */
 typedef struct {

@@ -278,3 +278,30 @@ def ref_dense_grm(tblock, blocksize=1024, nthreads=4):
                               out.ctypes.data_as(C.c_void_p))
     assert rc == 0
     return out
+
+
+def port_pop_counts(packed, numindivs, xtypes, npops, xindex=None):
+    nsnp, rlen = packed.shape; xi = _xi(xindex, numindivs); xt = np.ascontiguousarray(xtypes, np.int32)
+    out = np.empty((nsnp, npops, 3), np.int32)
+    port().orc_pop_counts(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen), xi.ctypes.data_as(C.c_void_p),
+                          xt.ctypes.data_as(C.c_void_p), C.c_int(len(xi)), C.c_int(npops), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def port_fstcol(counts):
+    """Fst numerator / denominator matrices per SNP from class counts [nsnp][numeg][3] (qpsubs.c:1303-1340)"""
+    counts = np.ascontiguousarray(counts, np.int32); nsnp, numeg, _ = counts.shape
+    en = np.empty((nsnp, numeg, numeg)); ed = np.empty((nsnp, numeg, numeg))
+    for s in range(nsnp):
+        port().orc_fstcol(counts[s].ctypes.data_as(C.c_void_p), C.c_int(numeg), en[s].ctypes.data_as(C.c_void_p), ed[s].ctypes.data_as(C.c_void_p))
+    return en, ed
+
+
+def ref_fstcol(packed, numindivs, xtypes, numeg, xindex=None):
+    nsnp, rlen = packed.shape; xi = _xi(xindex, numindivs); xt = np.ascontiguousarray(xtypes, np.int32)
+    en = np.empty((nsnp, numeg, numeg)); ed = np.empty((nsnp, numeg, numeg))
+    rc = ref().refh_fstcol(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen), C.c_int(numindivs),
+                           xi.ctypes.data_as(C.c_void_p), xt.ctypes.data_as(C.c_void_p), C.c_int(len(xi)), C.c_int(numeg),
+                           en.ctypes.data_as(C.c_void_p), ed.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return en, ed

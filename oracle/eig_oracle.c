@@ -539,3 +539,39 @@ void orc_dense_grm (const double *tblock_all, long ncols, int nrows, double *XTX
   }
   for (int i = 0; i < nrows; i++) for (int j = 0; j < i; j++) XTX[(size_t) j * nrows + i] = XTX[(size_t) i * nrows + j];
 }
+
+/* per-population genotype-class counts (the counting loop of fstcolyy, qpsubs.c:1256-1281) and the Fst numerator /
+ * denominator of one SNP for every population pair, non-inbreed branch (qpsubs.c:1303-1340).
+ * counts[k*3+g]; estn/estd numeg*numeg with the reference's initial values (0 / -1, diagonal of estd 0). */
+void orc_pop_counts (const uint8_t * packed, long nsnp, long rlen, const int *xindex, const int *xtypes, int nrows, int npops, int *counts)
+{
+  memset (counts, 0, sizeof (int) * (size_t) nsnp * npops * 3);
+  for (long s = 0; s < nsnp; s++)
+    for (int i = 0; i < nrows; i++) {
+      const int k = xtypes[i];
+      if (k < 0 || k >= npops) continue;
+      const int g = gt (packed + s * rlen, xindex[i]);
+      if (g >= 0) counts[((size_t) s * npops + k) * 3 + g]++;
+    }
+}
+void orc_fstcol (const int *cnt /* [numeg][3] */ , int numeg, double *estn, double *estd)
+{
+  for (int i = 0; i < numeg * numeg; i++) { estn[i] = 0.0; estd[i] = -1.0; }
+  for (int a = 0; a < numeg; a++) estd[a * numeg + a] = 0.0;
+  for (int i = 0; i < numeg; i++)
+    for (int j = i + 1; j < numeg; j++) {
+      const double ya = cnt[i * 3 + 1] + 2 * cnt[i * 3 + 2], yb = cnt[i * 3 + 1] + 2 * cnt[i * 3 + 0];
+      const double yaa = cnt[j * 3 + 1] + 2 * cnt[j * 3 + 2], ybb = cnt[j * 3 + 1] + 2 * cnt[j * 3 + 0];
+      const double zz = yaa + ybb, z = ya + yb;
+      if ((z < 1.5) || (zz < 1.5)) continue;
+      double yt = ya + yb;
+      const double p1 = ya / yt, h1 = ya * yb / (yt * (yt - 1.0));
+      yt = yaa + ybb;
+      const double p2 = yaa / yt, h2 = yaa * ybb / (yt * (yt - 1.0));
+      double en = (p1 - p2) * (p1 - p2);
+      en -= h1 / z; en -= h2 / zz;
+      double ed = en; ed += h1; ed += h2;
+      estn[i * numeg + j] = estn[j * numeg + i] = en;
+      estd[i * numeg + j] = estd[j * numeg + i] = ed;
+    }
+}

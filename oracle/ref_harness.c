@@ -213,3 +213,17 @@ int refh_dense_grm (const double *tblock_all, long ncols, int nrows, int blocksi
   free (tb);
   return 0;
 }
+
+/* the reference's fstcolyy (qpsubs.c:1205-1346) for every SNP: estn/estd [nsnp][numeg*numeg] */
+int refh_fstcol (const unsigned char *packed, long nsnp, long rl, int nind, const int *xindex_in, const int *xtypes_in, int nrows, int numeg,
+                 double *estn, double *estd)
+{
+  long s; int *xidx, *xt;
+  hbuild (packed, nsnp, rl, nind);
+  ZALLOC (xidx, nrows, int); ZALLOC (xt, nrows, int);
+  memcpy (xidx, xindex_in, sizeof (int) * nrows); memcpy (xt, xtypes_in, sizeof (int) * nrows);
+  setinbreed (NO);
+  for (s = 0; s < nsnp; s++) fstcolyy (estn + s * numeg * numeg, estd + s * numeg * numeg, hsnpp[s], xidx, xt, nrows, numeg);
+  free (xidx); free (xt); hfree ();
+  return 0;
+}

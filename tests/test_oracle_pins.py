@@ -175,3 +175,17 @@ def test_port_lsqproj_against_reference():
     assert np.abs(ff - r["ffvecs"]).max() < 1e-11 and np.abs(sc - r["fxscal"]).max() < 1e-15
     assert np.abs(es - r["eigscale"]).max() <= 1e-12 * np.abs(es).max()
     assert np.abs(c - r["coords"]).max() < 1e-13
+
+
+def test_port_pop_counts_and_fst_against_reference():
+    """pin of orc_pop_counts + orc_fstcol: the reference's fstcolyy (qpsubs.c:1205-1346), bit for bit"""
+    if ob.ref() is None:
+        pytest.skip("oracle/_ref not built")
+    from eig_b200 import synth
+    nsnp, nind, npops = 300, 130, 4
+    P = synth.pack(synth.genotypes(5, nsnp, nind, missing=0.12, npops=npops, delta=0.3))
+    xi = np.arange(nind, dtype=np.int32)[3:]
+    xt = synth.pop_of(nind, npops)[xi].astype(np.int32); xt[2] = -1; xt[9] = npops + 3
+    en, ed = ob.port_fstcol(ob.port_pop_counts(P, nind, xt, npops, xindex=xi))
+    ren, red = ob.ref_fstcol(P, nind, xt, npops, xindex=xi)
+    assert np.array_equal(en, ren) and np.array_equal(ed, red)
