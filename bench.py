@@ -10,7 +10,9 @@ per-SNP allele counts + normalisation + drop rule, the packed->FP64 symmetric ra
   e2e   : the same pass through the C-ABI with HOST buffers (eb_upload_packed from pinned memory, eb_set_rows,
           eb_grm, per-SNP outputs copied back) -- H2D/D2H inside the timed region
 N>1: SNPs shard across ranks (each rank owns its own 600k-SNP slab: weak scaling); the one exchange step is the
-NCCL reduce of the partial N x N FP64 GRMs over NVLink, inside the timed region.
+reduction of the partial N x N FP64 GRMs, fused with the split-K finalize/mirror in the library's own kernel over peer
+memory (NVLink; CUDA IPC between the torchrun ranks), inside the timed region.  --reduce nccl (or a box without IPC)
+uses an NCCL all-reduce on the library's buffer instead and says so in config.parallelism.
 The reference arm (--impl reference) times the reference's own CPU code for the same region (oracle/_ref, built from
 /root/reference by oracle/Makefile) with all host threads on a bounded SNP sample of the same workload.
 """
@@ -148,6 +150,25 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # exchange step: the library's peer-memory kernel unless asked otherwise / unavailable on this box (all ranks agree)
+    reduce_mode = "none"
+    if world > 1:
+        reduce_mode = args.reduce
+        if reduce_mode == "peer":
+            ok = 1.0
+            try:
+                ctx.set_comm(parallel.TorchComm(device=dev))
+                chk = ctx.peer_allreduce_test(np.full(64, float(rank + 1)))
+                ok = 1.0 if np.all(chk == world * (world + 1) / 2) else 0.0
+            except capi.EigB200Error as ex:
+                print("rank %d: peer path unavailable: %s" % (rank, ex), file=sys.stderr)
+                ok = 0.0
+            t = torch.tensor([ok], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if t.item() < 1.0:
+                ctx.set_comm(None)
+                reduce_mode = "nccl"
+
     def reduce_partials():
         ptr, ld, n = ctx.grm_device_ptr()
         t = parallel.device_view(ptr, (ld, ld), dev)
@@ -155,7 +176,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def step_resident():
-        if world == 1:
+        if world == 1 or reduce_mode == "peer":
             return ctx.grm(want_snp=False)
         r = ctx.grm(want_snp=False, partial=True)
         reduce_partials()
@@ -165,7 +186,7 @@ def run_b200(args):
     def step_e2e():
         ctx.upload_packed(host_np, nind)
         ctx.set_rows(None)
-        if world == 1:
+        if world == 1 or reduce_mode == "peer":
             return ctx.grm(want_snp=True)
         r = ctx.grm(want_snp=True, partial=True)
         reduce_partials()
@@ -201,14 +222,17 @@ def run_b200(args):
     ctx.adopt_packed_device(slab.data_ptr(), nsnp, rl, nind)
     ctx.set_rows(None)
     ms, r, kern, launches, clocks = timed(step_resident, steps, warmup, sample_clocks=True)
-    used = torch.tensor([r["nused"]], dtype=torch.float64, device=dev)
+    own_used = int(ctx.snp_used_count())           # this shard's SNPs that entered XTX
+    used = torch.tensor([own_used], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(used)
+    if reduce_mode == "peer":
+        assert int(used.item()) == int(r["nused"]), "library total of used SNPs disagrees with the per-shard sum"
     units = float(used.item()) * float(nind) ** 2
     ms_per_step = ms / steps
     value = units / (ms_per_step * 1e-3)
     grm_ms = float(np.mean([k["grm_ms"] for k in kern]))
-    flops = float(nind) * (nind + 1.0) * r["nused"]
+    flops = float(nind) * (nind + 1.0) * own_used
     achieved = flops / (grm_ms * 1e-3) / 1e12
 
     # e2e arm (host buffers through the C-ABI)
@@ -256,7 +280,8 @@ def run_b200(args):
                 cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config({"parallelism": "snp-shard x%d + nccl all_reduce of partial GRM" % world if world > 1 else "single GPU",
+                "config": workload_config({"parallelism": ("snp-shard x%d + %s" % (world, "fused finalize+reduce kernel over peer memory (CUDA IPC / NVLink)" if reduce_mode == "peer"
+                                                            else "nccl all_reduce of partial GRM")) if world > 1 else "single GPU",
                                            "nsplit": kern[-1]["nsplit"]}),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ems / esteps},
@@ -283,6 +308,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"], help="N>1 exchange step: library peer-memory kernel | NCCL all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -40,6 +40,15 @@ class Timings(C.Structure):
                 ("chfsi_matvecs", C.c_int)]
 
 
+ALLGATHER_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
+BARRIER_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+class Comm(C.Structure):
+    """eb_comm: host-side plumbing of the SNP-sharded path (include/eigb200.h)."""
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("allgather_host", ALLGATHER_CB), ("barrier", BARRIER_CB), ("user", C.c_void_p)]
+
+
 EXPORTS = [
     "eb_last_error", "eb_version", "eb_create", "eb_destroy", "eb_device_count", "eb_stream", "eb_sync", "eb_launch_count",
     "eb_reset_launch_count", "eb_upload_packed", "eb_upload_packed_rows", "eb_adopt_packed_device", "eb_synth_packed_device",
@@ -47,6 +56,7 @@ EXPORTS = [
     "eb_eig", "eb_eigvecs", "eb_ridoutlier", "eb_pca_full", "eb_fpca", "eb_gauss_matrix", "eb_project", "eb_get_timings",
     "eb_microbench_fp64", "eb_set_option", "eb_debug_tridiag", "eb_lsqproj", "eb_evec_coords", "eb_pop_counts", "eb_hash_ids", "eb_packed_file_header", "eb_upload_packed_file",
     "eb_download_packed", "eb_write_eval", "eb_write_evec", "eb_write_grm", "eb_grm_dense_begin", "eb_grm_dense_add", "eb_grm_dense_end", "eigvecs", "eigvals",
+    "eb_set_comm", "eb_peer_allreduce_test", "eb_snp_used_count",
 ]
 
 _lib = None
@@ -146,6 +156,37 @@ class Context:
         except Exception:
             pass
 
+    # ---- multi-GPU
+    def set_comm(self, comm):
+        """comm: an object with .rank, .world, .allgather_host(src_ptr, dst_ptr, nbytes) and .barrier() (parallel.TorchComm),
+        or None for single-GPU operation."""
+        if comm is None:
+            _chk(lib().eb_set_comm(self.h, None)); self._comm = None
+            return
+
+        def _ag(user, src, dst, nbytes):
+            try:
+                comm.allgather_host(src, dst, nbytes); return 0
+            except Exception as ex:  # surfaced by the library as EB_ERR_STATE
+                import sys
+                print("eb_comm.allgather_host: %r" % (ex,), file=sys.stderr); return 1
+
+        def _bar(user):
+            try:
+                comm.barrier(); return 0
+            except Exception as ex:
+                import sys
+                print("eb_comm.barrier: %r" % (ex,), file=sys.stderr); return 1
+
+        st = Comm(comm.rank, comm.world, ALLGATHER_CB(_ag), BARRIER_CB(_bar), None)
+        self._comm = (st, comm)          # keep the callbacks alive as long as the context uses them
+        _chk(lib().eb_set_comm(self.h, C.byref(st)))
+
+    def peer_allreduce_test(self, vec):
+        v = np.ascontiguousarray(vec, np.float64).copy()
+        _chk(lib().eb_peer_allreduce_test(self.h, _p(v), C.c_int64(v.size)))
+        return v
+
     # ---- store
     def upload_packed(self, packed, numindivs):
         packed = np.ascontiguousarray(packed, np.uint8)
@@ -230,6 +271,11 @@ class Context:
                 r["XTX"] = xtx
         r["nused"] = nused.value
         return r
+
+    def snp_used_count(self):
+        """SNPs of THIS context's shard that entered XTX in the last GRM pass"""
+        lib().eb_snp_used_count.restype = C.c_int64
+        return lib().eb_snp_used_count(self.h)
 
     def grm_device_ptr(self):
         ld = C.c_int64(0); n = C.c_int64(0)

@@ -253,8 +253,8 @@ int eb_pop_counts(eb_ctx* c, const int* xtypes, int npops, int* counts) {
   return 0;
 }
 
-int eb_grm_partial(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* nmiss, uint8_t* used, double* xmean, double* xfancy,
-                   int64_t* nused_out) {
+static int grm_pass(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* nmiss, uint8_t* used, double* xmean, double* xfancy,
+                    int64_t* nused_out, bool peer) {
   int rc;
   if ((rc = need_rows(c, "eb_grm"))) return rc;
   if (!opts) { set_error("eb_grm: opts is NULL"); return EB_ERR_ARG; }
@@ -263,13 +263,31 @@ int eb_grm_partial(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* nm
   EB_CUDA(cudaEventRecord(c->ev[0], c->stream));
   if ((rc = launch_stats(c, opts))) return rc;
   EB_CUDA(cudaEventRecord(c->ev[1], c->stream));
-  if ((rc = grm_accumulate(c))) return rc;
+  if ((rc = grm_accumulate(c, !peer))) return rc;
   if ((rc = fetch_snp_outputs(c, c0, c1, nmiss, used, xmean, xfancy, nused_out))) return rc;
   cudaEventElapsedTime(&c->tm.stats_ms, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->tm.grm_ms, c->ev[2], c->ev[3]);
+  if (peer) {
+    // exchange step: split-K plane sum + mirror fused with the cross-GPU reduction over peer memory (peer.cu)
+    if ((rc = peer_grm_finalize(c))) return rc;
+    std::vector<long long> all(c->comm.world);
+    long long mine = c->nused;
+    if ((rc = peer_allgather_host(c, &mine, all.data(), sizeof(long long)))) return rc;
+    long long tot = 0;
+    for (long long v : all) tot += v;
+    c->nused_total = tot;
+    if (nused_out) *nused_out = tot;
+  } else {
+    c->nused_total = c->nused;
+  }
   cudaEventElapsedTime(&c->tm.finalize_ms, c->ev[3], c->ev[4]);
   c->grm_valid = true;
   return 0;
+}
+
+int eb_grm_partial(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* nmiss, uint8_t* used, double* xmean, double* xfancy,
+                   int64_t* nused_out) {
+  return grm_pass(c, opts, c0, c1, nmiss, used, xmean, xfancy, nused_out, false);
 }
 
 void* eb_grm_device_ptr(eb_ctx* c, int64_t* ld, int64_t* n) {
@@ -309,7 +327,7 @@ int eb_grm_finish(eb_ctx* c, double* y_out, double* XTX_host) {
 int eb_grm(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* nmiss, uint8_t* used, double* xmean, double* xfancy,
            double* y_out, int64_t* nused_out, double* XTX_host) {
   int rc;
-  if ((rc = eb_grm_partial(c, opts, c0, c1, nmiss, used, xmean, xfancy, nused_out))) return rc;
+  if ((rc = grm_pass(c, opts, c0, c1, nmiss, used, xmean, xfancy, nused_out, c && c->has_comm))) return rc;
   return eb_grm_finish(c, y_out, XTX_host);
 }
 
@@ -518,6 +536,16 @@ int eb_pca_full(eb_ctx* c, const eb_pca_opts* o, int* xindex_io, int nrows, doub
       const int neigs = std::min(o->numoutleigs, n - 1);                   // smartpca.c:1249
       nbad = eb_ridoutlier(ev.data(), n, neigs, o->outlthresh, outmode, bad.data(), vecno.data(), score.data());
     }
+    if (c->has_comm) {
+      // every rank holds the same reduced GRM bit for bit, so the decisions must agree; a mismatch would desynchronise
+      // the collective passes that follow -- fail loudly instead
+      std::vector<long long> all((size_t)2 * c->comm.world);
+      long long mine[2] = {nbad, 0};
+      for (int b = 0; b < nbad; b++) mine[1] = mine[1] * 1000003ll + bad[b];
+      if ((rc = peer_allgather_host(c, mine, all.data(), sizeof(mine)))) return rc;
+      for (int r = 0; r < c->comm.world; r++)
+        if (all[2 * r] != mine[0] || all[2 * r + 1] != mine[1]) { set_error("eb_pca_full: ranks disagree on the outlier list (pass %d)", iter); return EB_ERR_STATE; }
+    }
     if (nbad == 0) {
       if (two) {
         t0 = now_s();
@@ -605,6 +633,8 @@ int eb_evec_coords(eb_ctx* c, const double* evecs, int numeigs, const int* indiv
   if (ok) memcpy(ok, okv.data(), nindiv);
   return 0;
 }
+
+int64_t eb_snp_used_count(eb_ctx* c) { return c ? c->nused : 0; }
 
 int eb_get_timings(eb_ctx* c, eb_timings* t) {
   if (!c || !t) return EB_ERR_ARG;

@@ -35,9 +35,10 @@ template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  std::vector<void*>* defer = nullptr;   // exported to peers: the old allocation is freed only after they unmapped it
   int ensure(size_t count) {
     if (count <= n && p) return 0;
-    if (p) cudaFree(p);
+    if (p) { if (defer) defer->push_back(p); else cudaFree(p); }
     p = nullptr; n = 0;
     if (count == 0) return 0;
     cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
@@ -47,6 +48,22 @@ struct DevBuf {
   }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
   ~DevBuf() { release(); }
+};
+
+// multi-GPU exchange over peer memory (peer.cu)
+constexpr int EB_MAX_WORLD = 16;
+enum { PEER_SLOT_PARTIAL = 0, PEER_SLOT_XTX = 1, PEER_SLOT_A = 2, PEER_SLOT_B = 3, PEER_SLOT_C = 4, PEER_SLOT_T = 5, PEER_SLOTS = 6 };
+struct PeerRecord {             // what a rank publishes about one exported allocation
+  unsigned char handle[64];     // cudaIpcMemHandle_t
+  uint64_t ptr, bytes;          // device address in the owner's process, size of the allocation
+  int64_t pid;
+  int32_t device, aux;          // aux: slot-specific (GRM planes: nsplit; XTX: npad; all-reduce: element count)
+};
+struct PeerRegion {
+  std::vector<PeerRecord> rec;
+  std::vector<void*> mapped;    // this process's address of every rank's buffer
+  std::vector<bool> opened;     // mapped through cudaIpcOpenMemHandle (must be closed)
+  std::vector<void*> graveyard; // my superseded allocations of this slot, freed once every peer has re-mapped
 };
 
 constexpr int TILE = 128;       // GRM tile edge in individuals (32 packed bytes)
@@ -94,7 +111,8 @@ struct eb_ctx {
   int nsplit = 1;
   bool grm_valid = false;
   double y = 0.0;                 // trace/(nrows-1)
-  int64_t nused = 0;
+  int64_t nused = 0;              // SNPs of THIS shard that entered XTX
+  int64_t nused_total = 0;        // over all shards (== nused without a communicator)
 
   // eigensolver workspace
   eb::DevBuf<double> eigA;        // npad*npad working copy (reflectors end up in its lower part)
@@ -106,6 +124,13 @@ struct eb_ctx {
   double* dbg_band_h = nullptr;    // eb_debug_tridiag only
   int opt_eig_method = 0;          // 0 auto, 1 one-stage (dsytrd-style), 2 two-stage + subspace iteration
   int opt_two_stage_min = 1536;    // auto: n at which the two-stage path takes over
+
+  // multi-GPU (peer.cu)
+  eb_comm comm = {0, 1, nullptr, nullptr, nullptr};
+  bool has_comm = false;
+  eb::PeerRegion peer[eb::PEER_SLOTS];
+  eb::DevBuf<double> peer_scratch;
+  eb::DevBuf<double> fpG, fpB, fpS;   // fastmode buffers that take part in an exchange (persistent: peers map them)
 
   eb_timings tm = {};
   cudaEvent_t ev[12] = {};
@@ -121,7 +146,7 @@ int launch_indiv_counts(eb_ctx* c, const uint8_t* keep_d, int* out_d);
 int launch_synth(eb_ctx* c, uint8_t* dst, int64_t nsnp, int64_t pitch, int numindivs, uint64_t seed, int64_t s0,
                  double missing, int npops, double delta);
 // grm_kernel.cu
-int grm_accumulate(eb_ctx* c);   // work+table -> xtx (full symmetric, unnormalised), trace
+int grm_accumulate(eb_ctx* c, bool finalize_local = true);   // work+table -> split-K planes [-> xtx (full symmetric, unnormalised)]
 int grm_trace(eb_ctx* c);        // recompute trace_d / y from xtx
 int microbench_fp64(eb_ctx* c, double* dmma, double* dfma);
 // eig_kernels.cu
@@ -139,4 +164,12 @@ int fpca_run(eb_ctx* c, int fancynorm, int altnormstyle, size_t K, size_t L, siz
 int project_run(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, double* fxvecs, double* fxscal);
 int lsqproj_run(eb_ctx* c, const int* indiv, int nlist, const double* ffvecs, const double* fxscal, int k, double* acoeffs, double* bcoeffs,
                 int* nvalid, uint8_t* ok);
+// peer.cu
+int peer_allgather_host(eb_ctx* c, const void* src, void* dst, int64_t bytes);
+int peer_exchange(eb_ctx* c, int slot, void* local, size_t bytes, int aux);
+int peer_grm_finalize(eb_ctx* c);
+int peer_allreduce(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64_t count);
+void peer_release(eb_ctx* c);
+int peer_bury(eb_ctx* c);        // collective: barrier, then free superseded exported allocations
+
 }  // namespace eb

@@ -309,65 +309,141 @@ static int qr_orthonormal_rows(eb_ctx* c, double* At, int64_t ld, int64_t len, i
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ TSQR pieces (SNP-sharded fastmode)
+// St[l][col0 + j] = R[j][l] of the local QR (At after qr_reflector: R above the diagonal in place, diagonal in diag)
+__global__ void extract_r_kernel(const double* __restrict__ At, int64_t ld, const double* __restrict__ diag, int ncol,
+                                 double* __restrict__ St, int64_t lds, int col0) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, l = blockIdx.y;
+  if (j >= ncol) return;
+  St[(size_t)l * lds + col0 + j] = j < l ? At[(size_t)l * ld + j] : (j == l ? diag[l] : 0.0);
+}
+
+// Out[l][s] = sum_j C[l][j] In[j][s]   (C: ncol x ncol with leading dimension ldc; In/Out: ncol rows of length len)
+__global__ void __launch_bounds__(256) small_left_mult_kernel(const double* __restrict__ C, int64_t ldc, const double* __restrict__ In,
+                                                              int64_t ldi, double* __restrict__ Out, int64_t ldo, int ncol, int64_t len) {
+  extern __shared__ double Cs[];          // [8][ncol]
+  const int l0 = blockIdx.y * 8;
+  for (int idx = threadIdx.x; idx < 8 * ncol; idx += blockDim.x) {
+    const int ll = idx / ncol, j = idx - ll * ncol;
+    Cs[idx] = l0 + ll < ncol ? C[(size_t)(l0 + ll) * ldc + j] : 0.0;
+  }
+  __syncthreads();
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= len) return;
+  double acc[8];
+#pragma unroll
+  for (int ll = 0; ll < 8; ll++) acc[ll] = 0.0;
+  for (int j = 0; j < ncol; j++) {
+    const double x = In[(size_t)j * ldi + s];
+#pragma unroll
+    for (int ll = 0; ll < 8; ll++) acc[ll] = fma(Cs[ll * ncol + j], x, acc[ll]);
+  }
+#pragma unroll
+  for (int ll = 0; ll < 8; ll++)
+    if (l0 + ll < ncol) Out[(size_t)(l0 + ll) * ldo + s] = acc[ll];
+}
+
 // ------------------------------------------------------------------------------------------ fastmode driver
+// With a communicator (eb_set_comm) the SNPs of X are sharded over the ranks: Q_i = X G is local (the rows of
+// Q live with the shard), G = X^T Q_i / m and B = X^T Q are sums of per-shard partials -> one in-place all-reduce over
+// peer memory each, and the orthonormalisation of the row-sharded sketch is a TSQR (local Householder QR, all-reduce of
+// the stacked cw x cw R factors, QR of the stack, Q_g <- U_g U2_g).  Everything after B is replicated.
 int fpca_run(eb_ctx* c, int fancynorm, int altnormstyle, size_t K, size_t L, size_t I, long seed, double* eval, double* evec) {
   int rc;
   const int64_t m = c->nsnp, mpad = c->mpad;
   const int n = c->nrows, npad = c->npad;
   const int cw = (int)((I + 1) * L);
-  if ((int64_t)cw > m || cw > n) { set_error("eb_fpca: (I+1)*L = %d exceeds the matrix dimensions (%lld x %d)", cw, (long long)m, n); return EB_ERR_ARG; }
+  const bool shard = c->has_comm;
+  const int W = shard ? c->comm.world : 1, me = shard ? c->comm.rank : 0;
+  int64_t m_total = m;
+  if (shard) {
+    std::vector<long long> all(W);
+    long long mine[1] = {(long long)m};
+    if ((rc = peer_allgather_host(c, mine, all.data(), sizeof(long long)))) return rc;
+    m_total = 0;
+    for (long long v : all) m_total += v;
+  }
+  if ((int64_t)cw > m || cw > n) {
+    set_error("eb_fpca: (I+1)*L = %d exceeds the matrix dimensions (%lld SNPs%s x %d)", cw, (long long)m, shard ? " in this shard" : "", n);
+    return EB_ERR_ARG;
+  }
   // per-SNP statistics over the current rows (no drop rule: every uploaded SNP stays a row of X, gval.c:56-86)
   eb_grm_opts o = {fancynorm, altnormstyle, 0, 2147483647, nullptr, nullptr};
   if ((rc = launch_stats(c, &o))) return rc;
   c->grm_valid = false;
-  DevBuf<double> ftab, Gt, Qt, Ut, Bt, tau, diag, gram, uk;
-  if ((rc = ftab.ensure((size_t)mpad * 4)) || (rc = Gt.ensure((size_t)L * npad)) || (rc = Qt.ensure((size_t)cw * mpad)) ||
-      (rc = Ut.ensure((size_t)cw * mpad)) || (rc = Bt.ensure((size_t)cw * npad)) || (rc = tau.ensure(cw)) || (rc = diag.ensure(cw)) ||
+  DevBuf<double> ftab, Qt, Ut, tau, diag, gram, uk, U2t;
+  const int64_t lds = ((int64_t)W * cw + 1) & ~1ll;
+  if ((rc = ftab.ensure((size_t)mpad * 4)) || (rc = c->fpG.ensure((size_t)L * npad)) || (rc = Qt.ensure((size_t)cw * mpad)) ||
+      (rc = Ut.ensure((size_t)cw * mpad)) || (rc = c->fpB.ensure((size_t)cw * npad)) || (rc = tau.ensure(cw)) || (rc = diag.ensure(cw)) ||
       (rc = gram.ensure((size_t)cw * cw)) || (rc = uk.ensure((size_t)K * n)))
     return rc;
+  if (shard && ((rc = c->fpS.ensure((size_t)cw * lds)) || (rc = U2t.ensure((size_t)cw * lds)))) return rc;
+  double* Gt = c->fpG.p;
+  double* Bt = c->fpB.p;
   fpca_table_kernel<<<(unsigned)((mpad + 255) / 256), 256, 0, c->stream>>>(m, mpad, c->xmean_d.p, c->xfancy_d.p, c->nmiss_d.p, ftab.p);
   EB_CHECK_LAUNCH(c);
-  // G1 <- seeded Gaussians (host RNG, bit-exact with kjg_gsl.c:145-186), uploaded transposed
+  // G1 <- seeded Gaussians (host RNG, bit-exact with kjg_gsl.c:145-186), uploaded transposed; identical on every rank
   {
     std::vector<double> G((size_t)n * L), T((size_t)L * npad, 0.0);
     eb_gauss_matrix(seed, (size_t)n, L, G.data());
     for (int i = 0; i < n; i++) for (size_t l = 0; l < L; l++) T[l * npad + i] = G[(size_t)i * L + l];
-    EB_CUDA(cudaMemcpyAsync(Gt.p, T.data(), sizeof(double) * T.size(), cudaMemcpyHostToDevice, c->stream));
+    EB_CUDA(cudaMemcpyAsync(Gt, T.data(), sizeof(double) * T.size(), cudaMemcpyHostToDevice, c->stream));
     EB_CUDA(cudaStreamSynchronize(c->stream));
   }
   EB_CUDA(cudaMemsetAsync(Qt.p, 0, sizeof(double) * (size_t)cw * mpad, c->stream));
-  const double inv_m = 1.0 / (double)m;
+  const double inv_m = 1.0 / (double)m_total;
   for (size_t it = 0; it <= I; it++) {
     double* Qi = Qt.p + (size_t)it * L * mpad;
-    if ((rc = launch_packed_gemm<MODE_XA>(c, ftab.p, Gt.p, npad, Qi, mpad, (int)L, 1.0))) return rc;      // Q_i = X G       (kjg_fpca.c:121,148)
+    if ((rc = launch_packed_gemm<MODE_XA>(c, ftab.p, Gt, npad, Qi, mpad, (int)L, 1.0))) return rc;      // Q_i = X G       (kjg_fpca.c:121,148)
     if (it == I) break;
-    if ((rc = launch_packed_gemm<MODE_XTB>(c, ftab.p, Qi, mpad, Gt.p, npad, (int)L, inv_m))) return rc;    // G = X^T Q_i / m (kjg_fpca.c:123,53)
+    if ((rc = launch_packed_gemm<MODE_XTB>(c, ftab.p, Qi, mpad, Gt, npad, (int)L, inv_m))) return rc;    // G = X^T Q_i / m (kjg_fpca.c:123,53)
+    if (shard && (rc = peer_allreduce(c, PEER_SLOT_A, Gt, c->fpG.n, (int64_t)L * npad))) return rc;
   }
   // Q <- orthonormal basis of its column span (kjg_fpca.c:63-71 keeps U of the SVD; any orthonormal basis of the same
   // span gives the same B B^T and therefore the same leading singular triplets)
   if ((rc = qr_orthonormal_rows(c, Qt.p, mpad, m, cw, Ut.p, tau.p, diag.p))) return rc;
+  const double* Qfinal = Ut.p;
+  if (shard) {
+    double* St = c->fpS.p;
+    EB_CUDA(cudaMemsetAsync(St, 0, sizeof(double) * (size_t)cw * lds, c->stream));
+    {
+      dim3 grid((cw + 127) / 128, cw);
+      extract_r_kernel<<<grid, 128, 0, c->stream>>>(Qt.p, mpad, diag.p, cw, St, lds, me * cw);
+      EB_CHECK_LAUNCH(c);
+    }
+    if ((rc = peer_allreduce(c, PEER_SLOT_C, St, c->fpS.n, (int64_t)cw * lds))) return rc;     // every rank: the stacked R factors
+    if ((rc = qr_orthonormal_rows(c, St, lds, (int64_t)W * cw, cw, U2t.p, tau.p, diag.p))) return rc;
+    {
+      dim3 grid((unsigned)((m + 255) / 256), (cw + 7) / 8);
+      small_left_mult_kernel<<<grid, 256, sizeof(double) * 8 * cw, c->stream>>>(U2t.p + (size_t)me * cw, lds, Ut.p, mpad, Qt.p, mpad, cw, m);
+      EB_CHECK_LAUNCH(c);
+    }
+    Qfinal = Qt.p;       // the reflectors are no longer needed; pad columns [m, mpad) meet all-zero table rows in X^T Q
+  }
   // B = X^T Q   (kjg_fpca.c:79-80)
-  if ((rc = launch_packed_gemm<MODE_XTB>(c, ftab.p, Ut.p, mpad, Bt.p, npad, cw, 1.0))) return rc;
+  if ((rc = launch_packed_gemm<MODE_XTB>(c, ftab.p, Qfinal, mpad, Bt, npad, cw, 1.0))) return rc;
+  if (shard && (rc = peer_allreduce(c, PEER_SLOT_B, Bt, c->fpB.n, (int64_t)cw * npad))) return rc;
   // leading K left singular vectors / values of B through the cw x cw Gram matrix
   {
     dim3 grid(cw, cw);
-    gram_rows_kernel<<<grid, 256, 0, c->stream>>>(Bt.p, npad, n, cw, gram.p);
+    gram_rows_kernel<<<grid, 256, 0, c->stream>>>(Bt, npad, n, cw, gram.p);
     EB_CHECK_LAUNCH(c);
   }
   std::vector<double> lam(cw), V((size_t)K * cw);
   if ((rc = eig_resident(c, gram.p, cw, cw, 1.0, (int)K, lam.data(), V.data()))) return rc;
   {
     dim3 grid((n + 255) / 256, (unsigned)K);
-    left_vectors_kernel<<<grid, 256, 0, c->stream>>>(Bt.p, npad, n, cw, c->zvec_d.p, c->lambda_d.p, (int)K, uk.p);
+    left_vectors_kernel<<<grid, 256, 0, c->stream>>>(Bt, npad, n, cw, c->zvec_d.p, c->lambda_d.p, (int)K, uk.p);
     EB_CHECK_LAUNCH(c);
   }
   std::vector<double> U((size_t)K * n);
   EB_CUDA(cudaMemcpyAsync(U.data(), uk.p, sizeof(double) * U.size(), cudaMemcpyDeviceToHost, c->stream));
   EB_CUDA(cudaStreamSynchronize(c->stream));
   for (size_t k = 0; k < K; k++) {
-    eval[k] = lam[k] * (1.0 / (double)m);                      // S^2 / m, kjg_fpca.c:91-95
+    eval[k] = lam[k] * (1.0 / (double)m_total);                // S^2 / m, kjg_fpca.c:91-95
     for (int i = 0; i < n; i++) evec[(size_t)i * K + k] = U[k * n + i];
   }
+  if (shard && (rc = peer_bury(c))) return rc;
   return 0;
 }
 

@@ -331,7 +331,7 @@ int grm_trace(eb_ctx* c) {
   return 0;
 }
 
-int grm_accumulate(eb_ctx* c) {
+int grm_accumulate(eb_ctx* c, bool finalize_local) {
   const int T = c->npad / TILE;
   const int ntri = T * (T + 1) / 2;
   const int nkb = (int)(c->mpad / KT);
@@ -367,11 +367,12 @@ int grm_accumulate(eb_ctx* c) {
     grm_syrk_kernel<2, 4, 8, 4, 2><<<grid, GRM_THREADS, GRM_SMEM, c->stream>>>(map, c->table_d.p, c->partial.p, c->npad, c->nrows, ntri, nsplit, nkb);
   EB_CHECK_LAUNCH(c);
   EB_CUDA(cudaEventRecord(c->ev[3], c->stream));
+  c->tm.grm_launches = 2;
+  if (!finalize_local) return 0;       // multi-GPU: peer_grm_finalize() sums the planes of every rank (peer.cu)
   const int T32 = c->npad / 32;
   grm_finalize_kernel<<<T32 * (T32 + 1) / 2, 256, 0, c->stream>>>(c->partial.p, nsplit, c->npad, c->xtx.p);
   EB_CHECK_LAUNCH(c);
   EB_CUDA(cudaEventRecord(c->ev[4], c->stream));
-  c->tm.grm_launches = 2;
   return 0;
 }
 

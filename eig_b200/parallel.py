@@ -42,6 +42,40 @@ def allreduce_numpy_sum(a, group=None):
     return t.numpy()
 
 
+class TorchComm:
+    """eb_comm plumbing on top of torch.distributed: an all-gather of small host records and a barrier.  With the nccl
+    backend the records travel through a device staging tensor; with gloo they stay on the host.  Nothing else of the
+    sharded path goes through torch: the reductions themselves are the library's kernels over peer memory."""
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed as dist
+        self.group, self.device = group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.on_device = dist.get_backend(group) == "nccl"
+
+    def allgather_host(self, src_ptr, dst_ptr, nbytes):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        src = torch.frombuffer((ctypes.c_ubyte * nbytes).from_address(src_ptr), dtype=torch.uint8).clone()
+        if self.on_device:
+            src = src.to(self.device)
+        out = torch.empty(self.world * nbytes, dtype=torch.uint8, device=src.device)
+        dist.all_gather_into_tensor(out, src, group=self.group)
+        out = out.cpu().contiguous()
+        ctypes.memmove(dst_ptr, out.data_ptr(), self.world * nbytes)
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.on_device:
+            t = torch.zeros(1, device=self.device)
+            dist.all_reduce(t, group=self.group)
+            torch.cuda.synchronize(self.device)
+        else:
+            dist.barrier(group=self.group)
+
+
 class ShardedGrm:
     """GRM pass over SNP shards: ctx holds THIS rank's shard (already uploaded / adopted, rows set)."""
 

@@ -128,6 +128,27 @@ int eb_grm_partial (eb_ctx *, const eb_grm_opts * opts, int *c0, int *c1, int *n
 void *eb_grm_device_ptr (eb_ctx *, int64_t * ld_out, int64_t * n_out);
 int eb_grm_finish (eb_ctx *, double *y_out, double *XTX_host);
 
+/* -------- multi-GPU: one context per SNP shard, exchange steps as kernels over peer memory --------
+ * The launcher supplies host-side plumbing only: an all-gather of small host records (every rank contributes `bytes`
+ * bytes, dst receives world*bytes in rank order) and a barrier; both return 0 on success.  Device buffers are shared
+ * through CUDA IPC (directly when ranks are contexts of one process) and reduced by the library's own kernels over
+ * NVLink: no device pointer ever crosses this interface.  With a communicator set, eb_grm / eb_pca_full / eb_fpca
+ * are COLLECTIVE: every rank calls them with the same rows and options on its own SNP shard; the reduced GRM (hence
+ * y, lambda, evecs, outlier decisions) is bit-identical on every rank, per-SNP outputs stay per shard, and nused_out is
+ * the total over shards.  This replaces nothing in the reference (smartpca is single-node pthreads,
+ * smartpca.c:3331-3358); it is what "numthreads" becomes across the GPUs of one box. */
+typedef struct {
+  int rank, world;
+  int (*allgather_host) (void *user, const void *src, void *dst, int64_t bytes);
+  int (*barrier) (void *user);
+  void *user;
+} eb_comm;
+int eb_set_comm (eb_ctx *, const eb_comm * comm /* NULL or world <= 1: single GPU */ );
+/* testing aid: in-place sum over ranks of a host vector through the peer all-reduce kernel (count even) */
+int eb_peer_allreduce_test (eb_ctx *, double *host_io, int64_t count);
+/* SNPs of THIS context's shard that entered XTX in the last GRM pass (eb_grm's nused_out is the total over shards) */
+int64_t eb_snp_used_count (eb_ctx *);
+
 /* -------- symmetric eigensolver on the resident GRM: eigvecs(), eigsubs.c:39-55 / dspev_, eigx.c:107 --------
  * lambda[nrows] descending (all eigenvalues of XTX/y); evecs[nvec*nrows], row i = unit eigenvector i.
  * lambda may be NULL (leading vectors only: what the outlier iterations need, smartpca.c:1250) and nvec may be 0

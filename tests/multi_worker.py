@@ -1,0 +1,99 @@
+"""Worker of the multi-rank GPU tests: one process per rank (spawned by tests/test_gpu_multi.py, or by torchrun on a
+multi-GPU box).  Every rank owns one SNP shard; the exchange steps run as the library's kernels over peer memory
+(CUDA IPC).  With fewer GPUs than ranks all ranks share cuda:0 (gloo plumbing) -- the peer path is the same code."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from eig_b200 import capi, parallel, synth  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+    ngpu = torch.cuda.device_count()
+    backend = os.environ.get("EB_BACKEND", "nccl" if ngpu >= world else "gloo")
+    dev_index = rank if ngpu >= world else 0
+    torch.cuda.set_device(dev_index)
+    dev = torch.device("cuda", dev_index)
+    if backend == "nccl":
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group("gloo")
+    comm = parallel.TorchComm(device=dev)
+
+    nsnp, nind = 3000, 333
+    P = synth.packed_genotypes(11, nsnp, nind, missing=0.1, npops=3, delta=0.25)
+    P[5] = 0xFF                                   # an all-missing SNP (dropped by the rule) in rank 0's shard
+    s0, s1 = parallel.shard_snps(nsnp, rank, world)
+
+    single = capi.Context(dev_index)              # the whole matrix on one GPU: the expected result
+    single.upload_packed(P, nind); single.set_rows(None)
+    ref = single.grm(want_xtx=True)
+
+    ctx = capi.Context(dev_index)
+    ctx.set_comm(comm)
+    # 1. the all-reduce kernel alone
+    v = np.arange(1000, dtype=np.float64) * (rank + 1)
+    out = ctx.peer_allreduce_test(v)
+    assert np.array_equal(out, np.arange(1000, dtype=np.float64) * (world * (world + 1) // 2)), "peer all-reduce"
+    # 2. sharded GRM == single-GPU GRM; per-SNP outputs are the shard's slice; nused is the total
+    ctx.upload_packed(P[s0:s1], nind); ctx.set_rows(None)
+    for rep in range(2):                          # second pass reuses the mapped peer buffers
+        r = ctx.grm(want_xtx=True)
+        assert abs(r["y"] - ref["y"]) <= 1e-13 * ref["y"], (r["y"], ref["y"])
+        assert np.abs(r["XTX"] - ref["XTX"]).max() <= 1e-12 * np.abs(ref["XTX"]).max()
+        assert r["nused"] == ref["nused"], (r["nused"], ref["nused"])
+        for k in ("c0", "c1", "nmiss", "used", "xmean", "xfancy"):
+            assert np.array_equal(r[k], ref[k][s0:s1]), k
+    # bit-identical on every rank
+    h = torch.from_numpy(r["XTX"].view(np.int64).reshape(-1).copy())
+    hs = [torch.empty_like(h) for _ in range(world)]
+    if backend == "nccl":
+        hd = h.to(dev); hsd = [torch.empty_like(hd) for _ in range(world)]
+        dist.all_gather(hsd, hd); hs = [t.cpu() for t in hsd]
+    else:
+        dist.all_gather(hs, h)
+    assert all(torch.equal(hs[0], t) for t in hs), "GRM differs between ranks"
+    lam, vec = ctx.eig(4)
+    rl, rv = single.eig(4)
+    assert np.abs(lam - rl).max() <= 1e-9 * rl[0]
+    for i in range(3):
+        assert abs(abs(vec[i] @ rv[i]) - 1) < 1e-9
+    # 3. rows subset + outlier loop: same decisions and spectrum as the single-GPU run
+    pd = np.array([0.05] * 3 + [1.5])             # two planted outliers (tests/test_gpu_eig.py::test_pca_full_outlier_loop)
+    g = synth.genotypes(4, nsnp, nind, missing=0.02, npops=4, pop_delta=pd)
+    g0 = synth.genotypes(4, nsnp, nind, missing=0.02, npops=4, pop_delta=np.array([0.05] * 4))
+    sel = (synth.pop_of(nind, 4) == 3) & (np.arange(nind) < nind - 2)
+    g[:, sel] = g0[:, sel]
+    Q = synth.pack(g)
+    xi = np.arange(5, nind, dtype=np.int32)
+    single.upload_packed(Q, nind)
+    a = single.pca_full(xindex=xi, numeigs=4, numoutliter=3)
+    ctx.upload_packed(Q[s0:s1], nind)
+    b = ctx.pca_full(xindex=xi, numeigs=4, numoutliter=3)
+    assert np.array_equal(a["removed_index"], b["removed_index"]) and a["niter"] == b["niter"] and a["nused"] == b["nused"]
+    assert len(a["removed_index"]) >= 1, "test needs at least one outlier"
+    assert np.abs(a["lambda_"] - b["lambda_"]).max() <= 1e-9 * a["lambda_"][0]
+    assert np.array_equal(b["used"], a["used"][s0:s1])
+    # 4. sharded fastmode == single-GPU fastmode
+    single.upload_packed(P, nind); single.set_rows(None)
+    ctx.upload_packed(P[s0:s1], nind); ctx.set_rows(None)
+    for rep in range(2):
+        ev0, vec0 = single.fpca(4, 8, 3, seed=77)
+        ev1, vec1 = ctx.fpca(4, 8, 3, seed=77)
+        assert np.abs(ev1 - ev0).max() <= 1e-9 * ev0[0], (ev0, ev1)
+        for k in range(4):
+            assert abs(abs(vec0[:, k] @ vec1[:, k]) - 1) < 1e-8, k
+    dist.barrier()
+    ctx.close(); single.close()
+    dist.destroy_process_group()
+    print("rank %d/%d ok (backend %s, device %d)" % (rank, world, backend, dev_index))
+
+
+if __name__ == "__main__":
+    main()

@@ -54,3 +54,38 @@ def test_gloo_world2_partial_grm_allreduce(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+COMM_WORKER = r'''
+import ctypes as C, os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["EB_ROOT"])
+from eig_b200 import capi, parallel
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["EB_PORT"], rank=int(os.environ["RANK"]), world_size=2)
+comm = parallel.TorchComm()
+assert (comm.rank, comm.world, comm.on_device) == (dist.get_rank(), 2, False)
+# drive the plumbing exactly the way libeigb200 does: through the C callback types of eb_comm
+ag = capi.ALLGATHER_CB(lambda user, src, dst, n: (comm.allgather_host(src, dst, n), 0)[1])
+bar = capi.BARRIER_CB(lambda user: (comm.barrier(), 0)[1])
+st = capi.Comm(comm.rank, comm.world, ag, bar, None)
+rec = np.arange(96, dtype=np.uint8) + 100 * comm.rank           # sizeof(PeerRecord) = 96
+out = np.zeros(2 * 96, np.uint8)
+assert st.allgather_host(None, rec.ctypes.data, out.ctypes.data, 96) == 0
+assert np.array_equal(out[:96], np.arange(96, dtype=np.uint8)) and np.array_equal(out[96:], (np.arange(96) + 100).astype(np.uint8))
+assert st.barrier(None) == 0
+dist.destroy_process_group()
+print("rank", comm.rank, "ok")
+'''
+
+
+def test_gloo_world2_comm_callbacks():
+    """eb_comm plumbing (all-gather of host records + barrier) over gloo, called through the C callback types"""
+    port = 31500 + (os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), EB_ROOT=ROOT, EB_PORT=str(port), MASTER_ADDR="127.0.0.1")
+        procs.append(subprocess.Popen([sys.executable, "-c", COMM_WORKER], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
