@@ -56,7 +56,7 @@ EXPORTS = [
     "eb_eig", "eb_eigvecs", "eb_ridoutlier", "eb_pca_full", "eb_fpca", "eb_gauss_matrix", "eb_project", "eb_get_timings",
     "eb_microbench_fp64", "eb_set_option", "eb_debug_tridiag", "eb_lsqproj", "eb_evec_coords", "eb_pop_counts", "eb_hash_ids", "eb_packed_file_header", "eb_upload_packed_file",
     "eb_download_packed", "eb_write_eval", "eb_write_evec", "eb_write_grm", "eb_grm_dense_begin", "eb_grm_dense_add", "eb_grm_dense_end", "eigvecs", "eigvals",
-    "eb_set_comm", "eb_peer_allreduce_test", "eb_snp_used_count",
+    "eb_set_comm", "eb_peer_allreduce_test", "eb_snp_used_count", "eb_shrink_coords", "eb_debug_gemm",
 ]
 
 _lib = None
@@ -374,6 +374,21 @@ class Context:
         co = np.empty((k, nl)); es = np.empty(k); ok = np.empty(nl, np.uint8)
         _chk(lib().eb_evec_coords(self.h, _p(evecs), C.c_int(k), _p(lst), C.c_int(nl), _p(co), _p(es), _p(ok)))
         return co, es, ok
+
+    def shrink_coords(self, numeigs, newshrink=False):
+        """shrinkmode coordinates [numeigs][numindivs] (as printevecs writes them), header eigenvalues, ok flags"""
+        co = np.empty((numeigs, self.numindivs)); lam = np.empty(numeigs); ok = np.empty(self.numindivs, np.uint8)
+        _chk(lib().eb_shrink_coords(self.h, C.c_int(numeigs), C.c_int(1 if newshrink else 0), _p(co), _p(lam), _p(ok)))
+        return co, lam, ok
+
+    def debug_gemm(self, A, B, a_km=False, b_kn=False):
+        A = np.ascontiguousarray(A, np.float64); B = np.ascontiguousarray(B, np.float64)
+        K, M = A.shape if a_km else A.shape[::-1]
+        N = B.shape[1] if b_kn else B.shape[0]
+        assert (B.shape[0] if b_kn else B.shape[1]) == K
+        Cm = np.empty((M, N))
+        _chk(lib().eb_debug_gemm(self.h, C.c_int(int(a_km)), C.c_int(int(b_kn)), _p(A), _p(B), _p(Cm), C.c_int(M), C.c_int(N), C.c_int(K)))
+        return Cm
 
     # ---- measurement
     def timings(self):

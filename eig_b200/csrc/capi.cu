@@ -634,6 +634,34 @@ int eb_evec_coords(eb_ctx* c, const double* evecs, int numeigs, const int* indiv
   return 0;
 }
 
+int eb_shrink_coords(eb_ctx* c, int numeigs, int newshrink, double* coords, double* lambda_out, uint8_t* ok) {
+  int rc;
+  if ((rc = need_rows(c, "eb_shrink_coords"))) return rc;
+  if (!c->grm_valid || c->y <= 0.0) { set_error("eb_shrink_coords: run eb_grm first (needs the resident GRM and the per-SNP normalisation)"); return EB_ERR_STATE; }
+  if (!coords || !lambda_out) { set_error("eb_shrink_coords: null argument"); return EB_ERR_ARG; }
+  if (c->has_comm) { set_error("eb_shrink_coords: not available on a sharded context yet"); return EB_ERR_STATE; }
+  return shrink_run(c, numeigs, newshrink, coords, lambda_out, ok);
+}
+
+// testing aid: C = op(A) op(B)^T through the general FP64 tensor-core GEMM
+int eb_debug_gemm(eb_ctx* c, int a_km, int b_kn, const double* A, const double* B, double* C, int M, int N, int K) {
+  if (!c || !A || !B || !C) return EB_ERR_ARG;
+  EB_CUDA(cudaSetDevice(c->device));
+  const int64_t lda = ((a_km ? M : K) + 1) & ~1ll, ldb = ((b_kn ? N : K) + 1) & ~1ll, ldc = (N + 1) & ~1ll;
+  const int ra = a_km ? K : M, rb = b_kn ? K : N;
+  DevBuf<double> Ad, Bd, Cd;
+  int rc;
+  if ((rc = Ad.ensure((size_t)ra * lda)) || (rc = Bd.ensure((size_t)rb * ldb)) || (rc = Cd.ensure((size_t)M * ldc))) return rc;
+  EB_CUDA(cudaMemsetAsync(Ad.p, 0, sizeof(double) * ra * lda, c->stream));
+  EB_CUDA(cudaMemsetAsync(Bd.p, 0, sizeof(double) * rb * ldb, c->stream));
+  EB_CUDA(cudaMemcpy2DAsync(Ad.p, sizeof(double) * lda, A, sizeof(double) * (a_km ? M : K), sizeof(double) * (a_km ? M : K), ra, cudaMemcpyHostToDevice, c->stream));
+  EB_CUDA(cudaMemcpy2DAsync(Bd.p, sizeof(double) * ldb, B, sizeof(double) * (b_kn ? N : K), sizeof(double) * (b_kn ? N : K), rb, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = launch_gemm(c, a_km != 0, b_kn != 0, Ad.p, lda, Bd.p, ldb, Cd.p, ldc, M, N, K))) return rc;
+  EB_CUDA(cudaMemcpy2DAsync(C, sizeof(double) * N, Cd.p, sizeof(double) * ldc, sizeof(double) * N, M, cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int64_t eb_snp_used_count(eb_ctx* c) { return c ? c->nused : 0; }
 
 int eb_get_timings(eb_ctx* c, eb_timings* t) {

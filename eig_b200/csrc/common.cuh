@@ -154,6 +154,8 @@ int eig_resident(eb_ctx* c, const double* A_d, int64_t lda, int n, double scale,
 bool eig_uses_two_stage(const eb_ctx* c, int n, int nvec);
 // eig2_gemm.cu
 int launch_syrk_lower_add(eb_ctx* c, double* A, int64_t lda, int n, const double* T, int64_t ldt, int krows);
+int launch_gemm(eb_ctx* c, bool a_km, bool b_kn, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                int M, int N, int K);
 // grm_kernel.cu (dense path)
 int grm_dense_finalize(eb_ctx* c);
 // eig2_kernels.cu
@@ -162,6 +164,7 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
 // fpca_kernels.cu
 int fpca_run(eb_ctx* c, int fancynorm, int altnormstyle, size_t K, size_t L, size_t I, long seed, double* eval, double* evec);
 int project_run(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, double* fxvecs, double* fxscal);
+int shrink_run(eb_ctx* c, int k, int newshrink, double* coords, double* lambda_out, uint8_t* ok_out);
 int lsqproj_run(eb_ctx* c, const int* indiv, int nlist, const double* ffvecs, const double* fxscal, int k, double* acoeffs, double* bcoeffs,
                 int* nvalid, uint8_t* ok);
 // peer.cu

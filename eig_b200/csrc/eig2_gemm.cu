@@ -225,6 +225,104 @@ syr2k_lower_kernel(const __grid_constant__ CUtensorMap mapVZ_km, const __grid_co
   }
 }
 
+// ------------------------------------------------------------------------------------------------ C = op(A) op(B)^T (general)
+// C[i][j] = sum_k a(i,k) b(j,k) for i < M, j < N.  A_KM: A stored [k][i] (K x M) else [i][k] (M x K);
+// B_KN: B stored [k][j] (K x N) else [j][k] (N x K).  128 x 64 tiles, persistent over items (n-tile fastest so that
+// the CTAs resident at one time share A row panels through L2); edges rely on the TMA zero fill.
+template <bool A_KM, bool B_KN>
+__global__ void __launch_bounds__(DT_THREADS, 2)
+dt_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, double* __restrict__ C, int64_t ldc,
+               int M, int N, int K, int mt, int nt) {
+  extern __shared__ __align__(128) uint8_t dt_raw[];
+  const DtSmem sm = dt_setup(dt_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nitems = mt * nt;
+  const int nchunks = (K + DT_KC - 1) / DT_KC;
+  constexpr uint32_t TX = (A_KM ? DT_A_KM_BYTES : DT_A_BYTES) + (B_KN ? DT_B_KN_BYTES : DT_B_BYTES);
+
+  if (warp == DT_CONSUMERS / 32) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int im = item / nt, in = item - im * nt;
+        for (int kc = 0; kc < nchunks; kc++) {
+          const int k0 = kc * DT_KC;
+          dt_mbar_wait(sm.empty + stage, phase ^ 1);
+          dt_mbar_expect_tx(sm.full + stage, TX);
+          if (A_KM) dt_tma_2d(sm.A(stage), &mapA, im * DT_M, k0, sm.full + stage);
+          else dt_tma_2d(sm.A(stage), &mapA, k0, im * DT_M, sm.full + stage);
+          if (B_KN) dt_tma_2d(sm.B(stage), &mapB, in * DT_N, k0, sm.full + stage);
+          else dt_tma_2d(sm.B(stage), &mapB, k0, in * DT_N, sm.full + stage);
+          if (++stage == DT_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, q = lane & 3;
+  double acc[8][4][2];
+#pragma unroll
+  for (int t = 0; t < 8; t++)
+#pragma unroll
+    for (int u = 0; u < 4; u++) acc[t][u][0] = acc[t][u][1] = 0.0;
+  uint32_t stage = 0, phase = 0;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int im = item / nt, in = item - im * nt;
+    for (int kc = 0; kc < nchunks; kc++) {
+      dt_mbar_wait(sm.full + stage, phase);
+      dt_stage_mma<A_KM, B_KN>(sm.A(stage), sm.B(stage), acc, wm, wn, g, q);
+      __syncwarp();
+      if (lane == 0) dt_mbar_arrive(sm.empty + stage);
+      if (++stage == DT_STAGES) { stage = 0; phase ^= 1; }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      const int row = im * DT_M + wm * 64 + t * 8 + g;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int col = in * DT_N + wn * 32 + u * 8 + q * 2;
+        if (row < M) {
+          if (col + 1 < N) *reinterpret_cast<double2*>(C + (size_t)row * ldc + col) = make_double2(acc[t][u][0], acc[t][u][1]);
+          else if (col < N) C[(size_t)row * ldc + col] = acc[t][u][0];
+        }
+        acc[t][u][0] = acc[t][u][1] = 0.0;
+      }
+    }
+  }
+}
+
+template <bool A_KM, bool B_KN>
+static int launch_gemm_t(eb_ctx* c, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int N, int K) {
+  CUtensorMap ma, mb;
+  int rc;
+  if (A_KM) { if ((rc = make_f64_tensormap(&ma, A, K, M, lda, DT_LD_M, DT_KC))) return rc; }
+  else { if ((rc = make_f64_tensormap(&ma, A, M, K, lda, DT_LD_K, DT_M))) return rc; }
+  if (B_KN) { if ((rc = make_f64_tensormap(&mb, B, K, N, ldb, DT_LD_N, DT_KC))) return rc; }
+  else { if ((rc = make_f64_tensormap(&mb, B, N, K, ldb, DT_LD_K, DT_N))) return rc; }
+  static bool attr = false;
+  if (!attr) {
+    EB_CUDA(cudaFuncSetAttribute(dt_gemm_kernel<A_KM, B_KN>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
+    attr = true;
+  }
+  const int mt = (M + DT_M - 1) / DT_M, nt = (N + DT_N - 1) / DT_N;
+  const int grid = std::min(mt * nt, 2 * c->num_sms);
+  dt_gemm_kernel<A_KM, B_KN><<<grid, DT_THREADS, DT_SMEM, c->stream>>>(ma, mb, C, ldc, M, N, K, mt, nt);
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
+// C (M x N, ldc; must be 16-byte aligned rows) = op(A) op(B)^T on the FP64 tensor cores; a_km / b_kn select the storage
+// of the operands (see dt_gemm_kernel).  Leading dimensions must be even (TMA strides are multiples of 16 bytes).
+int launch_gemm(eb_ctx* c, bool a_km, bool b_kn, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                int M, int N, int K) {
+  if ((lda & 1) || (ldb & 1) || (ldc & 1)) { set_error("launch_gemm: leading dimensions must be even"); return EB_ERR_ARG; }
+  if (!a_km && !b_kn) return launch_gemm_t<false, false>(c, A, lda, B, ldb, C, ldc, M, N, K);
+  if (a_km && b_kn) return launch_gemm_t<true, true>(c, A, lda, B, ldb, C, ldc, M, N, K);
+  if (a_km) return launch_gemm_t<true, false>(c, A, lda, B, ldb, C, ldc, M, N, K);
+  return launch_gemm_t<false, true>(c, A, lda, B, ldb, C, ldc, M, N, K);
+}
+
 int dt_resident_ctas(eb_ctx* c) {
   static int cached = 0;
   if (!cached) {

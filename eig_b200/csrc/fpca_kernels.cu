@@ -580,6 +580,328 @@ int lsqproj_run(eb_ctx* c, const int* indiv, int nlist, const double* ffvecs, co
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ shrinkmode
+// doshrinkp / doshrinkp2 (smartpca.c:4223-4419, 4022-4220): leave-one-out ("shrunk") coordinates of every PCA sample.
+// For eigenvector i and sample a the reference perturbs the normalised GRM X by removing a's row and column
+// (dd = -(e_a x_a^T + x_a e_a^T), smartpca.c:4332-4338), applies first-order perturbation theory over the FULL eigenbasis
+// (4339-4347), re-centres / re-normalises the perturbed vector with entry a zeroed (4359-4364), recomputes the SNP loadings
+// from the other samples (4366-4368) and re-projects sample a by least squares on its observed genotypes (doproj, 3986-4019).
+// The reference does this with an m x m scratch matrix per (i, a) and a dense m x n FP64 copy of the data:
+// O(k m (m^2 + m n)) scalar flops.  Here, per eigenvector i:
+//   S_i[k'][a] = (e_k' . ww_a) / (lam_i - lam_k')   in closed form (ww_a has only the row/column-a structure)
+//   Enew_i     = rows { norme0_a(e_i + S_i[:,a]^T E) }              one m x m x m DMMA GEMM + a row kernel
+//   F_i[s][a]  = sum_t x_ts Enew_i[a][t]                            DMMA GEMM per SNP block against the decoded block
+//   per-sample sums over s (all / observed only) of F_i^2, F_i x_a, F_i F_l or F_i ff_l       reduction kernel
+// and a k x k Cholesky per sample.  mmat is never materialised beyond one SNP block.
+constexpr int SHR_KMAX = 16;
+
+// (g - ymean) * yfancy of getcolxf (smartpca.c:3564-3597 via fvadjust 2236-2279): no SNP weight; zero rows for unused SNPs
+__global__ void mm_table_kernel(int64_t nsnp, int64_t mpad, int nrows, const int* __restrict__ c0, const int* __restrict__ nmiss,
+                                const double* __restrict__ xfancy, const uint8_t* __restrict__ used, double* __restrict__ table) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= mpad) return;
+  double t0 = 0, t1 = 0, t2 = 0;
+  if (s < nsnp && used[s]) {
+    const double ym = __ddiv_rn((double)c0[s], (double)(nrows - nmiss[s])), yf = xfancy[s];
+    t0 = __dmul_rn(__dadd_rn(0.0, -ym), yf); t1 = __dmul_rn(__dadd_rn(1.0, -ym), yf); t2 = __dmul_rn(__dadd_rn(2.0, -ym), yf);
+  }
+  reinterpret_cast<double4*>(table)[s] = make_double4(t0, t1, t2, 0.0);
+}
+
+// Xn = G * scale restricted to n x n -> X (ld), plus x1[a] = sum_t Xn[a][t] and dg[a] = Xn[a][a]   (one block per row)
+__global__ void __launch_bounds__(256) shr_scale_rows_kernel(const double* __restrict__ G, int64_t ldg, int n, double scale, double* __restrict__ X,
+                                                             int64_t ldx, double* __restrict__ x1, double* __restrict__ dg) {
+  __shared__ double sh[32];
+  const int a = blockIdx.x;
+  double s = 0.0;
+  for (int t = threadIdx.x; t < ldx; t += blockDim.x) {
+    const double v = t < n ? G[(size_t)a * ldg + t] * scale : 0.0;
+    X[(size_t)a * ldx + t] = v;
+    s += v;
+  }
+  s = bsum(s, sh);
+  if (threadIdx.x == 0) { x1[a] = s; dg[a] = G[(size_t)a * ldg + a] * scale; }
+}
+
+// norme (smartpca.c:3955-3963) on row blockIdx.x of E: subtract the mean, scale to unit length; mu/sc remember the map
+// e = sc * e~ + mu so that X e~ can be written with the eigen-relation of the original vector
+__global__ void __launch_bounds__(256) shr_norme_rows_kernel(double* __restrict__ E, int64_t ld, int n, double* __restrict__ mu, double* __restrict__ sc) {
+  __shared__ double sh[32];
+  double* r = E + (size_t)blockIdx.x * ld;
+  double s = 0.0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) s += r[t];
+  const double mean = bsum(s, sh) / (double)n;
+  double q = 0.0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) { const double v = r[t] - mean; q += v * v; }
+  const double nrm = sqrt(bsum(q, sh));
+  for (int t = threadIdx.x; t < n; t += blockDim.x) r[t] = (r[t] - mean) * (1.0 / nrm);
+  if (threadIdx.x == 0) { mu[blockIdx.x] = mean; sc[blockIdx.x] = nrm; }
+}
+
+// S[k'][a] for eigenvector i (see the derivation above); also delta / ymul per sample (smartpca.c:4339, 4348-4357 / 4143-4152)
+__global__ void __launch_bounds__(256) shr_coeff_kernel(const double* __restrict__ E, int64_t ld, int n, int k, int i, const double* __restrict__ lam,
+                                                        const double* __restrict__ mu, const double* __restrict__ sc, const double* __restrict__ x1,
+                                                        const double* __restrict__ dg, int newshrink, double* __restrict__ S,
+                                                        double* __restrict__ ymul) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, kk = blockIdx.y;
+  if (a >= ld) return;
+  if (a >= n) { S[(size_t)kk * ld + a] = 0.0; return; }
+  const double li = lam[i], lk = lam[kk];
+  const double ei = E[(size_t)i * ld + a], ek = E[(size_t)kk * ld + a], xaa = dg[a];
+  const double Pi = (li * (sc[i] * ei + mu[i]) - mu[i] * x1[a]) / sc[i];                    // (X e~_i)[a]
+  const double Pk = kk < k ? (lk * (sc[kk] * ek + mu[kk]) - mu[kk] * x1[a]) / sc[kk] : lk * ek;
+  const double eco = -ei * (Pk - xaa * ek) - ek * Pi;
+  S[(size_t)kk * ld + a] = kk == i ? 0.0 : eco / (li - lk);
+  if (kk == i) {
+    const double delta = ei * (xaa * ei - 2.0 * Pi);
+    const bool good = newshrink ? (li > -delta) : (li > delta);
+    ymul[a] = good ? li / (li + delta) : 1.0;
+  }
+}
+
+// row a of C holds ediff; -> enew = norme(centre_a(e~_i + ediff)) (smartpca.c:4359-4364), zero in the pad columns
+__global__ void __launch_bounds__(256) shr_enew_kernel(double* __restrict__ C, int64_t ld, int n, const double* __restrict__ ei) {
+  __shared__ double sh[32];
+  const int a = blockIdx.x;
+  double* r = C + (size_t)a * ld;
+  double s = 0.0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) { const double v = t == a ? 0.0 : ei[t] + r[t]; r[t] = v; s += v; }
+  const double y = bsum(s, sh) / (double)(n - 1);
+  double s2 = 0.0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) { const double v = t == a ? 0.0 : r[t] - y; r[t] = v; s2 += v; }
+  const double mean = bsum(s2, sh) / (double)n;
+  double q = 0.0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) { const double v = r[t] - mean; q += v * v; }
+  const double inv = 1.0 / sqrt(bsum(q, sh));
+  for (int t = threadIdx.x; t < ld; t += blockDim.x) r[t] = t < n ? (r[t] - mean) * inv : 0.0;
+}
+
+// D[s - s0][t] = table[s][code(s, t)] for the SNP block [s0, s0 + nb)
+__global__ void __launch_bounds__(256) shr_decode_kernel(const uint8_t* __restrict__ work, int64_t wpitch, const double* __restrict__ table, int64_t s0,
+                                                         int npad, double* __restrict__ D) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t s = s0 + blockIdx.y;
+  if (t >= npad) return;
+  const int code = (work[s * wpitch + (t >> 2)] >> ((3 - (t & 3)) * 2)) & 3;
+  D[(size_t)blockIdx.y * npad + t] = table[s * 4 + code];
+}
+
+// ff[j][s] /= sqrt(sum_s ff[j][s]^2 / ncols)   (smartpca.c:4309-4310)
+__global__ void __launch_bounds__(1024) shr_unit_rows_kernel(double* __restrict__ FF, int64_t ld, int64_t len, double ncols) {
+  __shared__ double sh[32];
+  double* r = FF + (size_t)blockIdx.x * ld;
+  double q = 0.0;
+  for (int64_t t = threadIdx.x; t < len; t += blockDim.x) q += r[t] * r[t];
+  const double inv = 1.0 / sqrt(bsum(q, sh) / ncols);
+  for (int64_t t = threadIdx.x; t < len; t += blockDim.x) r[t] *= inv;
+}
+
+// Per (sample a, eigenvector i = blockIdx.y, SNP slice blockIdx.z): sums over the SNPs of this block of
+//   slot l < k : NEW  F_i F_l over observed SNPs (l >= i)     OLD  F_i ff_l over observed SNPs (l != i), F_i^2 observed (l == i)
+//   slot k     : F_i^2 over all SNPs   (normalisation, smartpca.c:4367)
+//   slot k + 1 : F_i x_a               (right-hand side; x_a = 0 where missing)
+// Ft: [k][nb][npad] (F_i[s][a]); acc: [nz][k][k + 2][npad], each thread owns its slots (no atomics, fixed order).
+template <bool NEWSHRINK>
+__global__ void __launch_bounds__(128) shr_reduce_kernel(const double* __restrict__ Ft, int nb, int npad, int n, int k,
+                                                         const uint8_t* __restrict__ work, int64_t wpitch, const double* __restrict__ ftab,
+                                                         const uint8_t* __restrict__ used, const double* __restrict__ FF, int64_t ldf, int64_t s0,
+                                                         double* __restrict__ acc) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, z = blockIdx.z, nz = gridDim.z;
+  if (a >= n) return;
+  const int b0 = (int)(((long long)nb * z) / nz), b1 = (int)(((long long)nb * (z + 1)) / nz);
+  double g[SHR_KMAX], sq = 0.0, rx = 0.0;
+#pragma unroll
+  for (int l = 0; l < SHR_KMAX; l++) g[l] = 0.0;
+  const size_t plane = (size_t)nb * npad;
+  const int sh = (3 - (a & 3)) * 2;
+  for (int b = b0; b < b1; b++) {
+    const int64_t s = s0 + b;
+    const int code = (work[s * wpitch + (a >> 2)] >> sh) & 3;
+    const bool v = code != 3 && used[s];
+    const double fi = Ft[(size_t)i * plane + (size_t)b * npad + a];
+    sq = fma(fi, fi, sq);
+    rx = fma(fi, ftab[s * 4 + code], rx);
+    if (v) {
+#pragma unroll
+      for (int l = 0; l < SHR_KMAX; l++) {
+        if (l < k) {
+          if (NEWSHRINK) { if (l >= i) g[l] = fma(fi, Ft[(size_t)l * plane + (size_t)b * npad + a], g[l]); }
+          else g[l] = fma(fi, l == i ? fi : FF[(size_t)l * ldf + s], g[l]);
+        }
+      }
+    }
+  }
+  double* o = acc + ((size_t)(z * k + i) * (k + 2)) * npad + a;
+#pragma unroll
+  for (int l = 0; l < SHR_KMAX; l++)
+    if (l < k) o[(size_t)l * npad] += g[l];
+  o[(size_t)k * npad] += sq;
+  o[(size_t)(k + 1) * npad] += rx;
+}
+
+__device__ __forceinline__ bool shr_cholsolve(double* a, double* p, double* x, const double* rr, int k) {
+  // choldc / cholsl in the reference's operation order (nicksrc/linsubs.c:331-393), as lsq_solve_kernel
+  for (int i = 0; i < k; i++)
+    for (int j = i; j < k; j++) {
+      double sum = a[i * k + j];
+      for (int m = i - 1; m >= 0; m--) sum -= a[i * k + m] * a[j * k + m];
+      if (i == j) { if (!(sum > 0.0)) return false; p[i] = sqrt(sum); }
+      else a[j * k + i] = sum / p[i];
+    }
+  for (int i = 0; i < k; i++) { double sum = rr[i]; for (int m = i - 1; m >= 0; m--) sum -= a[i * k + m] * x[m]; x[i] = sum / p[i]; }
+  for (int i = k - 1; i >= 0; i--) { double sum = x[i]; for (int m = i + 1; m < k; m++) sum -= a[m * k + i] * x[m]; x[i] = sum / p[i]; }
+  return true;
+}
+
+// doshrinkp2: one regression per sample on all k leave-one-out loadings (smartpca.c:4165-4169) -> snew[i][a] = ans[i] * ymul[i][a]
+__global__ void __launch_bounds__(128) shr_solve_new_kernel(const double* __restrict__ acc, int nz, int npad, int n, int k, double ncols,
+                                                            const double* __restrict__ ymul, double* __restrict__ snew, uint8_t* __restrict__ okf) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  double co[SHR_KMAX * SHR_KMAX], p[SHR_KMAX], x[SHR_KMAX], rr[SHR_KMAX], yn[SHR_KMAX];
+  auto A = [&](int i, int q) { double s = 0.0; for (int z = 0; z < nz; z++) s += acc[((size_t)(z * k + i) * (k + 2) + q) * npad + a]; return s; };
+  for (int i = 0; i < k; i++) yn[i] = sqrt(A(i, k) / ncols);
+  for (int i = 0; i < k; i++) {
+    rr[i] = A(i, k + 1) / yn[i];
+    for (int l = i; l < k; l++) { const double v = A(i, l) / (yn[i] * yn[l]); co[i * k + l] = v; co[l * k + i] = v; }
+  }
+  const bool good = shr_cholsolve(co, p, x, rr, k);
+  for (int i = 0; i < k; i++) snew[(size_t)i * npad + a] = good ? x[i] * ymul[(size_t)i * npad + a] : 0.0;
+  okf[a] = good ? 1 : 0;
+}
+
+// doshrinkp: for every (a, i) a regression on the base loadings with row i replaced (smartpca.c:4369-4374)
+// Nt: [k(k+1)/2 + 1][npad] base normal-equation pairs (lsq_pairs_kernel order), Rt: [k][npad] base right-hand sides
+__global__ void __launch_bounds__(128) shr_solve_old_kernel(const double* __restrict__ acc, int nz, int npad, int n, int k, double ncols,
+                                                            const double* __restrict__ Nt, const double* __restrict__ Rt,
+                                                            const double* __restrict__ ymul, double* __restrict__ snew, uint8_t* __restrict__ okf) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (a >= n) return;
+  double co[SHR_KMAX * SHR_KMAX], p[SHR_KMAX], x[SHR_KMAX], rr[SHR_KMAX];
+  auto A = [&](int q) { double s = 0.0; for (int z = 0; z < nz; z++) s += acc[((size_t)(z * k + i) * (k + 2) + q) * npad + a]; return s; };
+  int pr = 0;
+  for (int j = 0; j < k; j++) {
+    rr[j] = Rt[(size_t)j * npad + a];
+    for (int l = j; l < k; l++) { const double v = Nt[(size_t)(pr++) * npad + a]; co[j * k + l] = v; co[l * k + j] = v; }
+  }
+  const double yn = sqrt(A(k) / ncols);
+  for (int l = 0; l < k; l++) {
+    const double v = l == i ? A(i) / (yn * yn) : A(l) / yn;
+    co[i * k + l] = v; co[l * k + i] = v;
+  }
+  rr[i] = A(k + 1) / yn;
+  const bool good = shr_cholsolve(co, p, x, rr, k);
+  snew[(size_t)i * npad + a] = good ? x[i] * ymul[(size_t)i * npad + a] : 0.0;
+  if (!good) okf[a] = 0;
+}
+
+int shrink_run(eb_ctx* c, int k, int newshrink, double* coords, double* lambda_out, uint8_t* ok_out) {
+  if (k < 1 || k > SHR_KMAX) { set_error("eb_shrink_coords: numeigs must be in 1..%d", SHR_KMAX); return EB_ERR_ARG; }
+  int rc;
+  const int64_t m = c->nsnp, mpad = c->mpad;
+  const int n = c->nrows, npad = c->npad, N = c->numindivs;
+  if (k >= n) { set_error("eb_shrink_coords: numeigs must be smaller than the number of PCA rows"); return EB_ERR_ARG; }
+  // ---- full eigenbasis of Xn = XTX / y (smartpca.c:4285-4290; the second trace normalisation is the identity up to rounding)
+  std::vector<double> lam(n), Eh((size_t)n * n);
+  if ((rc = eig_resident(c, c->xtx.p, c->npad, n, 1.0 / c->y, n, lam.data(), Eh.data()))) return rc;
+  for (int j = 0; j < k; j++) lambda_out[j] = lam[j];
+  const int npairs = k * (k + 1) / 2 + 1;
+  const int nb_max = (int)std::min<int64_t>(mpad, 2048);
+  const int nz = std::max(1, std::min(16, (4 * c->num_sms * 128) / std::max(1, n * k)));
+  DevBuf<double> E, X, x1, dg, mu, sc, lam_d, S, En, ymul, mtab, ftab, vtab, FF, Pt, Nt, Rt, D, Ft, acc, snew;
+  DevBuf<uint8_t> okf;
+  if ((rc = E.ensure((size_t)n * npad)) || (rc = X.ensure((size_t)n * npad)) || (rc = x1.ensure(npad)) || (rc = dg.ensure(npad)) ||
+      (rc = mu.ensure(SHR_KMAX)) || (rc = sc.ensure(SHR_KMAX)) || (rc = lam_d.ensure(n)) || (rc = S.ensure((size_t)n * npad)) ||
+      (rc = En.ensure((size_t)k * n * npad)) || (rc = ymul.ensure((size_t)k * npad)) || (rc = mtab.ensure((size_t)mpad * 4)) ||
+      (rc = ftab.ensure((size_t)mpad * 4)) || (rc = vtab.ensure((size_t)mpad * 4)) || (rc = FF.ensure((size_t)k * mpad)) ||
+      (rc = Pt.ensure((size_t)npairs * mpad)) || (rc = Nt.ensure((size_t)npairs * npad)) || (rc = Rt.ensure((size_t)k * npad)) ||
+      (rc = D.ensure((size_t)nb_max * npad)) || (rc = Ft.ensure((size_t)k * nb_max * npad)) ||
+      (rc = acc.ensure((size_t)nz * k * (k + 2) * npad)) || (rc = snew.ensure((size_t)k * npad)) || (rc = okf.ensure(npad)))
+    return rc;
+  // the reference divides by ncols = |xsnplist|; the factor is common to every loading vector and cancels in the final
+  // unit-length normalisation of printevecs, so the uploaded SNP count serves
+  const double ncols = (double)m;
+  EB_CUDA(cudaMemsetAsync(E.p, 0, sizeof(double) * (size_t)n * npad, c->stream));
+  EB_CUDA(cudaMemcpy2DAsync(E.p, sizeof(double) * npad, Eh.data(), sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice, c->stream));
+  EB_CUDA(cudaMemcpyAsync(lam_d.p, lam.data(), sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+  shr_scale_rows_kernel<<<n, 256, 0, c->stream>>>(c->xtx.p, c->npad, n, 1.0 / c->y, X.p, npad, x1.p, dg.p);
+  EB_CHECK_LAUNCH(c);
+  shr_norme_rows_kernel<<<k, 256, 0, c->stream>>>(E.p, npad, n, mu.p, sc.p);                 // smartpca.c:4305-4307
+  EB_CHECK_LAUNCH(c);
+  const unsigned gm = (unsigned)((mpad + 255) / 256);
+  mm_table_kernel<<<gm, 256, 0, c->stream>>>(m, mpad, n, c->c0_d.p, c->nmiss_d.p, c->xfancy_d.p, c->used_d.p, mtab.p);
+  EB_CHECK_LAUNCH(c);
+  fix_table_kernel<<<gm, 256, 0, c->stream>>>(m, mpad, c->xmean_d.p, c->xfancy_d.p, c->used_d.p, ftab.p);
+  EB_CHECK_LAUNCH(c);
+  mask_table_kernel<<<gm, 256, 0, c->stream>>>(m, mpad, c->used_d.p, vtab.p);
+  EB_CHECK_LAUNCH(c);
+  // ---- base loadings ffvecs (smartpca.c:4309-4311) and the old-style projection of EVERY individual (4313-4318)
+  EB_CUDA(cudaMemsetAsync(FF.p, 0, sizeof(double) * (size_t)k * mpad, c->stream));
+  if ((rc = launch_packed_gemm<MODE_XA>(c, mtab.p, E.p, npad, FF.p, mpad, k, 1.0))) return rc;
+  shr_unit_rows_kernel<<<k, 1024, 0, c->stream>>>(FF.p, mpad, m, ncols);
+  EB_CHECK_LAUNCH(c);
+  std::vector<double> ffh((size_t)k * m), ones(k, 1.0), ss((size_t)k * N);
+  std::vector<uint8_t> okall(N);
+  std::vector<int> all(N);
+  for (int i = 0; i < N; i++) all[i] = i;
+  EB_CUDA(cudaMemcpy2DAsync(ffh.data(), sizeof(double) * m, FF.p, sizeof(double) * mpad, sizeof(double) * m, k, cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  if ((rc = lsqproj_run(c, all.data(), N, ffh.data(), ones.data(), k, ss.data(), nullptr, nullptr, okall.data()))) return rc;
+  // ---- base normal equations of the PCA rows (needed by the one-row-replaced regressions of doshrinkp)
+  if (!newshrink) {
+    lsq_pairs_kernel<<<gm, 256, 0, c->stream>>>(FF.p, mpad, m, mpad, k, Pt.p);
+    EB_CHECK_LAUNCH(c);
+    if ((rc = launch_packed_gemm<MODE_XTB>(c, ftab.p, FF.p, mpad, Rt.p, npad, k, 1.0))) return rc;
+    if ((rc = launch_packed_gemm<MODE_XTB>(c, vtab.p, Pt.p, mpad, Nt.p, npad, npairs, 1.0))) return rc;
+  }
+  // ---- leave-one-out eigenvectors, one m x m block per eigenvector
+  for (int i = 0; i < k; i++) {
+    shr_coeff_kernel<<<dim3((npad + 255) / 256, n), 256, 0, c->stream>>>(E.p, npad, n, k, i, lam_d.p, mu.p, sc.p, x1.p, dg.p, newshrink, S.p,
+                                                                          ymul.p + (size_t)i * npad);
+    EB_CHECK_LAUNCH(c);
+    double* Ei = En.p + (size_t)i * n * npad;
+    if ((rc = launch_gemm(c, true, true, S.p, npad, E.p, npad, Ei, npad, n, n, n))) return rc;       // ediff rows
+    shr_enew_kernel<<<n, 256, 0, c->stream>>>(Ei, npad, n, E.p + (size_t)i * npad);
+    EB_CHECK_LAUNCH(c);
+  }
+  // ---- SNP blocks: loadings of every leave-one-out vector and the per-sample sums
+  EB_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * (size_t)nz * k * (k + 2) * npad, c->stream));
+  for (int64_t s0 = 0; s0 < mpad; s0 += nb_max) {
+    const int nb = (int)std::min<int64_t>(nb_max, mpad - s0);
+    shr_decode_kernel<<<dim3((npad + 255) / 256, nb), 256, 0, c->stream>>>(c->work.p, c->wpitch, mtab.p, s0, npad, D.p);
+    EB_CHECK_LAUNCH(c);
+    for (int i = 0; i < k; i++)
+      if ((rc = launch_gemm(c, false, false, D.p, npad, En.p + (size_t)i * n * npad, npad, Ft.p + (size_t)i * nb * npad, npad, nb, n, n))) return rc;
+    const dim3 grid((n + 127) / 128, k, nz);
+    if (newshrink)
+      shr_reduce_kernel<true><<<grid, 128, 0, c->stream>>>(Ft.p, nb, npad, n, k, c->work.p, c->wpitch, ftab.p, c->used_d.p, FF.p, mpad, s0, acc.p);
+    else
+      shr_reduce_kernel<false><<<grid, 128, 0, c->stream>>>(Ft.p, nb, npad, n, k, c->work.p, c->wpitch, ftab.p, c->used_d.p, FF.p, mpad, s0, acc.p);
+    EB_CHECK_LAUNCH(c);
+  }
+  EB_CUDA(cudaMemsetAsync(okf.p, 1, npad, c->stream));
+  if (newshrink) shr_solve_new_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(acc.p, nz, npad, n, k, ncols, ymul.p, snew.p, okf.p);
+  else shr_solve_old_kernel<<<dim3((n + 127) / 128, k), 128, 0, c->stream>>>(acc.p, nz, npad, n, k, ncols, Nt.p, Rt.p, ymul.p, snew.p, okf.p);
+  EB_CHECK_LAUNCH(c);
+  std::vector<double> sn((size_t)k * npad);
+  std::vector<uint8_t> okh(npad);
+  EB_CUDA(cudaMemcpyAsync(sn.data(), snew.p, sizeof(double) * (size_t)k * npad, cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaMemcpyAsync(okh.data(), okf.p, npad, cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  // ---- PCA rows take the shrunk value (smartpca.c:4381-4389); printevecs: 10 x, unit length per eigenvector (3849-3866)
+  for (int j = 0; j < k; j++)
+    for (int t = 0; t < n; t++) ss[(size_t)j * N + c->xindex_h[t]] = sn[(size_t)j * npad + t];
+  for (int t = 0; t < n; t++) if (!okh[t]) okall[c->xindex_h[t]] = 0;
+  for (int j = 0; j < k; j++) {
+    double q = 0.0;
+    for (int i = 0; i < N; i++) { const double v = 10.0 * ss[(size_t)j * N + i]; q += v * v; }
+    const double inv = 1.0 / sqrt(q);
+    for (int i = 0; i < N; i++) coords[(size_t)j * N + i] = 10.0 * ss[(size_t)j * N + i] * inv;
+  }
+  if (ok_out) memcpy(ok_out, okall.data(), N);
+  return 0;
+}
+
 }  // namespace eb
 
 // Seeded Gaussian start matrix: kjg_gsl.c:96-113 (GSL mt19937, seed 0 -> 4357) and kjg_gsl.c:145-186

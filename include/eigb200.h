@@ -224,6 +224,17 @@ int eb_lsqproj (eb_ctx *, const int *indiv, int nindiv, const double *ffvecs /* 
 int eb_evec_coords (eb_ctx *, const double *evecs /* [numeigs][nrows] */ , int numeigs, const int *indiv, int nindiv,
                     double *coords, double *eigscale /* [numeigs] or NULL */ , uint8_t * ok /* [nindiv] or NULL */ );
 
+/* shrinkmode: doshrinkp (smartpca.c:4223-4419) or, with newshrink != 0, doshrinkp2 (4022-4220): leave-one-out
+ * ("shrunk") coordinates of every PCA sample, least-squares coordinates (doproj, 3986-4019) of everybody else.
+ * Needs the GRM of the last eb_grm resident.  coords [numeigs][numindivs] are the values printevecs writes in
+ * shrinkmode (3849-3866: x10, unit length per eigenvector, one row per individual of the store); lambda_out[numeigs]
+ * are the eigenvalues of the .evec header; ok[numindivs] (may be NULL) is 0 where a regression was singular.
+ * The full eigenbasis comes from eb_eig's solver, so this entry is for PCA sizes it returns all vectors for. */
+int eb_shrink_coords (eb_ctx *, int numeigs, int newshrink, double *coords, double *lambda_out, uint8_t * ok);
+/* testing aid: C[M][N] = op(A) op(B)^T on the FP64 tensor cores; a_km: A given as [K][M] else [M][K]; b_kn: B as [K][N]
+ * else [N][K] (all dense row-major host arrays) */
+int eb_debug_gemm (eb_ctx *, int a_km, int b_kn, const double *A, const double *B, double *C, int M, int N, int K);
+
 /* -------- measurement helpers -------- */
 /* last pass timings measured with CUDA events on the library's stream (milliseconds) */
 typedef struct {

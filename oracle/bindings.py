@@ -305,3 +305,103 @@ def ref_fstcol(packed, numindivs, xtypes, numeg, xindex=None):
                            en.ctypes.data_as(C.c_void_p), ed.ctypes.data_as(C.c_void_p))
     assert rc == 0
     return en, ed
+
+
+def ref_shrink(packed, numindivs, used, xmean, xfancy, XTXn, k, xindex=None, newshrink=False, fancynorm=1, altnormstyle=1):
+    """the unmodified reference's doshrinkp / doshrinkp2 (smartpca.c:4223-4419 / 4022-4220), run in a forked child;
+    returns the shrinkmode .evec values [k][numindivs]"""
+    nsnp, rlen = packed.shape; xi = _xi(xindex, numindivs); n = len(xi)
+    X = np.ascontiguousarray(XTXn, np.float64); assert X.shape == (n, n)
+    out = np.zeros((k, numindivs))
+    rc = ref().refh_shrink(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen), C.c_int(numindivs),
+                           xi.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(fancynorm), C.c_int(altnormstyle),
+                           np.ascontiguousarray(used, np.uint8).ctypes.data_as(C.c_void_p),
+                           np.ascontiguousarray(xmean).ctypes.data_as(C.c_void_p), np.ascontiguousarray(xfancy).ctypes.data_as(C.c_void_p),
+                           X.ctypes.data_as(C.c_void_p), C.c_int(k), C.c_int(1 if newshrink else 0), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0, rc
+    return out
+
+
+def port_shrink(packed, numindivs, used, xmean, xfancy, XTXn, k, xindex=None, newshrink=False):
+    """numpy restatement of doshrinkp (smartpca.c:4223-4419) and doshrinkp2 (4022-4220) -- small cases only (O(k m^3 + k m^2 n)).
+    Follows the reference step by step: trace normalisation 4285-4290, eigvecs 4292, norme + loadings 4305-4311, old-style
+    projection doproj 4313-4318 (3986-4019: least squares on the observed SNPs, x = g*xfancy - xmean via fixxrow qpsubs.c:338),
+    then per (eigenvector i, sample a): dd / ww / delta 4332-4339, first-order perturbation 4340-4347, ymul 4348-4357
+    (old: lam > delta; new: lam > -delta, 4143), zero / centre / norme 4359-4364, loadings 4366-4368, re-projection
+    4369-4374 (old: only row i replaced; new 4165-4169: all rows replaced, one regression per sample), printevecs 3849-3866."""
+    from eig_b200 import synth          # unpack helper only (2-bit layout, admutils.c:718-735)
+    nsnp, rlen = packed.shape; xi = _xi(xindex, numindivs); m = len(xi)
+    used = np.asarray(used).astype(bool)
+    g = synth.unpack(packed, numindivs).astype(np.float64).T        # [numindivs][nsnp], -1 missing
+    # mmat = getcolxf columns (smartpca.c:3564-3597): (g - mean) * yfancy over the PCA rows, 0 where missing / ignored SNP
+    gp = g[xi]
+    valid = gp >= 0
+    cnt = np.maximum(valid.sum(0), 1)
+    ymean = np.where(valid, gp, 0).sum(0) / cnt
+    mmat = np.where(valid, gp - ymean, 0.0) * np.asarray(xfancy)[None, :]
+    mmat[:, ~used] = 0.0
+    n = nsnp
+    xmat = np.array(XTXn, np.float64)
+    xmat = xmat * (1.0 / (np.trace(xmat) / (m - 1)))
+    lam, vec = np.linalg.eigh(xmat)
+    lam = lam[::-1].copy(); evecs = vec[:, ::-1].T.copy()            # row i = eigenvector i, descending (eigsubs.c:39-55)
+
+    def norme(v):
+        v = v - v.sum() / len(v)
+        return v / np.sqrt((v * v).sum())
+
+    def doproj(isample, fx):
+        row = g[isample]
+        ok = (row >= 0) & used
+        x = row * xfancy - xmean
+        e = fx[:, ok].T
+        co = e.T @ e; rr = e.T @ x[ok]
+        return np.linalg.solve(co, rr)
+
+    ffvecs = np.zeros((k, n))
+    for i in range(k):
+        evecs[i] = norme(evecs[i])
+        ff = evecs[i] @ mmat
+        ffvecs[i] = ff / np.sqrt((ff * ff).sum() / n)
+    ss = np.zeros((k, numindivs))
+    for i in range(numindivs):
+        ss[:, i] = doproj(i, ffvecs)
+    snew = np.zeros((k, m))
+
+    def enew_of(i, a):
+        evec = evecs[i]; l = lam[i]
+        ww = -xmat[a] * evec[a]
+        ww[a] = -(xmat[a] @ evec)
+        delta = ww @ evec
+        eco = evecs @ ww
+        den = l - lam
+        den[i] = 1.0
+        eco = eco / den
+        eco[i] = 0.0
+        ediff = eco @ evecs
+        good = (l > -delta) if newshrink else (l > delta)
+        ymul = l / (l + delta) if good else 1.0
+        en = evec + ediff
+        en[a] = 0
+        en = en - en.sum() / (m - 1)
+        en[a] = 0
+        en = norme(en)
+        ff = en @ mmat
+        return ff / np.sqrt((ff * ff).sum() / n), ymul
+
+    if newshrink:
+        for a in range(m):
+            fx = ffvecs.copy(); ym = np.ones(k)
+            for i in range(k):
+                fx[i], ym[i] = enew_of(i, a)
+            snew[:, a] = doproj(xi[a], fx) * ym
+    else:
+        for i in range(k):
+            for a in range(m):
+                fx = ffvecs.copy()
+                fx[i], ym = enew_of(i, a)
+                snew[i, a] = doproj(xi[a], fx)[i] * ym
+    ss[:, xi] = snew
+    out = 10.0 * ss
+    out /= np.sqrt((out * out).sum(1))[:, None]
+    return out, lam[:k]

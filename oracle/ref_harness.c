@@ -194,6 +194,48 @@ int refh_evec_coords (const unsigned char *packed, long nsnp, long rl, int nind,
   return 0;
 }
 
+/* shrinkmode: the reference's own doshrinkp / doshrinkp2 (smartpca.c:4223-4419, 4022-4220) on flat inputs, with the state
+ * smartpca.c:main has at the call (1642-1662): XTX = normalised GRM of the last pass (nrxtx = nrows), xmean/xfancy of that
+ * pass, mmat filled by getcolxf.  Runs in a forked child (doshrinkp frees XTX, printevecs is once-only).
+ * coords_o [k][nind]: the values printevecs leaves in xcoeffs (what the .evec file holds in shrinkmode). */
+int refh_shrink (const unsigned char *packed, long nsnp, long rl, int nind, const int *xindex_in, int nrows,
+                 int fancy, int altnorm, const unsigned char *used, const double *xmean_in, const double *xfancy_in,
+                 const double *XTXn, int k, int newshrink_in, double *coords_o)
+{
+  size_t na = sizeof (double) * (size_t) k * nind;
+  unsigned char *sh = mmap (NULL, na, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+  if (sh == MAP_FAILED) return -1;
+  pid_t pid = fork ();
+  if (pid < 0) return -2;
+  if (pid == 0) {
+    long i; int j; double *cc, *mmat, *xco = (double *) sh; int *xidx;
+    fclose (stdout); stdout = fopen ("/dev/null", "w");
+    hbuild (packed, nsnp, rl, nind);
+    fancynorm = fancy; altnormstyle = altnorm; usepopsformissing = NO; regmode = YES; plotmode = NO; easymode = NO;
+    shrinkmode = YES; newshrink = newshrink_in; toprightindex = -1; flip = NULL; verbose = NO;
+    numeigs = k; numindivs = nind; indivmarkers = hindp; ofile = fopen ("/dev/null", "w");
+    for (i = 0; i < nsnp; i++) hsnps[i].ignore = used[i] ? NO : YES;
+    for (i = 0; i < nind; i++) hind[i].idnum = (int) i;
+    ZALLOC (xmean, nsnp, double); ZALLOC (xfancy, nsnp, double);
+    memcpy (xmean, xmean_in, sizeof (double) * nsnp); memcpy (xfancy, xfancy_in, sizeof (double) * nsnp);
+    ZALLOC (xidx, nrows, int); memcpy (xidx, xindex_in, sizeof (int) * nrows);
+    ZALLOC (XTX, (long) nrows * nrows, double); memcpy (XTX, XTXn, sizeof (double) * (size_t) nrows * nrows); nrxtx = nrows;
+    ZALLOC (cc, nrows > 3 ? nrows : 3, double); ZALLOC (mmat, (long) nrows * nsnp, double);
+    for (i = 0; i < nsnp; i++) {                                   /* smartpca.c:1644-1650 */
+      getcolxf (cc, hsnpp[i], xidx, nrows, (int) i, NULL, NULL);
+      for (j = 0; j < nrows; j++) mmat[(long) j * nsnp + i] = cc[j];
+    }
+    doshrinkp (mmat, nrows, (int) nsnp, xidx, hsnpp, xco);
+    _exit (0);
+  }
+  int status = 0;
+  waitpid (pid, &status, 0);
+  if (!WIFEXITED (status) || WEXITSTATUS (status) != 0) { munmap (sh, na); return -3; }
+  memcpy (coords_o, sh, na);
+  munmap (sh, na);
+  return 0;
+}
+
 /* dense path: the reference's domult_increment_normal (smartpca.c:3531-3561) over consecutive blocks of `blocksize`
  * columns, then symit2 (smartpca.c:480-508).  XTX_out: nrows*nrows (packed lower triangle while accumulating). */
 int refh_dense_grm (const double *tblock_all, long ncols, int nrows, int blocksize, int nthreads, double *XTX_out)
