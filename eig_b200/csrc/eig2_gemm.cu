@@ -47,6 +47,8 @@ struct DtSmem {
   uint64_t* empty;
   __device__ double* A(int s) const { return reinterpret_cast<double*>(base + s * DT_STAGE_BYTES); }
   __device__ double* B(int s) const { return reinterpret_cast<double*>(base + s * DT_STAGE_BYTES + DT_A_BYTES); }
+  __device__ uint32_t a32(int s) const { return dt_smem_u32(base) + s * DT_STAGE_BYTES; }
+  __device__ uint32_t b32(int s) const { return dt_smem_u32(base) + s * DT_STAGE_BYTES + DT_A_BYTES; }
 };
 
 __device__ __forceinline__ DtSmem dt_setup(uint8_t* raw) {
@@ -107,10 +109,9 @@ sym_skinny_kernel(const __grid_constant__ CUtensorMap mapA_mk, const __grid_cons
     for (int kc = c0; kc < c1; kc++) {
       const int k0 = t0 * DT_M + kc * DT_KC;
       dt_mbar_wait(sm.full + stage, phase);
-      if (k0 < (T + 1) * DT_M) dt_stage_mma<false, false>(sm.A(stage), sm.B(stage), acc, wm, wn, g, q);
-      else dt_stage_mma<true, false>(sm.A(stage), sm.B(stage), acc, wm, wn, g, q);
-      __syncwarp();
-      if (lane == 0) dt_mbar_arrive(sm.empty + stage);
+      if (k0 < (T + 1) * DT_M) dt_stage_mma<false, false>(sm.a32(stage), sm.b32(stage), acc, wm, wn, g, q);
+      else dt_stage_mma<true, false>(sm.a32(stage), sm.b32(stage), acc, wm, wn, g, q);
+      dt_release_stage(sm.empty + stage, lane);
       if (++stage == DT_STAGES) { stage = 0; phase ^= 1; }
     }
     // epilogue: transposed store Wpart[ks][c][row]
@@ -178,9 +179,8 @@ syr2k_lower_kernel(const __grid_constant__ CUtensorMap mapVZ_km, const __grid_co
     int I, J64; syr2k_item(item, t0, I, J64);
     for (int kc = 0; kc < nkc; kc++) {
       dt_mbar_wait(sm.full + stage, phase);
-      dt_stage_mma<true, true>(sm.A(stage), sm.B(stage), acc, wm, wn, g, q);
-      __syncwarp();
-      if (lane == 0) dt_mbar_arrive(sm.empty + stage);
+      dt_stage_mma<true, true>(sm.a32(stage), sm.b32(stage), acc, wm, wn, g, q);
+      dt_release_stage(sm.empty + stage, lane);
       if (++stage == DT_STAGES) { stage = 0; phase ^= 1; }
     }
     // read-modify-write of the 128 x 64 tile in batches of two row blocks: 8 independent 16-byte loads in flight per
@@ -271,9 +271,8 @@ dt_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int im = item / nt, in = item - im * nt;
     for (int kc = 0; kc < nchunks; kc++) {
       dt_mbar_wait(sm.full + stage, phase);
-      dt_stage_mma<A_KM, B_KN>(sm.A(stage), sm.B(stage), acc, wm, wn, g, q);
-      __syncwarp();
-      if (lane == 0) dt_mbar_arrive(sm.empty + stage);
+      dt_stage_mma<A_KM, B_KN>(sm.a32(stage), sm.b32(stage), acc, wm, wn, g, q);
+      dt_release_stage(sm.empty + stage, lane);
       if (++stage == DT_STAGES) { stage = 0; phase ^= 1; }
     }
 #pragma unroll
@@ -332,6 +331,7 @@ int dt_resident_ctas(eb_ctx* c) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sym_skinny_kernel, DT_THREADS, DT_SMEM);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, syr2k_lower_kernel, DT_THREADS, DT_SMEM);
     cached = std::max(1, std::min(a, b));
+    if (const char* e = getenv("EB_DBG_SLOTS")) cached = std::max(1, atoi(e));
   }
   return cached * c->num_sms;
 }
@@ -356,6 +356,7 @@ int launch_sym_skinny(eb_ctx* c, const double* A, int64_t lda, int n, int t0, co
     const double eff = waves / std::ceil(waves) - 0.004 * ks;
     if (eff > beste + 1e-9) { beste = eff; best = ks; }
   }
+  if (const char* e = getenv("EB_DBG_KSPLIT")) best = std::max(1, std::min(atoi(e), max_ksplit));
   *ksplit_out = best;
   const int grid = std::min(ntile * best, slots);
   sym_skinny_kernel<<<grid, DT_THREADS, DT_SMEM, c->stream>>>(mk, km, mb, Wpart, ldw, n, t0, ntile, best);

@@ -212,7 +212,8 @@ __global__ void __launch_bounds__(256, 1) panel_qr_kernel(PanelParams p) {
 // Out[c][i] = a1 * sum_ks Wpart[ks][c][i] + a2 * Y1[c][i] + a3 * Y0[c][i]   for i in [i_lo, n), zero for [i_zero0, i_lo)
 __global__ void __launch_bounds__(256) combine_kernel(const double* __restrict__ Wpart, int ksplit, int64_t ldw, double* __restrict__ Out,
                                                       int64_t ldo, int n, int i_zero0, int i_lo, double a1, const double* __restrict__ Y1,
-                                                      double a2, const double* __restrict__ Y0, double a3, int64_t ldy) {
+                                                      double a2, const double* __restrict__ Y0, double a3, int64_t ldy,
+                                                      const double* __restrict__ Y2 = nullptr, double a4 = 0.0) {
   const int i = i_zero0 + blockIdx.x * 256 + threadIdx.x, c = blockIdx.y;
   if (i >= n) return;
   double v = 0.0;
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(256) combine_kernel(const double* __restrict__
     v *= a1;
     if (Y1) v += a2 * Y1[(size_t)c * ldy + i];
     if (Y0) v += a3 * Y0[(size_t)c * ldy + i];
+    if (Y2) v += a4 * Y2[(size_t)c * ldy + i];
   }
   Out[(size_t)c * ldo + i] = v;
 }
@@ -781,6 +783,25 @@ struct Eig2Work {
   int64_t ldv;
 };
 
+// ---- debugging aids (EB_DBG_REF_W / EB_DBG_REF_SYR2K): plain reference kernels for the two tensor-core products
+__global__ void __launch_bounds__(256) dbg_ref_w_kernel(const double* __restrict__ A, int64_t lda, int n, int r0, const double* __restrict__ V,
+                                                        int64_t ldv, double* __restrict__ Wt) {
+  const int i = blockIdx.x * 256 + threadIdx.x, c = blockIdx.y;
+  if (i >= n) return;
+  double s = 0.0;
+  if (i >= r0)
+    for (int k = r0; k < n; k++) s += (k <= i ? A[(size_t)i * lda + k] : A[(size_t)k * lda + i]) * V[(size_t)c * ldv + k];
+  Wt[(size_t)c * ldv + i] = s;
+}
+__global__ void __launch_bounds__(256) dbg_ref_syr2k_kernel(double* __restrict__ A, int64_t lda, int n, int lo, const double* __restrict__ VZ, int64_t ldv) {
+  const int col = lo + blockIdx.x * 256 + threadIdx.x, row = lo + blockIdx.y;
+  if (col >= n || row >= n) return;
+  if (col > row && (col >> 7) != (row >> 7)) return;          // lower tiles + complete diagonal 128-tiles
+  double s = 0.0;
+  for (int k = 0; k < 64; k++) s += VZ[(size_t)k * ldv + row] * VZ[(size_t)(64 + k) * ldv + col] + VZ[(size_t)(64 + k) * ldv + row] * VZ[(size_t)k * ldv + col];
+  A[(size_t)row * lda + col] -= s;
+}
+
 // Stage 1 + stage 2: A (n x n, lda, lower triangle + complete diagonal tiles valid; destroyed) -> d, e (unscaled)
 int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, double* e) {
   cudaStream_t st = c->stream;
@@ -818,6 +839,8 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
     attr_set = true;
   }
 
+  const bool dbg_sync = getenv("EB_DBG_SYNC") != nullptr, dbg_ref_w = getenv("EB_DBG_REF_W") != nullptr,
+             dbg_ref_syr2k = getenv("EB_DBG_REF_SYR2K") != nullptr;
   for (int j = 0; n - j - BW >= 2; j += BW) {
     const int r0 = j + BW, np = n - r0, t0 = r0 / DT_M;
     // ---- panel QR
@@ -835,9 +858,12 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
     if ((rc = coop_launch(c, (const void*)panel_qr_kernel, dim3(G), dim3(256), args, smem))) return rc;
     // ---- W = A22 V
     int ksplit = 1;
-    if ((rc = launch_sym_skinny(c, A, lda, n, t0, w.VZ, ldv, w.Wpart, ldv, MAX_KSPLIT, &ksplit))) return rc;
     const int i_z0 = t0 * DT_M;
-    {
+    if (dbg_ref_w) {
+      dbg_ref_w_kernel<<<dim3((n + 255) / 256, 64), 256, 0, st>>>(A, lda, n, r0, w.VZ, ldv, w.Wt);
+      EB_CHECK_LAUNCH(c);
+    } else {
+      if ((rc = launch_sym_skinny(c, A, lda, n, t0, w.VZ, ldv, w.Wpart, ldv, MAX_KSPLIT, &ksplit))) return rc;
       dim3 grid((n - i_z0 + 255) / 256, 64);
       combine_kernel<<<grid, 256, 0, st>>>(w.Wpart, ksplit, ldv, w.Wt, ldv, n, i_z0, r0, 1.0, nullptr, 0.0, nullptr, 0.0, ldv);
       EB_CHECK_LAUNCH(c);
@@ -852,7 +878,11 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
     left_mult_kernel<<<(n - i_z0 + 63) / 64, 256, 16384 * 8, st>>>(w.C1, w.Wt, w.C2, w.VZ, ldv, w.VZ + (size_t)64 * ldv, ldv, i_z0, n);
     EB_CHECK_LAUNCH(c);
     // ---- A22 -= V Z^T + Z V^T
-    if ((rc = launch_syr2k_lower(c, A, lda, n, t0, w.VZ, ldv))) return rc;
+    if (dbg_ref_syr2k) {
+      dbg_ref_syr2k_kernel<<<dim3((n - i_z0 + 255) / 256, n - i_z0), 256, 0, st>>>(A, lda, n, i_z0, w.VZ, ldv);
+      EB_CHECK_LAUNCH(c);
+    } else if ((rc = launch_syr2k_lower(c, A, lda, n, t0, w.VZ, ldv))) return rc;
+    if (dbg_sync) EB_CUDA(cudaStreamSynchronize(st));
   }
 
   // ---- stage 2
@@ -895,6 +925,15 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
   return 0;
 }
 
+// Cm[j][c] = dvec[j] * sum_chunks Gpart[chunk][j][c]   (coefficients of the deflation term L^T diag(d) (L X^T))
+__global__ void __launch_bounds__(256) defl_coef_kernel(const double* __restrict__ Gpart, int nchunk, const double* __restrict__ dvec,
+                                                        double* __restrict__ Cm) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  double v = 0.0;
+  for (int ch = 0; ch < nchunk; ch++) v += Gpart[(size_t)ch * 4096 + idx];
+  Cm[idx] = v * dvec[idx >> 6];
+}
+
 // Leading nvec eigenpairs of the symmetric matrix A (n x n, lda; lower triangle + complete diagonal tiles valid, preserved).
 // theta_h[nvec] (unscaled), vec_d: device [nvec][n] unit vectors.
 int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* theta_h, double* vec_d, int* iters_out, int* matvecs_out) {
@@ -907,6 +946,7 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
   auto take = [&](size_t cnt) { size_t o = off; off += (cnt + 15) & ~size_t(15); return o; };
   size_t oY[5];
   for (int i = 0; i < 5; i++) oY[i] = take((size_t)64 * ld);
+  const size_t oL = take((size_t)64 * ld), oCorr = take((size_t)64 * ld), oCm = take(4096), oDv = take(64);
   const size_t oWp = take((size_t)MAX_KSPLIT * 64 * ld), oGp = take((size_t)nchunk * 4096), oZ = take(4096), oTh = take(64), oRes = take(64),
                oErr = take(16);
   if ((rc = c->chfsiw.ensure(off))) return rc;
@@ -915,6 +955,8 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
   for (int i = 0; i < 5; i++) Y[i] = W + oY[i];
   double *Wpart = W + oWp, *Gpart = W + oGp, *Zm = W + oZ, *theta_d = W + oTh, *res_d = W + oRes;
   int* err_d = reinterpret_cast<int*>(W + oErr);
+  double *Lk = W + oL, *Corr = W + oCorr, *Cm = W + oCm, *dvec_d = W + oDv;
+  EB_CUDA(cudaMemsetAsync(Lk, 0, sizeof(double) * 64 * ld, st));
   EB_CUDA(cudaMemsetAsync(err_d, 0, sizeof(int), st));
   for (int i = 0; i < 5; i++) EB_CUDA(cudaMemsetAsync(Y[i], 0, sizeof(double) * 64 * ld, st));
   constexpr int SM64x2 = 2 * 64 * 65 * 8;
@@ -929,10 +971,25 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
   const int lm_grid = (n + 63) / 64;
   int nmat = 0;
 
+  // Locked (converged) leading Ritz vectors live in Lk (rows >= nlock are zero).  With nlock > 0 the filter runs on the
+  // deflated operator A' = A - L^T diag(theta_j - c) L, which moves the locked eigenvalues to the centre of the damped
+  // interval: outlier eigenvalues (population structure puts them 100-1000x above the bulk) then no longer bound the
+  // filter degree through the 1e8 dynamic-range budget, and rounding-level components along them cannot grow.
+  int nlock = 0;
   auto matvec = [&](const double* X, double* Out, double a1, const double* Y1, double a2, const double* Y0, double a3) -> int {
     int ks = 1, r;
     if ((r = launch_sym_skinny(c, A, lda, n, 0, X, ld, Wpart, ld, MAX_KSPLIT, &ks))) return r;
-    combine_kernel<<<cgrid, 256, 0, st>>>(Wpart, ks, ld, Out, ld, n, 0, 0, a1, Y1, a2, Y0, a3, ld);
+    if (nlock > 0) {
+      gram64_kernel<<<nchunk, 256, 0, st>>>(Lk, ld, X, ld, 0, n, gch, Gpart);
+      EB_CHECK_LAUNCH(c);
+      defl_coef_kernel<<<16, 256, 0, st>>>(Gpart, nchunk, dvec_d, Cm);
+      EB_CHECK_LAUNCH(c);
+      left_mult_kernel<<<lm_grid, 256, 16384 * 8, st>>>(Cm, Lk, nullptr, nullptr, ld, Corr, ld, 0, n);
+      EB_CHECK_LAUNCH(c);
+      combine_kernel<<<cgrid, 256, 0, st>>>(Wpart, ks, ld, Out, ld, n, 0, 0, a1, Y1, a2, Y0, a3, ld, Corr, -a1);
+    } else {
+      combine_kernel<<<cgrid, 256, 0, st>>>(Wpart, ks, ld, Out, ld, n, 0, 0, a1, Y1, a2, Y0, a3, ld);
+    }
     EB_CHECK_LAUNCH(c);
     nmat++;
     return 0;
@@ -966,8 +1023,14 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
   bool converged = false;
   const int maxouter = 80;
   for (outer = 0; outer < maxouter; outer++) {
-    // Rayleigh-Ritz
-    if ((rc = matvec(V, AV, 1.0, nullptr, 0.0, nullptr, 0.0))) return rc;
+    // Rayleigh-Ritz (on A itself)
+    {
+      const int keep = nlock;
+      nlock = 0;
+      rc = matvec(V, AV, 1.0, nullptr, 0.0, nullptr, 0.0);
+      nlock = keep;
+      if (rc) return rc;
+    }
     gram64_kernel<<<nchunk, 256, 0, st>>>(V, ld, AV, ld, 0, n, gch, Gpart);
     EB_CHECK_LAUNCH(c);
     jacobi64_kernel<<<1, 256, SM64x2, st>>>(Gpart, nchunk, theta_d, Zm);
@@ -983,12 +1046,14 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
     EB_CUDA(cudaMemcpyAsync(res2, res_d, sizeof(double) * 64, cudaMemcpyDeviceToHost, st));
     EB_CUDA(cudaStreamSynchronize(st));
     const double anorm = std::max(fabs(th[0]), fabs(th[63]));
+    // lock the leading Ritz pairs that have reached the final tolerance (monotone: a locked pair stays locked)
+    while (nlock < nvec && sqrt(res2[nlock]) <= tol * anorm) nlock++;
     double worst = 0.0;
-    for (int i = 0; i < nvec; i++) worst = std::max(worst, sqrt(res2[i]));
+    for (int i = nlock; i < nvec; i++) worst = std::max(worst, sqrt(res2[i]));
     if (debug) fprintf(stderr, "[chfsi] outer %d matvecs %d theta0 %.6e theta_k %.6e cut %.6e worst_res/anorm %.3e\n", outer, nmat, th[0],
                        th[std::max(nvec - 1, 0)], th[63], worst / anorm);
     // converged: residual at the rounding floor of an n-term FP64 mat-vec, or stagnating just above it
-    if (!(anorm > 0.0) || worst <= tol * anorm) { converged = true; break; }
+    if (!(anorm > 0.0) || nlock >= nvec || worst <= tol * anorm) { converged = true; break; }
     if (worst <= 1e-11 * anorm && worst > 0.5 * prev_worst && prev_worst > 0.5 * prev2_worst) { converged = true; break; }
     prev2_worst = prev_worst; prev_worst = worst;
     // Chebyshev filter damping [lo, cut]
@@ -996,15 +1061,25 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
     lo = std::min(lo, cut);
     double cc = 0.5 * (cut + lo), ee = 0.5 * (cut - lo);
     if (!(ee > 0.0)) ee = 1e-3 * anorm;
-    const double xi1 = std::max((th[0] - cc) / ee, 1.0 + 1e-12);
+    const double th_ref = th[nlock];             // largest eigenvalue the filter still has to resolve
+    const double xi1 = std::max((th_ref - cc) / ee, 1.0 + 1e-12);
     int deg = (int)floor(acosh(1e8) / std::max(acosh(xi1), 1e-6));
     deg = std::max(2, std::min(deg, 40));
-    double sigma1 = ee / (th[0] - cc), sigma = sigma1;
+    double sigma1 = ee / std::max(th_ref - cc, ee * (1.0 + 1e-12)), sigma = sigma1;
+    if (nlock > 0) {
+      double dv[64];
+      for (int j = 0; j < 64; j++) dv[j] = j < nlock ? th[j] - cc : 0.0;
+      EB_CUDA(cudaMemcpyAsync(dvec_d, dv, sizeof(dv), cudaMemcpyHostToDevice, st));
+      EB_CUDA(cudaStreamSynchronize(st));
+      EB_CUDA(cudaMemcpyAsync(Lk, V, sizeof(double) * (size_t)nlock * ld, cudaMemcpyDeviceToDevice, st));
+    }
     // Y1 = (A V - c V) sigma1/e   (A V is already in AV)
     {
       const double a1 = sigma1 / ee;
       combine_kernel<<<cgrid, 256, 0, st>>>(AV, 1, ld, Ya, ld, n, 0, 0, a1, V, -cc * a1, nullptr, 0.0, ld);
       EB_CHECK_LAUNCH(c);
+      // under the deflated operator the locked columns map to (c - c) v = 0
+      if (nlock > 0) EB_CUDA(cudaMemsetAsync(Ya, 0, sizeof(double) * (size_t)nlock * ld, st));
     }
     double *y0 = V, *y1 = Ya, *y2 = Yb;          // AV and Yc are free scratch now
     double* spare = AV;
@@ -1016,7 +1091,8 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
       if (jd == 2) spare = t;                    // V's buffer joins the rotation after its last use
       sigma = sn;
     }
-    // orthonormalise the filtered block -> V
+    // the locked columns go back in unchanged, then orthonormalise the block -> V
+    if (nlock > 0) EB_CUDA(cudaMemcpyAsync(y1, Lk, sizeof(double) * (size_t)nlock * ld, cudaMemcpyDeviceToDevice, st));
     double* X = y1; double* tmp = Yc;
     if ((rc = chol_qr(X, tmp))) return rc;
     // re-assign buffer roles: V = X, the other four are scratch

@@ -235,6 +235,9 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restri
           }
         }
       }
+      // release the stage: every lane fences its own shared-memory reads, the warp converges, lane 0 arrives (the
+      // arrive alone does not order the still outstanding operand loads of the last k-step -- see dmma_tile.cuh)
+      asm volatile("fence.acq_rel.cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + stage);
       if (threadIdx.x == 0) ahead--;

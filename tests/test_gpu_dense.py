@@ -66,3 +66,14 @@ def test_dropin_eigvecs_symbols():
         if ob.ref() is not None:
             rl, rv = ob.ref_eigvecs(A)
             assert np.abs(ev - rl).max() <= 1e-12 * max(1.0, np.abs(w).max())
+
+
+def test_dense_syrk_many_tiles_per_cta(ctx):
+    """4608 rows: the tensor-core SYRK runs 4-5 output tiles per persistent CTA (see test_two_stage_tridiagonal_many_tiles_per_cta)"""
+    n = 4608
+    rs = np.random.RandomState(5)
+    T = rs.randn(192, n); T -= T.mean(axis=1, keepdims=True)
+    want = T.T @ T
+    for rep in range(3):
+        y, X = ctx.grm_dense([T[:64], T[64:]], n, want_xtx=True)
+        assert np.abs(X * y - want).max() <= 1e-12 * np.abs(want).max()

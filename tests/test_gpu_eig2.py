@@ -52,6 +52,27 @@ def test_two_stage_tridiagonal_is_similar(ctx, n):
     assert abs(d.sum() - np.trace(A)) <= 1e-12 * np.trace(A)
 
 
+def test_two_stage_tridiagonal_many_tiles_per_cta(ctx):
+    """n = 4608: 36 row tiles -> 1332 rank-128 update tiles on 296 resident CTAs (4-5 per CTA).  This is the regime in
+    which a stage of the TMA ring was once released while operand loads of its last k-step were still outstanding
+    (band matrices differed from run to run, eigenvalue errors 1e-5 .. O(1) from n = 4096 up; sizes <= 3584 passed)."""
+    n = 4608
+    rs = np.random.RandomState(n)
+    X = rs.randn(n, 2 * n)
+    A = X @ X.T / (2 * n)
+    w = np.linalg.eigvalsh(A)[::-1]
+    bands = []
+    for rep in range(2):
+        d, e, band = ctx.debug_tridiag(A)
+        bands.append(band)
+        ab = np.zeros((65, n))
+        for k in range(65):
+            ab[k, :n - k] = band[:n - k, k]
+        _eval_check(sl.eigvals_banded(ab, lower=True)[::-1], w)
+        _eval_check(sl.eigvalsh_tridiagonal(d, e)[::-1], w)
+    assert np.array_equal(bands[0], bands[1]), "band reduction is not bit-reproducible"
+
+
 @pytest.mark.parametrize("n,npops", [(700, 4), (1537, 1), (2050, 6)])
 def test_eigvecs_two_stage_vs_lapack(ctx2, n, npops):
     A = _spd(n, 7 + n, npops=npops)
@@ -66,6 +87,27 @@ def test_eigvecs_two_stage_vs_lapack(ctx2, n, npops):
         assert abs(np.linalg.norm(vec[i]) - 1.0) < 1e-12
         if gap > 1e-4 * w[0]:
             assert abs(abs(float(vec[i] @ v[i])) - 1.0) <= COS_TOL, (i, gap)
+
+
+def test_eigvecs_outliers_far_above_a_dense_bulk(ctx2):
+    """Population structure at scale: a few eigenvalues 100-1000x above a densely packed bulk edge (what 20,000 x 1.2M
+    structured genotypes produce).  The subspace iteration must lock the outliers and keep filtering the bulk edge
+    (without locking + deflation the 1e8 dynamic-range budget caps the filter at degree 2 and it never converges)."""
+    n = 1700
+    rs = np.random.RandomState(11)
+    Q, _ = np.linalg.qr(rs.randn(n, n))
+    w = np.concatenate([[900.0, 520.0, 310.0], 1.7 - 1.2 * (np.arange(n - 3) / (n - 3.0)) ** (2.0 / 3.0)])   # edge ~ j^(2/3) law
+    A = (Q * w) @ Q.T
+    A = 0.5 * (A + A.T)
+    lam, vec = ctx2.eigvecs(A, nvec=10)
+    assert ctx2.timings()["eig_method"] == 2
+    we = np.linalg.eigvalsh(A)[::-1]
+    _eval_check(lam, we)
+    for i in range(10):
+        assert np.linalg.norm(A @ vec[i] - lam[i] * vec[i]) <= 2e-13 * we[0], i
+    assert np.abs(vec @ vec.T - np.eye(10)).max() < 1e-12
+    for i in range(3):
+        assert abs(abs(float(vec[i] @ Q[:, i])) - 1.0) <= COS_TOL
 
 
 def test_eigvecs_two_stage_degenerate(ctx2):

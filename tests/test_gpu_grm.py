@@ -98,3 +98,27 @@ def test_grm_large_property(ctx):
     assert abs(np.trace(X) - (nind - 1)) < 1e-9 * nind
     assert np.abs(X.sum(1)).max() < 1e-8 * np.abs(X).max() * nind
     assert r["nused"] > 0.99 * nsnp
+
+
+def test_grm_many_items_per_cta_exact_and_repeatable(ctx):
+    """3000 x 60000 with missing data and structure: ~20 (tile, SNP-chunk) items per persistent CTA.  The result must be
+    bit-identical from run to run (fixed-order split-K) and agree with an independent FP64 product of the decoded matrix."""
+    import torch
+    nsnp, nind = 60000, 3000
+    rl = synth.rlen_for(nind)
+    buf = torch.empty((nsnp, rl), dtype=torch.uint8, device="cuda")
+    ctx.synth_packed_device(buf.data_ptr(), nsnp, rl, nind, seed=3, missing=0.1, npops=3, delta=0.1)
+    ctx.adopt_packed_device(buf.data_ptr(), nsnp, rl, nind); ctx.set_rows(None)
+    r = ctx.grm(want_xtx=True)
+    a = r["XTX"] * r["y"]
+    b = ctx.grm(want_xtx=True, want_snp=False)
+    assert np.array_equal(a, b["XTX"] * b["y"])
+    P = buf.cpu().numpy()
+    ref = torch.zeros((nind, nind), dtype=torch.float64, device="cuda")
+    xm = torch.from_numpy(r["xmean"]).cuda(); xf = torch.from_numpy(r["xfancy"]).cuda(); us = torch.from_numpy(r["used"].astype(np.float64)).cuda()
+    for s0 in range(0, nsnp, 20000):
+        g = torch.from_numpy(synth.unpack(P[s0:s0 + 20000], nind).astype(np.float64)).cuda()
+        x = torch.where(g < 0, torch.zeros_like(g), g * xf[s0:s0 + 20000, None] - xm[s0:s0 + 20000, None]) * us[s0:s0 + 20000, None]
+        ref += x.T @ x
+    ref = ref.cpu().numpy()
+    assert np.abs(a - ref).max() <= 1e-12 * np.abs(ref).max()
