@@ -119,6 +119,7 @@ struct eb_ctx {
   eb::DevBuf<double> eigw;        // misc vectors
   eb::DevBuf<double> eigV, eigW;  // panels
   eb::DevBuf<double> lambda_d, zvec_d;
+  int64_t zvec_ld = 0;             // row pitch of zvec_d after the last solve (n, or n rounded up to even for the full basis)
   eb::DevBuf<double> eig2w, chfsiw;   // two-stage reduction / subspace-iteration workspaces (eig2_kernels.cu)
   std::vector<double> ritz;        // scaled Ritz values of the last subspace iteration
   double* dbg_band_h = nullptr;    // eb_debug_tridiag only
@@ -155,7 +156,7 @@ bool eig_uses_two_stage(const eb_ctx* c, int n, int nvec);
 // eig2_gemm.cu
 int launch_syrk_lower_add(eb_ctx* c, double* A, int64_t lda, int n, const double* T, int64_t ldt, int krows);
 int launch_gemm(eb_ctx* c, bool a_km, bool b_kn, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
-                int M, int N, int K);
+                int M, int N, int K, double alpha = 1.0, double beta = 0.0);
 // grm_kernel.cu (dense path)
 int grm_dense_finalize(eb_ctx* c);
 // eig2_kernels.cu

@@ -232,7 +232,7 @@ syr2k_lower_kernel(const __grid_constant__ CUtensorMap mapVZ_km, const __grid_co
 template <bool A_KM, bool B_KN>
 __global__ void __launch_bounds__(DT_THREADS, 2)
 dt_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, double* __restrict__ C, int64_t ldc,
-               int M, int N, int K, int mt, int nt) {
+               int M, int N, int K, int mt, int nt, double alpha, double beta) {
   extern __shared__ __align__(128) uint8_t dt_raw[];
   const DtSmem sm = dt_setup(dt_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -282,8 +282,14 @@ dt_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int u = 0; u < 4; u++) {
         const int col = in * DT_N + wn * 32 + u * 8 + q * 2;
         if (row < M) {
-          if (col + 1 < N) *reinterpret_cast<double2*>(C + (size_t)row * ldc + col) = make_double2(acc[t][u][0], acc[t][u][1]);
-          else if (col < N) C[(size_t)row * ldc + col] = acc[t][u][0];
+          double* cp = C + (size_t)row * ldc + col;
+          if (col + 1 < N) {
+            double2 v = make_double2(alpha * acc[t][u][0], alpha * acc[t][u][1]);
+            if (beta != 0.0) { const double2 o = __ldcg(reinterpret_cast<const double2*>(cp)); v.x += beta * o.x; v.y += beta * o.y; }
+            *reinterpret_cast<double2*>(cp) = v;
+          } else if (col < N) {
+            cp[0] = alpha * acc[t][u][0] + (beta != 0.0 ? beta * cp[0] : 0.0);
+          }
         }
         acc[t][u][0] = acc[t][u][1] = 0.0;
       }
@@ -292,7 +298,8 @@ dt_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 template <bool A_KM, bool B_KN>
-static int launch_gemm_t(eb_ctx* c, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int N, int K) {
+static int launch_gemm_t(eb_ctx* c, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int M, int N, int K,
+                         double alpha, double beta) {
   CUtensorMap ma, mb;
   int rc;
   if (A_KM) { if ((rc = make_f64_tensormap(&ma, A, K, M, lda, DT_LD_M, DT_KC))) return rc; }
@@ -306,20 +313,20 @@ static int launch_gemm_t(eb_ctx* c, const double* A, int64_t lda, const double* 
   }
   const int mt = (M + DT_M - 1) / DT_M, nt = (N + DT_N - 1) / DT_N;
   const int grid = std::min(mt * nt, 2 * c->num_sms);
-  dt_gemm_kernel<A_KM, B_KN><<<grid, DT_THREADS, DT_SMEM, c->stream>>>(ma, mb, C, ldc, M, N, K, mt, nt);
+  dt_gemm_kernel<A_KM, B_KN><<<grid, DT_THREADS, DT_SMEM, c->stream>>>(ma, mb, C, ldc, M, N, K, mt, nt, alpha, beta);
   EB_CHECK_LAUNCH(c);
   return 0;
 }
 
-// C (M x N, ldc; must be 16-byte aligned rows) = op(A) op(B)^T on the FP64 tensor cores; a_km / b_kn select the storage
+// C (M x N, ldc; must be 16-byte aligned rows) = alpha op(A) op(B)^T + beta C on the FP64 tensor cores; a_km / b_kn select the storage
 // of the operands (see dt_gemm_kernel).  Leading dimensions must be even (TMA strides are multiples of 16 bytes).
 int launch_gemm(eb_ctx* c, bool a_km, bool b_kn, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
-                int M, int N, int K) {
+                int M, int N, int K, double alpha, double beta) {
   if ((lda & 1) || (ldb & 1) || (ldc & 1)) { set_error("launch_gemm: leading dimensions must be even"); return EB_ERR_ARG; }
-  if (!a_km && !b_kn) return launch_gemm_t<false, false>(c, A, lda, B, ldb, C, ldc, M, N, K);
-  if (a_km && b_kn) return launch_gemm_t<true, true>(c, A, lda, B, ldb, C, ldc, M, N, K);
-  if (a_km) return launch_gemm_t<true, false>(c, A, lda, B, ldb, C, ldc, M, N, K);
-  return launch_gemm_t<false, true>(c, A, lda, B, ldb, C, ldc, M, N, K);
+  if (!a_km && !b_kn) return launch_gemm_t<false, false>(c, A, lda, B, ldb, C, ldc, M, N, K, alpha, beta);
+  if (a_km && b_kn) return launch_gemm_t<true, true>(c, A, lda, B, ldb, C, ldc, M, N, K, alpha, beta);
+  if (a_km) return launch_gemm_t<true, false>(c, A, lda, B, ldb, C, ldc, M, N, K, alpha, beta);
+  return launch_gemm_t<false, true>(c, A, lda, B, ldb, C, ldc, M, N, K, alpha, beta);
 }
 
 int dt_resident_ctas(eb_ctx* c) {

@@ -11,7 +11,9 @@
 //   3. leading eigenvectors of the tridiagonal by inverse iteration with cluster re-orthogonalisation
 //      (dstein scheme), then back-transformation through the stored reflectors.
 #include <algorithm>
+#include <algorithm>
 #include <cmath>
+#include <vector>
 #include "common.cuh"
 
 namespace eb {
@@ -407,6 +409,357 @@ __global__ void __launch_bounds__(1024) tri_backtransform_kernel(const double* _
   for (int c = threadIdx.x; c < n; c += blockDim.x) z[c] *= inv;
 }
 
+// ------------------------------------------------------------------------------------------ all eigenvectors (nvec > 64)
+// The single-block inverse iteration above is sequential in the vectors and the per-vector back-transformation re-reads the
+// whole reflector matrix for every vector; both are fine for the 10-40 leading vectors smartpca prints, not for the full
+// basis that eigvecs() promises (eigsubs.c:39-55) and shrinkmode consumes (smartpca.c:4292, 4340-4347).  Full-basis path:
+//   tri_invit_batch_kernel : one THREAD per eigenvector; dgttrf-style pivoted LU of T - shift I and the dgtts2-style solves
+//                            run sequentially in the thread over interleaved work arrays ([row][vector] => coalesced)
+//   tri_invit_cluster_kernel: groups of numerically coincident eigenvalues only: sequential inverse iteration with
+//                            re-orthogonalisation inside every iteration (one block per group)
+//   blocked back-transformation: 64 reflectors at a time as I - V T V^T (dlarft), applied to all vectors with two FP64
+//                            tensor-core GEMMs per panel (launch_gemm), restricted to the columns the reflectors touch.
+__global__ void __launch_bounds__(128) tri_invit_batch_kernel(int n, int v0, int nb, const double* __restrict__ d, const double* __restrict__ e,
+                                                              const double* __restrict__ shifts, double tn, double* __restrict__ dl,
+                                                              double* __restrict__ dd, double* __restrict__ du, double* __restrict__ du2,
+                                                              double* __restrict__ b, uint8_t* __restrict__ ipiv) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb) return;
+  const int v = v0 + t;
+#define IX(i) ((size_t)(i) * nb + t)
+  const double shift = shifts[v];
+  const double piv0 = 2.220446049250313e-16 * tn;
+  {
+    double dd_i = d[0] - shift, du_i = n > 1 ? e[0] : 0.0;
+    for (int i = 0; i < n - 1; i++) {
+      double dl_i = e[i];
+      double dd_n = d[i + 1] - shift, du_n = i + 1 < n - 1 ? e[i + 1] : 0.0, du2_i = 0.0;
+      uint8_t pv = 0;
+      if (fabs(dd_i) >= fabs(dl_i)) {
+        if (fabs(dd_i) < piv0) dd_i = piv0;
+        const double f = dl_i / dd_i;
+        dl_i = f; dd_n -= f * du_i;
+      } else {
+        const double f = dd_i / dl_i;
+        dd_i = dl_i; dl_i = f;
+        const double tt = du_i;
+        du_i = dd_n; dd_n = tt - f * du_i;
+        if (i < n - 2) { du2_i = du_n; du_n = -f * du_n; }
+        pv = 1;
+      }
+      dl[IX(i)] = dl_i; dd[IX(i)] = dd_i; du[IX(i)] = du_i; du2[IX(i)] = du2_i; ipiv[IX(i)] = pv;
+      dd_i = dd_n; du_i = du_n;
+    }
+    if (fabs(dd_i) < piv0) dd_i = piv0;
+    dd[IX(n - 1)] = dd_i;
+  }
+  for (int i = 0; i < n; i++) {            // deterministic pseudo-random start (same generator as tri_invit_kernel)
+    uint32_t hsh = (uint32_t)(i * 2654435761u) ^ (uint32_t)((v + 1) * 40503u);
+    hsh ^= hsh >> 15; hsh *= 2246822519u; hsh ^= hsh >> 13;
+    b[IX(i)] = 0.5 + (double)(hsh & 0xFFFF) / 65536.0;
+  }
+  double sc = 1.0;
+  for (int iter = 0; iter < 4; iter++) {
+    double cur = b[IX(0)] * sc;              // forward: L y = P b
+    for (int i = 0; i < n - 1; i++) {
+      double nxt = b[IX(i + 1)] * sc;
+      const double m = dl[IX(i)];
+      if (ipiv[IX(i)]) { const double tt = cur; cur = nxt; nxt = tt - m * cur; }
+      else nxt -= m * cur;
+      b[IX(i)] = cur;
+      cur = nxt;
+    }
+    double x1 = cur / dd[IX(n - 1)];         // backward: U x = y
+    b[IX(n - 1)] = x1;
+    double ss = x1 * x1, x2 = 0.0;
+    if (n > 1) {
+      const double x0 = (b[IX(n - 2)] - du[IX(n - 2)] * x1) / dd[IX(n - 2)];
+      b[IX(n - 2)] = x0; ss += x0 * x0; x2 = x1; x1 = x0;
+    }
+    for (int i = n - 3; i >= 0; i--) {
+      const double x0 = (b[IX(i)] - du[IX(i)] * x1 - du2[IX(i)] * x2) / dd[IX(i)];
+      b[IX(i)] = x0; ss += x0 * x0; x2 = x1; x1 = x0;
+    }
+    sc = 1.0 / sqrt(ss);
+  }
+  for (int i = 0; i < n; i++) b[IX(i)] *= sc;
+#undef IX
+}
+
+// Zt[v0 + t][i] = Bi[i][t]   (interleaved work array -> one contiguous row per eigenvector)
+__global__ void __launch_bounds__(256) invit_transpose_kernel(const double* __restrict__ Bi, int n, int nb, int v0, double* __restrict__ Zt, int64_t ldz) {
+  __shared__ double tile[32][33];
+  const int t0 = blockIdx.x * 32, i0 = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = (i0 + r < n && t0 + tx < nb) ? Bi[(size_t)(i0 + r) * nb + t0 + tx] : 0.0;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    if (t0 + r < nb && i0 + tx < n) Zt[(size_t)(v0 + t0 + r) * ldz + i0 + tx] = tile[tx][r];
+}
+
+// One block per group of numerically coincident eigenvalues (rows [start, start + len) of Zt): inverse iteration with
+// re-orthogonalisation against the earlier members INSIDE every iteration (dstein), as tri_invit_kernel does.  Independent
+// inverse iterations followed by Gram-Schmidt are not enough here: within a coincident group every start vector converges
+// towards the same few directions and the orthogonalisation then cancels catastrophically (seen as 1e-5 orthogonality with
+// a 230-fold zero eigenvalue).  work: 5n doubles per block, ipiv: n ints per block.
+__global__ void __launch_bounds__(1024) tri_invit_cluster_kernel(int n, const double* __restrict__ d, const double* __restrict__ e,
+                                                                 const double* __restrict__ shifts, double tn, const int* __restrict__ starts,
+                                                                 const int* __restrict__ lens, double* __restrict__ work_all,
+                                                                 int* __restrict__ ipiv_all, double* __restrict__ Zt, int64_t ldz) {
+  __shared__ double red[32];
+  double* work = work_all + (size_t)blockIdx.x * 5 * n;
+  int* ipiv = ipiv_all + (size_t)blockIdx.x * n;
+  double* dl = work; double* dd = work + n; double* du = work + 2 * n; double* du2 = work + 3 * n; double* b = work + 4 * n;
+  const int s0 = starts[blockIdx.x], len = lens[blockIdx.x];
+  const double eps = 2.220446049250313e-16;
+  for (int v = s0; v < s0 + len; v++) {
+    const double shift = shifts[v];
+    double* z = Zt + (size_t)v * ldz;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      uint32_t hsh = (uint32_t)(i * 2654435761u) ^ (uint32_t)((v + 1) * 40503u);
+      hsh ^= hsh >> 15; hsh *= 2246822519u; hsh ^= hsh >> 13;
+      b[i] = 0.5 + (double)(hsh & 0xFFFF) / 65536.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < n; i++) { dd[i] = d[i] - shift; if (i < n - 1) { dl[i] = e[i]; du[i] = e[i]; } du2[i] = 0.0; }
+      const double piv0 = eps * tn;
+      for (int i = 0; i < n - 1; i++) {
+        if (fabs(dd[i]) >= fabs(dl[i])) {
+          if (fabs(dd[i]) < piv0) dd[i] = piv0;
+          const double f = dl[i] / dd[i];
+          dl[i] = f; dd[i + 1] -= f * du[i]; ipiv[i] = 0;
+        } else {
+          const double f = dd[i] / dl[i];
+          dd[i] = dl[i]; dl[i] = f;
+          const double t = du[i];
+          du[i] = dd[i + 1]; dd[i + 1] = t - f * du[i];
+          if (i < n - 2) { du2[i] = du[i + 1]; du[i + 1] = -f * du[i + 1]; }
+          ipiv[i] = 1;
+        }
+      }
+      if (fabs(dd[n - 1]) < piv0) dd[n - 1] = piv0;
+    }
+    __syncthreads();
+    for (int iter = 0; iter < 4; iter++) {
+      if (threadIdx.x == 0) {
+        for (int i = 0; i < n - 1; i++) {
+          if (ipiv[i]) { const double t = b[i]; b[i] = b[i + 1]; b[i + 1] = t - dl[i] * b[i]; }
+          else b[i + 1] -= dl[i] * b[i];
+        }
+        b[n - 1] /= dd[n - 1];
+        if (n > 1) b[n - 2] = (b[n - 2] - du[n - 2] * b[n - 1]) / dd[n - 2];
+        for (int i = n - 3; i >= 0; i--) b[i] = (b[i] - du[i] * b[i + 1] - du2[i] * b[i + 2]) / dd[i];
+      }
+      __syncthreads();
+      for (int pass = 0; pass < 2; pass++)
+        for (int u = s0; u < v; u++) {
+          const double* zu = Zt + (size_t)u * ldz;
+          double sacc = 0.0;
+          for (int i = threadIdx.x; i < n; i += blockDim.x) sacc += zu[i] * b[i];
+          sacc = block_sum(sacc, red);
+          for (int i = threadIdx.x; i < n; i += blockDim.x) b[i] -= sacc * zu[i];
+          __syncthreads();
+        }
+      double q = 0.0;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) q += b[i] * b[i];
+      q = block_sum(q, red);
+      const double inv = 1.0 / sqrt(q);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) b[i] *= inv;
+      __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) z[i] = b[i];
+    __syncthreads();
+  }
+}
+
+// Vp[k][c] = reflector j0 + k as a dense row (zero up to column j0 + k, then row j0 + k of A; rows >= kp zero)
+__global__ void __launch_bounds__(256) bt_extract_kernel(const double* __restrict__ A, int64_t lda, int n, int j0, int kp, double* __restrict__ Vp,
+                                                         int64_t ldv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+  if (c >= ldv) return;
+  const int j = j0 + k;
+  Vp[(size_t)k * ldv + c] = (k < kp && c > j && c < n) ? A[(size_t)j * lda + c] : 0.0;
+}
+
+// partial Gram of the 64 rows of Vp over a column chunk: Gp[chunk][a][b]
+__global__ void __launch_bounds__(256) bt_gram_kernel(const double* __restrict__ Vp, int64_t ldv, int c0, int n, int chunk, double* __restrict__ Gp) {
+  __shared__ double Xs[64][33];
+  const int tid = threadIdx.x, ta = tid >> 4, tc = tid & 15;
+  const int lo = c0 + blockIdx.x * chunk, hi = min(n, lo + chunk);
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+  for (int s0 = lo; s0 < hi; s0 += 32) {
+    __syncthreads();
+    for (int idx = tid; idx < 64 * 32; idx += 256) {
+      const int r = idx >> 5, ii = idx & 31, i = s0 + ii;
+      Xs[r][ii] = i < hi ? Vp[(size_t)r * ldv + i] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int ii = 0; ii < 32; ii++) {
+      double xa[4], xb[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) xa[a] = Xs[ta * 4 + a][ii];
+#pragma unroll
+      for (int b = 0; b < 4; b++) xb[b] = Xs[tc * 4 + b][ii];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] += xa[a] * xb[b];
+    }
+  }
+  double* out = Gp + (size_t)blockIdx.x * 4096;
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) out[(ta * 4 + a) * 64 + tc * 4 + b] = acc[a][b];
+}
+
+// T of the block reflector H_j0 ... H_{j0+63} = I - V T V^T (dlarft, forward columnwise): T[0:k,k] = -tau_k T[0:k,0:k] (V^T v_k)
+__global__ void __launch_bounds__(256) bt_tfactor_kernel(const double* __restrict__ Gp, int nchunk, const double* __restrict__ tau, int kp,
+                                                         double* __restrict__ Gs, double* __restrict__ T) {
+  __shared__ double Ts[64 * 64];
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < 4096; idx += 256) {
+    double g = 0.0;
+    for (int ch = 0; ch < nchunk; ch++) g += Gp[(size_t)ch * 4096 + idx];
+    Gs[idx] = g; Ts[idx] = 0.0;
+  }
+  __threadfence_block();
+  __syncthreads();
+  for (int k = 0; k < 64; k++) {
+    const double tk = k < kp ? tau[k] : 0.0;
+    if (tid < k && tk != 0.0) {
+      double sacc = 0.0;
+      for (int m = tid; m < k; m++) sacc += Ts[tid * 64 + m] * Gs[m * 64 + k];
+      Ts[tid * 64 + k] = -tk * sacc;
+    }
+    if (tid == k) Ts[k * 64 + k] = tk;
+    __syncthreads();
+  }
+  for (int idx = tid; idx < 4096; idx += 256) T[idx] = Ts[idx];
+}
+
+// W2[v][a] = sum_b W[v][b] T[a][b]
+__global__ void __launch_bounds__(256) bt_wt_kernel(const double* __restrict__ W, const double* __restrict__ T, int nvec, double* __restrict__ W2) {
+  __shared__ double Ts[64][65];
+  for (int idx = threadIdx.x; idx < 4096; idx += 256) Ts[idx >> 6][idx & 63] = T[idx];
+  __syncthreads();
+  const int a = threadIdx.x & 63;
+  for (int v = blockIdx.x * 4 + (threadIdx.x >> 6); v < nvec; v += gridDim.x * 4) {
+    const double* w = W + (size_t)v * 64;
+    double sacc = 0.0;
+#pragma unroll 8
+    for (int b = 0; b < 64; b++) sacc += w[b] * Ts[a][b];
+    W2[(size_t)v * 64 + a] = sacc;
+  }
+}
+
+__global__ void __launch_bounds__(256) normalize_rows_full_kernel(double* __restrict__ Zt, int64_t ldz, int n) {
+  __shared__ double red[32];
+  double* z = Zt + (size_t)blockIdx.x * ldz;
+  double q = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) q += z[i] * z[i];
+  q = block_sum(q, red);
+  const double inv = 1.0 / sqrt(q);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) z[i] *= inv;
+}
+
+// eigenvectors 0..nvec-1 of the tridiagonal (d, e; lam descending on the device and the host) and their back-transformation
+// through the reflectors kept in the rows of A.  Result: c->zvec_d, [nvec][ldz] with ldz = n rounded up to even.
+static int full_basis(eb_ctx* c, double* A, int64_t lda, int n, int nvec, const double* d, const double* e, const double* tau,
+                      const std::vector<double>& lam_h, double tn, int64_t* ldz_out) {
+  cudaStream_t st = c->stream;
+  int rc;
+  const int64_t ldz = ((int64_t)n + 1) & ~1ll;
+  *ldz_out = ldz;
+  if ((rc = c->zvec_d.ensure((size_t)nvec * ldz))) return rc;
+  EB_CUDA(cudaMemsetAsync(c->zvec_d.p, 0, sizeof(double) * (size_t)nvec * ldz, st));
+  // shifts: dstein's separation of near-coincident eigenvalues; groups that need re-orthogonalisation
+  const double eps = 2.220446049250313e-16;
+  std::vector<double> shifts(nvec);
+  std::vector<int> starts, lens;
+  {
+    const double tight = 1e-6 * tn;
+    double prev = 0.0;
+    int cs = 0;
+    for (int v = 0; v < nvec; v++) {
+      double sh = lam_h[v];
+      if (v > 0) {
+        const double sep = 10.0 * eps * fabs(sh) + 10.0 * eps * tn * 1e-3;
+        if (prev - sh < sep) sh = prev - sep;
+        if (fabs(lam_h[v - 1] - lam_h[v]) > tight) {
+          if (v - cs > 1) { starts.push_back(cs); lens.push_back(v - cs); }
+          cs = v;
+        }
+      }
+      shifts[v] = sh; prev = sh;
+    }
+    if (nvec - cs > 1) { starts.push_back(cs); lens.push_back(nvec - cs); }
+  }
+  DevBuf<double> sh_d, wk, Vp, Gp, T, W, W2;
+  DevBuf<uint8_t> piv;
+  DevBuf<int> cl;
+  const int batch = (int)std::min<int64_t>(nvec, std::max<int64_t>(256, (int64_t)(3ll << 30) / (5 * 8 * (int64_t)n)));   // <= 3 GiB of work arrays
+  if ((rc = sh_d.ensure(nvec)) || (rc = wk.ensure((size_t)5 * n * batch)) || (rc = piv.ensure((size_t)n * batch))) return rc;
+  EB_CUDA(cudaMemcpyAsync(sh_d.p, shifts.data(), sizeof(double) * nvec, cudaMemcpyHostToDevice, st));
+  const size_t nbsz = (size_t)n * batch;
+  for (int v0 = 0; v0 < nvec; v0 += batch) {
+    const int nb = std::min(batch, nvec - v0);
+    tri_invit_batch_kernel<<<(nb + 127) / 128, 128, 0, st>>>(n, v0, nb, d, e, sh_d.p, tn, wk.p, wk.p + nbsz, wk.p + 2 * nbsz, wk.p + 3 * nbsz,
+                                                             wk.p + 4 * nbsz, piv.p);
+    EB_CHECK_LAUNCH(c);
+    invit_transpose_kernel<<<dim3((nb + 31) / 32, (n + 31) / 32), 256, 0, st>>>(wk.p + 4 * nbsz, n, nb, v0, c->zvec_d.p, ldz);
+    EB_CHECK_LAUNCH(c);
+  }
+  EB_CUDA(cudaStreamSynchronize(st));      // shifts (host vector) consumed
+  if (!starts.empty()) {
+    const int ncl = (int)starts.size();
+    if ((rc = cl.ensure((size_t)2 * ncl))) return rc;
+    EB_CUDA(cudaMemcpyAsync(cl.p, starts.data(), sizeof(int) * ncl, cudaMemcpyHostToDevice, st));
+    EB_CUDA(cudaMemcpyAsync(cl.p + ncl, lens.data(), sizeof(int) * ncl, cudaMemcpyHostToDevice, st));
+    DevBuf<double> cw;
+    DevBuf<int> cp;
+    if ((rc = cw.ensure((size_t)ncl * 5 * n)) || (rc = cp.ensure((size_t)ncl * n))) return rc;
+    tri_invit_cluster_kernel<<<ncl, 1024, 0, st>>>(n, d, e, sh_d.p, tn, cl.p, cl.p + ncl, cw.p, cp.p, c->zvec_d.p, ldz);
+    EB_CHECK_LAUNCH(c);
+    EB_CUDA(cudaStreamSynchronize(st));
+  }
+  wk.release(); piv.release();
+  // back-transformation: z <- H_0 H_1 ... H_{n-3} z, reflectors grouped 64 at a time, last group first
+  const int nrefl = std::max(0, n - 2);
+  if (nrefl > 0) {
+    const int chunk = 512;
+    const int nchunk_max = (n + chunk - 1) / chunk + 1;
+    if ((rc = Vp.ensure((size_t)64 * ldz)) || (rc = Gp.ensure((size_t)(nchunk_max + 1) * 4096)) || (rc = T.ensure(4096)) ||
+        (rc = W.ensure((size_t)nvec * 64)) || (rc = W2.ensure((size_t)nvec * 64)))
+      return rc;
+    const int npanel = (nrefl + 63) / 64;
+    for (int pnl = npanel - 1; pnl >= 0; pnl--) {
+      const int j0 = pnl * 64, kp = std::min(64, nrefl - j0);
+      const int c0 = j0 & ~1;                                   // reflectors of this group are zero left of column j0 + 1
+      bt_extract_kernel<<<dim3((unsigned)((ldz + 255) / 256), 64), 256, 0, st>>>(A, lda, n, j0, kp, Vp.p, ldz);
+      EB_CHECK_LAUNCH(c);
+      const int nchunk = (n - c0 + chunk - 1) / chunk;
+      bt_gram_kernel<<<nchunk, 256, 0, st>>>(Vp.p, ldz, c0, n, chunk, Gp.p);
+      EB_CHECK_LAUNCH(c);
+      bt_tfactor_kernel<<<1, 256, 0, st>>>(Gp.p, nchunk, tau + j0, kp, Gp.p + (size_t)nchunk_max * 4096, T.p);
+      EB_CHECK_LAUNCH(c);
+      // W = Z V   (nvec x 64);  W2 = W T^T;  Z -= W2 V^T
+      if ((rc = launch_gemm(c, false, false, c->zvec_d.p + c0, ldz, Vp.p + c0, ldz, W.p, 64, nvec, 64, n - c0))) return rc;
+      bt_wt_kernel<<<std::min((nvec + 3) / 4, 4 * c->num_sms), 256, 0, st>>>(W.p, T.p, nvec, W2.p);
+      EB_CHECK_LAUNCH(c);
+      if ((rc = launch_gemm(c, false, true, W2.p, 64, Vp.p + c0, ldz, c->zvec_d.p + c0, ldz, nvec, n - c0, 64, -1.0, 1.0))) return rc;
+    }
+  }
+  normalize_rows_full_kernel<<<nvec, 256, 0, st>>>(c->zvec_d.p, ldz, n);
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
 __global__ void copy_matrix_kernel(const double* __restrict__ src, int64_t lds, double* __restrict__ dst, int64_t ldd, int n) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
   if (c < n) dst[(size_t)r * ldd + c] = src[(size_t)r * lds + c];
@@ -455,6 +808,7 @@ static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, do
   }
   if (nvec > 0) {
     if ((rc = c->zvec_d.ensure((size_t)nvec * n))) return rc;
+    c->zvec_ld = n;
     std::vector<double> th(nvec);
     EB_CUDA(cudaEventRecord(c->ev[8], st));
     if ((rc = chfsi_top(c, A_d, lda_in, n, nvec, th.data(), c->zvec_d.p, &c->tm.chfsi_iters, &c->tm.chfsi_matvecs))) return rc;
@@ -538,7 +892,17 @@ int eig_resident(eb_ctx* c, const double* A_d, int64_t lda_in, int n, double sca
   EB_CUDA(cudaEventRecord(c->ev[6], st));
   if ((rc = tridiag_spectrum(c, n, d, e, e2, bounds, scale))) return rc;
   EB_CUDA(cudaEventRecord(c->ev[7], st));
-  if (nvec > 0) {
+  int64_t ldz = n;
+  c->zvec_ld = n;
+  if (nvec > 64) {
+    std::vector<double> lam_h(n);
+    double bnd[4];
+    EB_CUDA(cudaMemcpyAsync(lam_h.data(), c->lambda_d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    EB_CUDA(cudaMemcpyAsync(bnd, bounds, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+    EB_CUDA(cudaStreamSynchronize(st));
+    if ((rc = full_basis(c, A, lda, n, nvec, d, e, tau, lam_h, bnd[2], &ldz))) return rc;
+    c->zvec_ld = ldz;
+  } else if (nvec > 0) {
     tri_invit_kernel<<<1, 1024, 0, st>>>(n, nvec, d, e, c->lambda_d.p, bounds, work, ipiv, c->zvec_d.p);
     EB_CHECK_LAUNCH(c);
     tri_backtransform_kernel<<<nvec, 1024, 0, st>>>(A, lda, n, tau, c->zvec_d.p);
@@ -546,7 +910,8 @@ int eig_resident(eb_ctx* c, const double* A_d, int64_t lda_in, int n, double sca
   }
   EB_CUDA(cudaEventRecord(c->ev[1], st));
   if (lambda_h) EB_CUDA(cudaMemcpyAsync(lambda_h, c->lambda_d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-  if (evecs_h && nvec > 0) EB_CUDA(cudaMemcpyAsync(evecs_h, c->zvec_d.p, sizeof(double) * (size_t)nvec * n, cudaMemcpyDeviceToHost, st));
+  if (evecs_h && nvec > 0)
+    EB_CUDA(cudaMemcpy2DAsync(evecs_h, sizeof(double) * n, c->zvec_d.p, sizeof(double) * ldz, sizeof(double) * n, nvec, cudaMemcpyDeviceToHost, st));
   EB_CUDA(cudaStreamSynchronize(st));
   cudaEventElapsedTime(&c->tm.tridiag_ms, c->ev[5], c->ev[6]);
   cudaEventElapsedTime(&c->tm.bisect_ms, c->ev[6], c->ev[7]);

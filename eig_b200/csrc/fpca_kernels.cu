@@ -802,8 +802,9 @@ int shrink_run(eb_ctx* c, int k, int newshrink, double* coords, double* lambda_o
   const int n = c->nrows, npad = c->npad, N = c->numindivs;
   if (k >= n) { set_error("eb_shrink_coords: numeigs must be smaller than the number of PCA rows"); return EB_ERR_ARG; }
   // ---- full eigenbasis of Xn = XTX / y (smartpca.c:4285-4290; the second trace normalisation is the identity up to rounding)
-  std::vector<double> lam(n), Eh((size_t)n * n);
-  if ((rc = eig_resident(c, c->xtx.p, c->npad, n, 1.0 / c->y, n, lam.data(), Eh.data()))) return rc;
+  // (all n vectors stay on the device in c->zvec_d, row pitch c->zvec_ld)
+  std::vector<double> lam(n);
+  if ((rc = eig_resident(c, c->xtx.p, c->npad, n, 1.0 / c->y, n, lam.data(), nullptr))) return rc;
   for (int j = 0; j < k; j++) lambda_out[j] = lam[j];
   const int npairs = k * (k + 1) / 2 + 1;
   const int nb_max = (int)std::min<int64_t>(mpad, 2048);
@@ -822,7 +823,7 @@ int shrink_run(eb_ctx* c, int k, int newshrink, double* coords, double* lambda_o
   // unit-length normalisation of printevecs, so the uploaded SNP count serves
   const double ncols = (double)m;
   EB_CUDA(cudaMemsetAsync(E.p, 0, sizeof(double) * (size_t)n * npad, c->stream));
-  EB_CUDA(cudaMemcpy2DAsync(E.p, sizeof(double) * npad, Eh.data(), sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice, c->stream));
+  EB_CUDA(cudaMemcpy2DAsync(E.p, sizeof(double) * npad, c->zvec_d.p, sizeof(double) * c->zvec_ld, sizeof(double) * n, n, cudaMemcpyDeviceToDevice, c->stream));
   EB_CUDA(cudaMemcpyAsync(lam_d.p, lam.data(), sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
   shr_scale_rows_kernel<<<n, 256, 0, c->stream>>>(c->xtx.p, c->npad, n, 1.0 / c->y, X.p, npad, x1.p, dg.p);
   EB_CHECK_LAUNCH(c);

@@ -111,3 +111,25 @@ def test_pca_full_outlier_loop(ctx):
     assert (np.abs(res["lambda_"] - lam) / np.maximum(np.abs(lam), 1e-6 * lam[0])).max() < 1e-9
     for i in range(2):
         assert abs(abs(res["evecs"][i] @ vec[i]) - 1) < 1e-9
+
+
+@pytest.mark.parametrize("n", [130, 700, 2300])
+def test_full_eigenbasis(ctx, n):
+    """all n eigenvectors (what eigvecs() promises, eigsubs.c:39-55, and shrinkmode consumes): batched inverse iteration,
+    Gram-Schmidt only inside numerically coincident groups, blocked back-transformation on the tensor cores.  The matrix has
+    a rank-deficient tail (a group of ~n/10 coincident zero eigenvalues) and population structure on top."""
+    rs = np.random.RandomState(n)
+    m = n - n // 10
+    X = rs.randn(n, m) + 0.5 * rs.randn(3, m)[rs.randint(0, 3, n)]
+    A = X @ X.T / m
+    ctx.set_option("eig_method", 1)
+    try:
+        lam, vec = ctx.eigvecs(A)
+    finally:
+        ctx.set_option("eig_method", 0)
+    w = np.linalg.eigvalsh(A)[::-1]
+    assert np.abs(lam - w).max() <= 1e-11 * w[0]
+    assert vec.shape == (n, n)
+    assert np.abs(vec @ vec.T - np.eye(n)).max() < 1e-9
+    R = vec @ A - lam[:, None] * vec
+    assert np.abs(R).max() <= 1e-11 * w[0]

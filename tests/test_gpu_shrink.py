@@ -28,7 +28,8 @@ def _case(nsnp, nind, missing, lo, hi, seed=3):
 
 
 @pytest.mark.parametrize("newshrink", [False, True])
-@pytest.mark.parametrize("nsnp,nind,missing,lo,hi,k", [(2500, 120, 0.15, 0, 0, 4), (3000, 170, 0.3, 6, 9, 6), (1200, 140, 0.0, 3, 0, 3)])
+@pytest.mark.parametrize("nsnp,nind,missing,lo,hi,k", [(2500, 120, 0.15, 0, 0, 4), (3000, 170, 0.3, 6, 9, 6), (1200, 140, 0.0, 3, 0, 3),
+                                                     (2000, 420, 0.1, 5, 5, 3)])
 def test_shrink_coords_vs_reference(ctx, nsnp, nind, missing, lo, hi, k, newshrink):
     P, xi = _case(nsnp, nind, missing, lo, hi)
     ctx.upload_packed(P, nind); ctx.set_rows(xi)
