@@ -639,7 +639,6 @@ int eb_shrink_coords(eb_ctx* c, int numeigs, int newshrink, double* coords, doub
   if ((rc = need_rows(c, "eb_shrink_coords"))) return rc;
   if (!c->grm_valid || c->y <= 0.0) { set_error("eb_shrink_coords: run eb_grm first (needs the resident GRM and the per-SNP normalisation)"); return EB_ERR_STATE; }
   if (!coords || !lambda_out) { set_error("eb_shrink_coords: null argument"); return EB_ERR_ARG; }
-  if (c->has_comm) { set_error("eb_shrink_coords: not available on a sharded context yet"); return EB_ERR_STATE; }
   return shrink_run(c, numeigs, newshrink, coords, lambda_out, ok);
 }
 

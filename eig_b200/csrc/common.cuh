@@ -173,6 +173,8 @@ int peer_allgather_host(eb_ctx* c, const void* src, void* dst, int64_t bytes);
 int peer_exchange(eb_ctx* c, int slot, void* local, size_t bytes, int aux);
 int peer_grm_finalize(eb_ctx* c);
 int peer_allreduce(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64_t count);
+int peer_allreduce_any(eb_ctx* c, double* buf, int64_t count);
+int peer_sum_host(eb_ctx* c, double* v, int count);
 void peer_release(eb_ctx* c);
 int peer_bury(eb_ctx* c);        // collective: barrier, then free superseded exported allocations
 

@@ -466,6 +466,7 @@ int project_run(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, dou
   fix_table_kernel<<<(unsigned)((mpad + 255) / 256), 256, 0, c->stream>>>(m, mpad, c->xmean_d.p, c->xfancy_d.p, c->used_d.p, ftab.p);
   EB_CHECK_LAUNCH(c);
   if ((rc = launch_packed_gemm<MODE_XTB>(c, ftab.p, FFt.p, mpad, FXt.p, npad, numeigs, 1.0))) return rc;
+  if ((rc = peer_allreduce_any(c, FXt.p, (int64_t)numeigs * npad))) return rc;      // SNP shards: sum of the per-shard projections
   col_sumsq_kernel<<<numeigs, 256, 0, c->stream>>>(FXt.p, npad, n, ss.p);
   EB_CHECK_LAUNCH(c);
   std::vector<double> s(numeigs);
@@ -570,6 +571,7 @@ int lsqproj_run(eb_ctx* c, const int* indiv, int nlist, const double* ffvecs, co
   // rr[j][q] = sum_s x_qs e_sj (also bcoeffs, smartpca.c:4743-4746);  co[(a,b)][q] = sum_s m_qs e_sa e_sb
   if ((rc = launch_packed_gemm<MODE_XTB>(c, ftab.p, Et.p, mpad, Rt.p, npad2, k, 1.0, &pv))) return rc;
   if ((rc = launch_packed_gemm<MODE_XTB>(c, mtab.p, Pt.p, mpad, Nt.p, npad2, npairs, 1.0, &pv))) return rc;
+  if ((rc = peer_allreduce_any(c, Rt.p, (int64_t)k * npad2)) || (rc = peer_allreduce_any(c, Nt.p, (int64_t)npairs * npad2))) return rc;
   lsq_solve_kernel<<<(nlist + 127) / 128, 128, 0, c->stream>>>(Nt.p, Rt.p, npad2, nlist, k, At.p, nv_d.p, ok_d.p);
   EB_CHECK_LAUNCH(c);
   if (acoeffs) EB_CUDA(cudaMemcpy2DAsync(acoeffs, sizeof(double) * nlist, At.p, sizeof(double) * npad2, sizeof(double) * nlist, k, cudaMemcpyDeviceToHost, c->stream));
@@ -686,14 +688,10 @@ __global__ void __launch_bounds__(256) shr_decode_kernel(const uint8_t* __restri
   D[(size_t)blockIdx.y * npad + t] = table[s * 4 + code];
 }
 
-// ff[j][s] /= sqrt(sum_s ff[j][s]^2 / ncols)   (smartpca.c:4309-4310)
-__global__ void __launch_bounds__(1024) shr_unit_rows_kernel(double* __restrict__ FF, int64_t ld, int64_t len, double ncols) {
-  __shared__ double sh[32];
-  double* r = FF + (size_t)blockIdx.x * ld;
-  double q = 0.0;
-  for (int64_t t = threadIdx.x; t < len; t += blockDim.x) q += r[t] * r[t];
-  const double inv = 1.0 / sqrt(bsum(q, sh) / ncols);
-  for (int64_t t = threadIdx.x; t < len; t += blockDim.x) r[t] *= inv;
+// ff[j][s] *= scale[j]   (the 1/sqrt(mean square) of smartpca.c:4309-4310, sums taken over all SNP shards on the host)
+__global__ void __launch_bounds__(256) shr_scale_rows2_kernel(double* __restrict__ FF, int64_t ld, int64_t len, const double* __restrict__ scale) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < len) FF[(size_t)blockIdx.y * ld + t] *= scale[blockIdx.y];
 }
 
 // Per (sample a, eigenvector i = blockIdx.y, SNP slice blockIdx.z): sums over the SNPs of this block of
@@ -821,7 +819,8 @@ int shrink_run(eb_ctx* c, int k, int newshrink, double* coords, double* lambda_o
     return rc;
   // the reference divides by ncols = |xsnplist|; the factor is common to every loading vector and cancels in the final
   // unit-length normalisation of printevecs, so the uploaded SNP count serves
-  const double ncols = (double)m;
+  double ncols = (double)m;
+  if ((rc = peer_sum_host(c, &ncols, 1))) return rc;
   EB_CUDA(cudaMemsetAsync(E.p, 0, sizeof(double) * (size_t)n * npad, c->stream));
   EB_CUDA(cudaMemcpy2DAsync(E.p, sizeof(double) * npad, c->zvec_d.p, sizeof(double) * c->zvec_ld, sizeof(double) * n, n, cudaMemcpyDeviceToDevice, c->stream));
   EB_CUDA(cudaMemcpyAsync(lam_d.p, lam.data(), sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
@@ -839,8 +838,22 @@ int shrink_run(eb_ctx* c, int k, int newshrink, double* coords, double* lambda_o
   // ---- base loadings ffvecs (smartpca.c:4309-4311) and the old-style projection of EVERY individual (4313-4318)
   EB_CUDA(cudaMemsetAsync(FF.p, 0, sizeof(double) * (size_t)k * mpad, c->stream));
   if ((rc = launch_packed_gemm<MODE_XA>(c, mtab.p, E.p, npad, FF.p, mpad, k, 1.0))) return rc;
-  shr_unit_rows_kernel<<<k, 1024, 0, c->stream>>>(FF.p, mpad, m, ncols);
-  EB_CHECK_LAUNCH(c);
+  {
+    // ff_j /= sqrt(sum_s ff_j[s]^2 / ncols) with the sum taken over every shard's SNPs
+    DevBuf<double> q_d;
+    std::vector<double> q(k);
+    if ((rc = q_d.ensure(k))) return rc;
+    col_sumsq_kernel<<<k, 256, 0, c->stream>>>(FF.p, mpad, m, q_d.p);
+    EB_CHECK_LAUNCH(c);
+    EB_CUDA(cudaMemcpyAsync(q.data(), q_d.p, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
+    EB_CUDA(cudaStreamSynchronize(c->stream));
+    if ((rc = peer_sum_host(c, q.data(), k))) return rc;
+    for (int j = 0; j < k; j++) q[j] = 1.0 / sqrt(q[j] / ncols);
+    EB_CUDA(cudaMemcpyAsync(q_d.p, q.data(), sizeof(double) * k, cudaMemcpyHostToDevice, c->stream));
+    shr_scale_rows2_kernel<<<dim3((unsigned)((mpad + 255) / 256), k), 256, 0, c->stream>>>(FF.p, mpad, m, q_d.p);
+    EB_CHECK_LAUNCH(c);
+    EB_CUDA(cudaStreamSynchronize(c->stream));
+  }
   std::vector<double> ffh((size_t)k * m), ones(k, 1.0), ss((size_t)k * N);
   std::vector<uint8_t> okall(N);
   std::vector<int> all(N);
@@ -854,6 +867,7 @@ int shrink_run(eb_ctx* c, int k, int newshrink, double* coords, double* lambda_o
     EB_CHECK_LAUNCH(c);
     if ((rc = launch_packed_gemm<MODE_XTB>(c, ftab.p, FF.p, mpad, Rt.p, npad, k, 1.0))) return rc;
     if ((rc = launch_packed_gemm<MODE_XTB>(c, vtab.p, Pt.p, mpad, Nt.p, npad, npairs, 1.0))) return rc;
+    if ((rc = peer_allreduce_any(c, Rt.p, (int64_t)k * npad)) || (rc = peer_allreduce_any(c, Nt.p, (int64_t)npairs * npad))) return rc;
   }
   // ---- leave-one-out eigenvectors, one m x m block per eigenvector
   for (int i = 0; i < k; i++) {
@@ -880,6 +894,7 @@ int shrink_run(eb_ctx* c, int k, int newshrink, double* coords, double* lambda_o
       shr_reduce_kernel<false><<<grid, 128, 0, c->stream>>>(Ft.p, nb, npad, n, k, c->work.p, c->wpitch, ftab.p, c->used_d.p, FF.p, mpad, s0, acc.p);
     EB_CHECK_LAUNCH(c);
   }
+  if ((rc = peer_allreduce_any(c, acc.p, (int64_t)nz * k * (k + 2) * npad))) return rc;      // per-sample sums over every shard's SNPs
   EB_CUDA(cudaMemsetAsync(okf.p, 1, npad, c->stream));
   if (newshrink) shr_solve_new_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(acc.p, nz, npad, n, k, ncols, ymul.p, snew.p, okf.p);
   else shr_solve_old_kernel<<<dim3((n + 127) / 128, k), 128, 0, c->stream>>>(acc.p, nz, npad, n, k, ncols, Nt.p, Rt.p, ymul.p, snew.p, okf.p);

@@ -228,6 +228,35 @@ int peer_allreduce(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64
   return 0;
 }
 
+// Sum over ranks of an arbitrary device buffer (any address, any owner): staged through the exported scratch allocation.
+// For the small per-individual / per-sample sums of the projection, lsqproj and shrinkmode passes.  Collective.
+int peer_allreduce_any(eb_ctx* c, double* buf, int64_t count) {
+  if (!c->has_comm) return 0;
+  const int64_t cnt2 = (count + 1) & ~1ll;
+  int rc;
+  if ((rc = c->peer_scratch.ensure((size_t)cnt2))) return rc;
+  if (cnt2 != count) EB_CUDA(cudaMemsetAsync(c->peer_scratch.p + count, 0, sizeof(double), c->stream));
+  EB_CUDA(cudaMemcpyAsync(c->peer_scratch.p, buf, sizeof(double) * count, cudaMemcpyDeviceToDevice, c->stream));
+  if ((rc = peer_allreduce(c, PEER_SLOT_T, c->peer_scratch.p, c->peer_scratch.n, cnt2))) return rc;
+  EB_CUDA(cudaMemcpyAsync(buf, c->peer_scratch.p, sizeof(double) * count, cudaMemcpyDeviceToDevice, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  return peer_bury(c);
+}
+
+// host-side sum over ranks of a few doubles (in place)
+int peer_sum_host(eb_ctx* c, double* v, int count) {
+  if (!c->has_comm) return 0;
+  std::vector<double> all((size_t)count * c->comm.world);
+  int rc;
+  if ((rc = peer_allgather_host(c, v, all.data(), sizeof(double) * count))) return rc;
+  for (int i = 0; i < count; i++) {
+    double s = 0.0;
+    for (int r = 0; r < c->comm.world; r++) s += all[(size_t)r * count + i];
+    v[i] = s;
+  }
+  return 0;
+}
+
 }  // namespace eb
 
 extern "C" int eb_set_comm(eb_ctx* c, const eb_comm* comm) {

@@ -80,6 +80,22 @@ def main():
     assert len(a["removed_index"]) >= 1, "test needs at least one outlier"
     assert np.abs(a["lambda_"] - b["lambda_"]).max() <= 1e-9 * a["lambda_"][0]
     assert np.array_equal(b["used"], a["used"][s0:s1])
+    # 3b. .evec coordinates (loadings, projections, lsqproj) and shrinkmode on SNP shards == single GPU
+    xi2 = np.arange(3, nind - 4, dtype=np.int32)
+    single.upload_packed(P, nind); single.set_rows(xi2); single.grm(want_snp=False)
+    ctx.upload_packed(P[s0:s1], nind); ctx.set_rows(xi2); ctx.grm(want_snp=False)
+    l0, v0_ = single.eig(4); l1, v1_ = ctx.eig(4)
+    assert np.array_equal(v0_, v1_) or np.abs(np.abs(np.einsum("ij,ij->i", v0_, v1_)) - 1).max() < 1e-12
+    c0, e0, k0 = single.evec_coords(v0_)
+    c1, e1, k1 = ctx.evec_coords(v0_)
+    assert np.array_equal(k0, k1) and np.abs(e0 - e1).max() <= 1e-10 * np.abs(e0).max()
+    assert np.abs(c0 - c1).max() <= 1e-10 * np.abs(c0).max(), np.abs(c0 - c1).max()
+    for new in (False, True):
+        a0, la0, ok0 = single.shrink_coords(3, newshrink=new)
+        a1, la1, ok1 = ctx.shrink_coords(3, newshrink=new)
+        assert ok0.all() and ok1.all() and np.abs(la0 - la1).max() <= 1e-12 * la0[0]
+        sg = np.sign((a0 * a1).sum(1))
+        assert np.abs(a0 - a1 * sg[:, None]).max() < 1e-8, (new, np.abs(a0 - a1 * sg[:, None]).max())
     # 4. sharded fastmode == single-GPU fastmode
     single.upload_packed(P, nind); single.set_rows(None)
     ctx.upload_packed(P[s0:s1], nind); ctx.set_rows(None)
