@@ -431,10 +431,10 @@ static eb_ctx* dropin_ctx() {
 }
 void eigvecs(double* mat, double* evals, double* evecs, int n) {
   eb_ctx* c = dropin_ctx();
-  // all n vectors for the sizes the remaining callers use (2 x 2 ellipses, smartpca.c:1751; mkorth); beyond that the
+  // all n vectors up to n = 8192 (1.3 s there; the remaining callers are 2 x 2 ellipses, smartpca.c:1751, and mkorth); beyond that the
   // leading block only -- what smartpca.c:4087,4298 consume -- and zeros for the rest
-  const int nvec = n <= 2048 ? n : 40;
-  if (n > 2048) memset(evecs, 0, sizeof(double) * (size_t)n * n);
+  const int nvec = n <= 8192 ? n : 40;
+  if (n > 8192) memset(evecs, 0, sizeof(double) * (size_t)n * n);
   if (eb_eigvecs(c, mat, evals, evecs, n, nvec) != 0) { fprintf(stderr, "eigvecs (libeigb200): %s\n", eb_last_error()); exit(1); }
 }
 void eigvals(double* mat, double* evals, int n) {

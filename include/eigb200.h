@@ -159,7 +159,7 @@ int eb_eigvecs (eb_ctx *, const double *mat, double *evals, double *evecs, int n
 
 /* drop-in symbols under the reference's own names (include/eigsubs.h:6-7): same contract as eigsubs.c:21,39 (mat
  * preserved, eigenvalues descending, row i of evecs = vector i, fatal on failure).  eigvecs fills all n vectors for
- * n <= 2048 and the leading 40 (zeros elsewhere) beyond -- every reference caller reads at most numeigs of them. */
+ * n <= 8192 and the leading 40 (zeros elsewhere) beyond -- every reference caller reads at most numeigs of them. */
 void eigvecs (double *mat, double *evals, double *evecs, int n);
 void eigvals (double *mat, double *evals, int n);
 
@@ -229,7 +229,7 @@ int eb_evec_coords (eb_ctx *, const double *evecs /* [numeigs][nrows] */ , int n
  * Needs the GRM of the last eb_grm resident.  coords [numeigs][numindivs] are the values printevecs writes in
  * shrinkmode (3849-3866: x10, unit length per eigenvector, one row per individual of the store); lambda_out[numeigs]
  * are the eigenvalues of the .evec header; ok[numindivs] (may be NULL) is 0 where a regression was singular.
- * The full eigenbasis comes from eb_eig's solver, so this entry is for PCA sizes it returns all vectors for. */
+ * Collective on a sharded context.  Cost: one full eigendecomposition + 2 numeigs nrows^2 nsnp tensor-core flops. */
 int eb_shrink_coords (eb_ctx *, int numeigs, int newshrink, double *coords, double *lambda_out, uint8_t * ok);
 /* testing aid: C[M][N] = op(A) op(B)^T on the FP64 tensor cores; a_km: A given as [K][M] else [M][K]; b_kn: B as [K][N]
  * else [N][K] (all dense row-major host arrays) */

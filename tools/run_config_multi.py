@@ -46,6 +46,17 @@ def main():
         dist.barrier()
     t = time.perf_counter() - t0
     tm = ctx.timings()
+    extra = {}
+    if "coords" in sys.argv[2:]:          # lsqproject: the .evec coordinate sequence smartpca.c:1440-1564 on the shards
+        t1 = time.perf_counter(); co, es, ok = ctx.evec_coords(res["evecs"]); torch.cuda.synchronize()
+        extra["evec_coords_s"] = time.perf_counter() - t1; extra["coords_ok"] = bool(ok.all())
+    if "shrink" in sys.argv[2:]:          # shrinkmode: doshrinkp on the shards
+        t1 = time.perf_counter(); sc, sl, sok = ctx.shrink_coords(10, newshrink=False); torch.cuda.synchronize()
+        extra["shrink_s"] = time.perf_counter() - t1; extra["shrink_ok"] = bool(sok.all())
+        extra["shrink_unit_err"] = float(np.abs((sc * sc).sum(1) - 1).max()); extra["shrink_lam"] = sl[:4].tolist()
+    if world > 1:
+        dist.barrier()
+    extra["total_s"] = time.perf_counter() - t0
     tt = torch.tensor([t, res["secs_grm"], res["secs_eig"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -55,7 +66,7 @@ def main():
                               passes=res["niter"], removed=len(res["removed_index"]), nused=int(res["nused"]),
                               snp_indiv2_per_s=float(N) * N * res["nused"] * res["niter"] / float(tt[1]),
                               grm_kernel_ms=tm["grm_ms"], finalize_reduce_ms=tm["finalize_ms"], tridiag_ms=tm["tridiag_ms"], bisect_ms=tm["bisect_ms"],
-                              vectors_ms=tm["vectors_ms"], lam_top=lam[:4].tolist(), lam_sum=float(lam.sum()), lam_min=float(lam.min()))), flush=True)
+                              vectors_ms=tm["vectors_ms"], lam_top=lam[:4].tolist(), lam_sum=float(lam.sum()), lam_min=float(lam.min()), **extra)), flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
