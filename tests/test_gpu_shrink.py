@@ -49,3 +49,18 @@ def test_shrink_coords_vs_reference(ctx, nsnp, nind, missing, lo, hi, k, newshri
     sg = np.sign((got * want).sum(1))              # eigenvector signs are LAPACK's choice
     assert np.abs(got * sg[:, None] - want).max() < 1e-6, np.abs(got * sg[:, None] - want).max()     # north_star: .evec entries 1e-6 absolute
     assert np.abs(np.sqrt((got * got).sum(1)) - 1).max() < 1e-12
+
+
+def test_shrink_coords_vs_committed_reference_vectors(ctx):
+    """against the unmodified reference's outputs committed in tests/golden/ref_shrink.npz"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_shrink.npz"))
+    nsnp, nind, k = int(g["nsnp"]), int(g["nind"]), int(g["k"])
+    P = synth.packed_genotypes(int(g["seed"]), nsnp, nind, missing=float(g["missing"]), npops=4, delta=0.35)
+    ctx.upload_packed(P, nind); ctx.set_rows(g["xindex"])
+    ctx.grm(want_snp=False)
+    for new, key in ((False, "shrink_old"), (True, "shrink_new")):
+        got, lam, ok = ctx.shrink_coords(k, newshrink=new)
+        want = g[key]
+        sg = np.sign((got * want).sum(1))
+        assert ok.all() and np.abs(got * sg[:, None] - want).max() < 1e-6

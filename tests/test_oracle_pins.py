@@ -189,3 +189,24 @@ def test_port_pop_counts_and_fst_against_reference():
     en, ed = ob.port_fstcol(ob.port_pop_counts(P, nind, xt, npops, xindex=xi))
     ren, red = ob.ref_fstcol(P, nind, xt, npops, xindex=xi)
     assert np.array_equal(en, ren) and np.array_equal(ed, red)
+
+
+def test_port_shrink_against_committed_reference_vectors():
+    """numpy restatement of doshrinkp / doshrinkp2 (oracle/bindings.py: port_shrink) against outputs of the unmodified
+    reference committed in tests/golden/ref_shrink.npz (tests/golden/make_golden_shrink.py), and against the compiled
+    reference itself when it is present."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_shrink.npz"))
+    nsnp, nind, k = int(g["nsnp"]), int(g["nind"]), int(g["k"])
+    P = synth.packed_genotypes(int(g["seed"]), nsnp, nind, missing=float(g["missing"]), npops=4, delta=0.35)
+    xi = g["xindex"]
+    o = ob.port_grm(P, nind, xindex=xi)
+    X = o["XTX"] / o["y"]
+    for new, key in ((False, "shrink_old"), (True, "shrink_new")):
+        got, lam = ob.port_shrink(P, nind, o["used"], o["xmean"], o["xfancy"], X, k, xindex=xi, newshrink=new)
+        want = g[key]
+        sg = np.sign((got * want).sum(1))
+        assert np.abs(got * sg[:, None] - want).max() < 1e-9
+        if ob.ref() is not None:
+            rw = ob.ref_shrink(P, nind, o["used"], o["xmean"], o["xfancy"], X, k, xindex=xi, newshrink=new)
+            sg = np.sign((rw * want).sum(1))
+            assert np.abs(rw * sg[:, None] - want).max() < 1e-9
