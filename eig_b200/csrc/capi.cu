@@ -1,5 +1,6 @@
 // capi.cu -- extern "C" entry points of libeigb200.so (declared in include/eigb200.h) and host orchestration.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <chrono>
@@ -259,17 +260,25 @@ static int grm_pass(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* n
   if ((rc = need_rows(c, "eb_grm"))) return rc;
   if (!opts) { set_error("eb_grm: opts is NULL"); return EB_ERR_ARG; }
   if (c->nrows < 2) { set_error("eb_grm: need at least 2 rows"); return EB_ERR_ARG; }
+  const bool dbg = getenv("EB_DEBUG") != nullptr;
+  const double t0 = now_s();
   if ((rc = stage_opts(c, opts))) return rc;
   EB_CUDA(cudaEventRecord(c->ev[0], c->stream));
   if ((rc = launch_stats(c, opts))) return rc;
   EB_CUDA(cudaEventRecord(c->ev[1], c->stream));
   if ((rc = grm_accumulate(c, !peer))) return rc;
+  // publish / map the peer buffers (first pass only does real work; see peer_grm_prepare)
+  if (peer && (rc = peer_grm_prepare(c))) return rc;
+  const double t1 = now_s();
   if ((rc = fetch_snp_outputs(c, c0, c1, nmiss, used, xmean, xfancy, nused_out))) return rc;
+  const double t2 = now_s();
   cudaEventElapsedTime(&c->tm.stats_ms, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->tm.grm_ms, c->ev[2], c->ev[3]);
   if (peer) {
     // exchange step: split-K plane sum + mirror fused with the cross-GPU reduction over peer memory (peer.cu)
     if ((rc = peer_grm_finalize(c))) return rc;
+    if (dbg) fprintf(stderr, "[grm_pass] launch + peer mapping %.3f s, kernels + per-SNP outputs %.3f s, peer finalize %.3f s\n",
+                     t1 - t0, t2 - t1, now_s() - t2);
     std::vector<long long> all(c->comm.world);
     long long mine = c->nused;
     if ((rc = peer_allgather_host(c, &mine, all.data(), sizeof(long long)))) return rc;

@@ -171,6 +171,7 @@ int lsqproj_run(eb_ctx* c, const int* indiv, int nlist, const double* ffvecs, co
 // peer.cu
 int peer_allgather_host(eb_ctx* c, const void* src, void* dst, int64_t bytes);
 int peer_exchange(eb_ctx* c, int slot, void* local, size_t bytes, int aux);
+int peer_grm_prepare(eb_ctx* c);
 int peer_grm_finalize(eb_ctx* c);
 int peer_allreduce(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64_t count);
 int peer_allreduce_any(eb_ctx* c, double* buf, int64_t count);

@@ -16,7 +16,9 @@
 //
 // Ordering: a host barrier separates "all inputs written" from the kernel, and the kernel's completion (stream sync on
 // every rank + barrier) from any consumer, so no device-side flags are needed and a hung peer cannot wedge the GPU.
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 #include <algorithm>
 #include "common.cuh"
@@ -151,14 +153,16 @@ __global__ void __launch_bounds__(256) grm_peer_finalize_kernel(const GrmPeerArg
 }
 
 // Reduce the per-rank split-K planes (left by grm_syrk_kernel in c->partial) across ranks into every rank's c->xtx.
-int peer_grm_finalize(eb_ctx* c) {
+// peer_grm_prepare: publish / map the buffers (host collectives + cudaIpcOpenMemHandle, ~0.1-0.2 s per 20 GB peer buffer the
+//   first time; later passes reuse the mappings).  It is called right after the SYRK kernel has been launched, but measured
+//   on 8 x B200 the open waits for the running kernel (3.1 s for 14 x 20 GB after a 5.1 s kernel), so nothing overlaps yet:
+//   a pull-only exchange that needs the partial planes alone would halve it (round-2 item).
+// peer_grm_finalize: barrier, reduce kernel, barrier.
+int peer_grm_prepare(eb_ctx* c) {
   const int W = c->comm.world;
   int rc;
   if ((rc = peer_exchange(c, PEER_SLOT_PARTIAL, c->partial.p, c->partial.n * sizeof(double), c->nsplit))) return rc;
   if ((rc = peer_exchange(c, PEER_SLOT_XTX, c->xtx.p, c->xtx.n * sizeof(double), c->npad))) return rc;
-  GrmPeerArgs a;
-  memset(&a, 0, sizeof(a));
-  a.world = W; a.rank = c->comm.rank;
   const size_t plane = (size_t)c->npad * c->npad;
   for (int r = 0; r < W; r++) {
     const PeerRecord& pr = c->peer[PEER_SLOT_PARTIAL].rec[r];
@@ -167,12 +171,28 @@ int peer_grm_finalize(eb_ctx* c) {
       set_error("multi-GPU GRM: rank %d has a different matrix size (npad %d vs %d): every shard must use the same rows", r, xr.aux, c->npad);
       return EB_ERR_STATE;
     }
+  }
+  return 0;
+}
+
+int peer_grm_finalize(eb_ctx* c) {
+  const int W = c->comm.world;
+  int rc;
+  GrmPeerArgs a;
+  memset(&a, 0, sizeof(a));
+  a.world = W; a.rank = c->comm.rank;
+  for (int r = 0; r < W; r++) {
     a.part[r] = (const double*)c->peer[PEER_SLOT_PARTIAL].mapped[r];
     a.xtx[r] = (double*)c->peer[PEER_SLOT_XTX].mapped[r];
-    a.nsplit[r] = pr.aux;
+    a.nsplit[r] = c->peer[PEER_SLOT_PARTIAL].rec[r].aux;
+    if (!a.part[r] || !a.xtx[r]) { set_error("peer_grm_finalize: buffers of rank %d are not mapped (peer_grm_prepare not called)", r); return EB_ERR_STATE; }
   }
+  const bool dbg = getenv("EB_DEBUG") != nullptr;
+  const auto tnow = [] { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+  const double tq0 = tnow();
   EB_CUDA(cudaStreamSynchronize(c->stream));     // my planes are complete ...
   if ((rc = comm_barrier(c))) return rc;         // ... and so are everybody else's
+  const double tq1 = tnow();
   const int T32 = c->npad / 32, nblocks = T32 * (T32 + 1) / 2;
   const int mine = (nblocks - a.rank + W - 1) / W;
   EB_CUDA(cudaEventRecord(c->ev[3], c->stream));
@@ -182,6 +202,7 @@ int peer_grm_finalize(eb_ctx* c) {
   }
   EB_CUDA(cudaEventRecord(c->ev[4], c->stream));
   EB_CUDA(cudaStreamSynchronize(c->stream));     // my stores have landed in every peer ...
+  if (dbg) fprintf(stderr, "[peer_grm_finalize] rank %d: wait for all ranks %.3f s, reduce kernel %.3f s\n", a.rank, tq1 - tq0, tnow() - tq1);
   return peer_bury(c);                            // ... and (barrier) everybody's have landed here
 }
 
