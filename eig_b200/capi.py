@@ -56,7 +56,7 @@ EXPORTS = [
     "eb_eig", "eb_eigvecs", "eb_ridoutlier", "eb_pca_full", "eb_fpca", "eb_gauss_matrix", "eb_project", "eb_get_timings",
     "eb_microbench_fp64", "eb_set_option", "eb_debug_tridiag", "eb_lsqproj", "eb_evec_coords", "eb_pop_counts", "eb_hash_ids", "eb_packed_file_header", "eb_upload_packed_file",
     "eb_download_packed", "eb_write_eval", "eb_write_evec", "eb_write_grm", "eb_grm_dense_begin", "eb_grm_dense_add", "eb_grm_dense_end", "eigvecs", "eigvals",
-    "eb_set_comm", "eb_peer_allreduce_test", "eb_snp_used_count", "eb_shrink_coords", "eb_debug_gemm",
+    "eb_set_comm", "eb_peer_allreduce_test", "eb_snp_used_count", "eb_shrink_coords", "eb_debug_gemm", "eb_local_comm_create", "eb_local_comm_get", "eb_local_comm_destroy",
 ]
 
 _lib = None
@@ -135,6 +135,28 @@ def write_grm(path, xtx, numsnps):
     _chk(lib().eb_write_grm(path.encode(), _p(xtx), C.c_int(xtx.shape[0]), C.c_int(numsnps)))
 
 
+class LocalComm:
+    """eb_local_comm: in-process communicator for `world` host threads with one Context each (include/eigb200.h)."""
+
+    def __init__(self, world):
+        lib().eb_local_comm_create.restype = C.c_void_p
+        self.h = lib().eb_local_comm_create(C.c_int(world))
+        if not self.h:
+            raise EigB200Error("libeigb200: %s" % lib().eb_last_error().decode())
+        self.h = C.c_void_p(self.h); self.world = world
+
+    def rank_comm(self, rank):
+        st = Comm()
+        lib().eb_local_comm_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _chk(lib().eb_local_comm_get(self.h, C.c_int(rank), C.byref(st)))
+        return st
+
+    def close(self):
+        if self.h:
+            lib().eb_local_comm_destroy.argtypes = [C.c_void_p]
+            lib().eb_local_comm_destroy(self.h); self.h = None
+
+
 class Context:
     """One eb_ctx = one GPU."""
 
@@ -181,6 +203,11 @@ class Context:
         st = Comm(comm.rank, comm.world, ALLGATHER_CB(_ag), BARRIER_CB(_bar), None)
         self._comm = (st, comm)          # keep the callbacks alive as long as the context uses them
         _chk(lib().eb_set_comm(self.h, C.byref(st)))
+
+    def set_comm_struct(self, comm_struct, keep=None):
+        """comm_struct: a filled capi.Comm (e.g. from LocalComm.rank_comm) whose callbacks are C functions"""
+        self._comm = (comm_struct, keep)
+        _chk(lib().eb_set_comm(self.h, C.byref(comm_struct)))
 
     def peer_allreduce_test(self, vec):
         v = np.ascontiguousarray(vec, np.float64).copy()

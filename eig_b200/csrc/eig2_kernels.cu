@@ -1017,7 +1017,7 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
   double th[64], res2[64];
   const bool debug = getenv("EB_DEBUG") != nullptr;
   const double tol = std::max(2e-14, 6e-16 * sqrt((double)n));
-  double prev_worst = 1e300, prev2_worst = 1e300;
+  double prev_worst = 1e300, prev2_worst = 1e300, last_worst = 1e300;
   double lo = 0.0;
   int outer = 0;
   bool converged = false;
@@ -1053,6 +1053,7 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
     if (debug) fprintf(stderr, "[chfsi] outer %d matvecs %d theta0 %.6e theta_k %.6e cut %.6e worst_res/anorm %.3e\n", outer, nmat, th[0],
                        th[std::max(nvec - 1, 0)], th[63], worst / anorm);
     // converged: residual at the rounding floor of an n-term FP64 mat-vec, or stagnating just above it
+    last_worst = anorm > 0.0 ? worst / anorm : 0.0;
     if (!(anorm > 0.0) || nlock >= nvec || worst <= tol * anorm) { converged = true; break; }
     if (worst <= 1e-11 * anorm && worst > 0.5 * prev_worst && prev_worst > 0.5 * prev2_worst) { converged = true; break; }
     prev2_worst = prev_worst; prev_worst = worst;
@@ -1105,7 +1106,11 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
   EB_CUDA(cudaMemcpyAsync(&herr, err_d, sizeof(int), cudaMemcpyDeviceToHost, st));
   EB_CUDA(cudaStreamSynchronize(st));
   if (herr) { set_error("chfsi_top: Cholesky breakdown in the block orthonormalisation"); return EB_ERR_NUMERIC; }
-  if (!converged) { set_error("chfsi_top: no convergence after %d outer iterations", maxouter); return EB_ERR_NUMERIC; }
+  if (!converged) {
+    // not at the rounding floor after maxouter filters: still usable if the residuals are far below what any consumer
+    // resolves (the .evec prints 4-6 decimals, ridoutlier compares z-scores with 6.0); otherwise let the caller fall back
+    if (!(last_worst <= 1e-9)) { set_error("chfsi_top: no convergence after %d outer iterations (worst residual / |A| = %.2e)", maxouter, last_worst); return EB_ERR_NUMERIC; }
+  }
   normalize_rows_kernel<<<nvec, 256, 0, st>>>(V, ld, n);
   EB_CHECK_LAUNCH(c);
   EB_CUDA(cudaMemcpy2DAsync(vec_d, sizeof(double) * n, V, sizeof(double) * ld, sizeof(double) * n, nvec, cudaMemcpyDeviceToDevice, st));

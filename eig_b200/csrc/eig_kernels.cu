@@ -811,7 +811,16 @@ static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, do
     c->zvec_ld = n;
     std::vector<double> th(nvec);
     EB_CUDA(cudaEventRecord(c->ev[8], st));
-    if ((rc = chfsi_top(c, A_d, lda_in, n, nvec, th.data(), c->zvec_d.p, &c->tm.chfsi_iters, &c->tm.chfsi_matvecs))) return rc;
+    if ((rc = chfsi_top(c, A_d, lda_in, n, nvec, th.data(), c->zvec_d.p, &c->tm.chfsi_iters, &c->tm.chfsi_matvecs))) {
+      if (rc != EB_ERR_NUMERIC) return rc;
+      // the subspace iteration gave up: take the vectors from the one-stage path (slower, direct)
+      const int keep = c->opt_eig_method;
+      c->opt_eig_method = 1;
+      rc = eig_resident(c, A_d, lda_in, n, scale, nvec, nullptr, evecs_h);
+      c->opt_eig_method = keep;
+      c->tm.eig_method = 2;
+      return rc;
+    }
     EB_CUDA(cudaEventRecord(c->ev[9], st));
     if (evecs_h) EB_CUDA(cudaMemcpyAsync(evecs_h, c->zvec_d.p, sizeof(double) * (size_t)nvec * n, cudaMemcpyDeviceToHost, st));
     EB_CUDA(cudaStreamSynchronize(st));

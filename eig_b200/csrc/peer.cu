@@ -301,6 +301,54 @@ extern "C" int eb_set_comm(eb_ctx* c, const eb_comm* comm) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ in-process communicator
+// `world` host threads of ONE process, one context (GPU) each: what a C caller such as smartpca.c needs to use every GPU of
+// the box without MPI or torch.  The callbacks are plain C functions over a pthread barrier and a shared staging buffer;
+// peer_exchange sees equal pids and uses the peers' device pointers directly (cudaDeviceEnablePeerAccess), no IPC handles.
+#include <pthread.h>
+struct eb_local_comm {
+  int world;
+  pthread_barrier_t bar;
+  std::vector<unsigned char> stage;
+  struct Rank { eb_local_comm* lc; int rank; };
+  std::vector<Rank> ranks;
+};
+static int local_barrier(void* user) {
+  auto* r = (eb_local_comm::Rank*)user;
+  const int rc = pthread_barrier_wait(&r->lc->bar);
+  return (rc == 0 || rc == PTHREAD_BARRIER_SERIAL_THREAD) ? 0 : 1;
+}
+static int local_allgather(void* user, const void* src, void* dst, int64_t bytes) {
+  auto* r = (eb_local_comm::Rank*)user;
+  eb_local_comm* lc = r->lc;
+  if (local_barrier(user)) return 1;                                   // the previous collective has been read by everyone
+  if (r->rank == 0 && lc->stage.size() < (size_t)bytes * lc->world) lc->stage.resize((size_t)bytes * lc->world);
+  if (local_barrier(user)) return 1;
+  memcpy(lc->stage.data() + (size_t)r->rank * bytes, src, (size_t)bytes);
+  if (local_barrier(user)) return 1;
+  memcpy(dst, lc->stage.data(), (size_t)bytes * lc->world);
+  return local_barrier(user);
+}
+extern "C" eb_local_comm* eb_local_comm_create(int world) {
+  if (world < 1 || world > eb::EB_MAX_WORLD) { eb::set_error("eb_local_comm_create: world must be in 1..%d", eb::EB_MAX_WORLD); return nullptr; }
+  eb_local_comm* lc = new eb_local_comm();
+  lc->world = world;
+  if (pthread_barrier_init(&lc->bar, nullptr, (unsigned)world) != 0) { delete lc; eb::set_error("eb_local_comm_create: pthread_barrier_init failed"); return nullptr; }
+  lc->ranks.resize(world);
+  for (int r = 0; r < world; r++) lc->ranks[r] = {lc, r};
+  return lc;
+}
+extern "C" int eb_local_comm_get(eb_local_comm* lc, int rank, eb_comm* out) {
+  if (!lc || !out || rank < 0 || rank >= lc->world) { eb::set_error("eb_local_comm_get: bad argument"); return EB_ERR_ARG; }
+  out->rank = rank; out->world = lc->world; out->allgather_host = local_allgather; out->barrier = local_barrier; out->user = &lc->ranks[rank];
+  return 0;
+}
+extern "C" void eb_local_comm_destroy(eb_local_comm* lc) {
+  if (!lc) return;
+  pthread_barrier_destroy(&lc->bar);
+  delete lc;
+}
+
 extern "C" int eb_peer_allreduce_test(eb_ctx* c, double* host_io, int64_t count) {
   // testing aid: all-reduce a host vector through the peer kernel (upload, exchange, download)
   if (!c || !c->has_comm) { eb::set_error("eb_peer_allreduce_test: no communicator set"); return EB_ERR_STATE; }

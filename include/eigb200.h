@@ -144,6 +144,14 @@ typedef struct {
   void *user;
 } eb_comm;
 int eb_set_comm (eb_ctx *, const eb_comm * comm /* NULL or world <= 1: single GPU */ );
+/* In-process communicator: `world` host threads of one process, one context (GPU) each -- what a C caller such as
+ * smartpca.c needs to drive every GPU of the box without MPI or torch.  eb_local_comm_get fills the eb_comm of one rank
+ * (plain C callbacks over a pthread barrier); each thread passes its own to eb_set_comm and then makes the collective calls.
+ * The handle must outlive the contexts that use it. */
+typedef struct eb_local_comm eb_local_comm;
+eb_local_comm *eb_local_comm_create (int world);
+int eb_local_comm_get (eb_local_comm *, int rank, eb_comm * out);
+void eb_local_comm_destroy (eb_local_comm *);
 /* testing aid: in-place sum over ranks of a host vector through the peer all-reduce kernel (count even) */
 int eb_peer_allreduce_test (eb_ctx *, double *host_io, int64_t count);
 /* SNPs of THIS context's shard that entered XTX in the last GRM pass (eb_grm's nused_out is the total over shards) */

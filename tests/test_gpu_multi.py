@@ -45,3 +45,52 @@ def test_three_ranks_shared_gpu_gloo():
         _run(3)
     else:
         _run(3, backend="gloo")
+
+
+def test_in_process_communicator_threads():
+    """eb_local_comm: two host threads of THIS process, one context each (both on cuda:0 when the box has one GPU, else one
+    GPU each) -- the C-caller route to several GPUs; same-process ranks use each other's device pointers directly."""
+    import threading
+    import numpy as np
+    import torch
+    from eig_b200 import capi, parallel, synth
+    world = 2
+    ngpu = torch.cuda.device_count()
+    nsnp, nind = 2500, 300
+    P = synth.packed_genotypes(13, nsnp, nind, missing=0.1, npops=3, delta=0.25)
+    single = capi.Context(0)
+    single.upload_packed(P, nind); single.set_rows(None)
+    ref = single.grm(want_xtx=True)
+    ev0, vec0 = single.fpca(3, 6, 2, seed=9)
+    lc = capi.LocalComm(world)
+    out = [None] * world; err = [None] * world
+
+    def work(rank):
+        try:
+            ctx = capi.Context(rank if ngpu >= world else 0)
+            ctx.set_comm_struct(lc.rank_comm(rank), keep=lc)
+            s0, s1 = parallel.shard_snps(nsnp, rank, world)
+            ctx.upload_packed(P[s0:s1], nind); ctx.set_rows(None)
+            r = ctx.grm(want_xtx=True)
+            ev, vec = ctx.fpca(3, 6, 2, seed=9)
+            res = ctx.pca_full(numeigs=3, numoutliter=2)
+            out[rank] = (r, ev, vec, res, (s0, s1))
+            ctx.set_comm(None); ctx.close()
+        except Exception as ex:  # noqa: BLE001
+            err[rank] = ex
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=300)
+    assert all(not t.is_alive() for t in th), "a rank is stuck in a collective"
+    assert err == [None] * world, err
+    for rank in range(world):
+        r, ev, vec, res, (s0, s1) = out[rank]
+        assert np.abs(r["XTX"] - ref["XTX"]).max() <= 1e-12 * np.abs(ref["XTX"]).max() and r["nused"] == ref["nused"]
+        assert np.array_equal(r["used"], ref["used"][s0:s1])
+        assert np.abs(ev - ev0).max() <= 1e-9 * ev0[0]
+    assert np.array_equal(out[0][0]["XTX"], out[1][0]["XTX"]), "reduced GRM must be bit-identical on both ranks"
+    assert np.array_equal(out[0][3]["lambda_"], out[1][3]["lambda_"])
+    lc.close(); single.close()
