@@ -27,6 +27,16 @@ __device__ __forceinline__ void dmma884f(double& c0, double& c1, double a, doubl
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void pg_cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void pg_cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void pg_cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
 // XTB: work tile [PG_KT snps][64 bytes = 256 individuals], table tile [PG_KT][4]
 // XA : work tile [256 snps][16 bytes = 64 individuals] (row stride 20 B to spread banks), table [256][4] fixed per CTA
 template <int MODE, int NBLK>
@@ -60,42 +70,52 @@ packed_gemm_kernel(const uint8_t* __restrict__ work, int64_t wpitch, const doubl
     }
   }
 
+  // Stage loads are asynchronous copies (cp.async -> SASS LDGSTS): the global-memory latency of stage kb+1 is hidden behind
+  // the DMMAs of stage kb instead of being paid by every thread before it may start computing (the first version staged
+  // through registers: DMMA pipe 69 % / 83 % active for X^T B / X A; see profiles/r1_kernels_ncu.md).
   auto load_stage = [&](int st, int kb) {
     const int64_t k0 = (int64_t)kb * PG_KT;
-    // dense tile: NC rows x PG_KT doubles
+    // dense tile: NC rows x PG_KT doubles (rows beyond ncols are zero-filled by a zero-length source)
     for (int idx = threadIdx.x; idx < NC * (PG_KT / 2); idx += 256) {
       const int l = idx / (PG_KT / 2), kk = (idx % (PG_KT / 2)) * 2;
-      double2 v = make_double2(0.0, 0.0);
-      if (l0 + l < ncols) v = *reinterpret_cast<const double2*>(In_t + (size_t)(l0 + l) * ld_in + k0 + kk);
-      *reinterpret_cast<double2*>(&In_s[st][l][kk]) = v;
+      const bool ok = l0 + l < ncols;
+      const double* src = ok ? In_t + (size_t)(l0 + l) * ld_in + k0 + kk : In_t;
+      pg_cp_async16(&In_s[st][l][kk], src, ok ? 16 : 0);
     }
     if (MODE == MODE_XTB) {
-      // packed: PG_KT snp rows x 64 bytes (256 individuals starting at r0)
+      // packed: PG_KT snp rows x 64 bytes (256 individuals starting at r0); beyond the row pitch: all-missing codes
       for (int idx = threadIdx.x; idx < PG_KT * 4; idx += 256) {
         const int kk = idx >> 2, part = idx & 3;
-        uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
         const int64_t byte0 = r0 / 4 + part * 16;
-        if (byte0 + 16 <= wpitch) v = *reinterpret_cast<const uint4*>(work + (k0 + kk) * wpitch + byte0);
-        *reinterpret_cast<uint4*>(&W_s[st][kk * 64 + part * 16]) = v;
+        if (byte0 + 16 <= wpitch) pg_cp_async16(&W_s[st][kk * 64 + part * 16], work + (k0 + kk) * wpitch + byte0, 16);
+        else *reinterpret_cast<uint4*>(&W_s[st][kk * 64 + part * 16]) = make_uint4(~0u, ~0u, ~0u, ~0u);
       }
-      for (int idx = threadIdx.x; idx < PG_KT * 4; idx += 256) T_s[st * PG_KT * 4 + idx] = table[k0 * 4 + idx];
+      for (int idx = threadIdx.x; idx < PG_KT * 4; idx += 256) pg_cp_async8(&T_s[st * PG_KT * 4 + idx], table + k0 * 4 + idx);
     } else {
-      // packed: 256 snp rows x 16 bytes (64 individuals starting at k0)
+      // packed: 256 snp rows x 16 bytes (64 individuals starting at k0); rows are 20 bytes apart in shared memory
       for (int idx = threadIdx.x; idx < PG_ROWS; idx += 256) {
         const int64_t s = r0 + idx;
-        uint4 v = make_uint4(~0u, ~0u, ~0u, ~0u);
-        if (s < mpad) v = *reinterpret_cast<const uint4*>(work + s * wpitch + k0 / 4);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&W_s[st][idx * XA_STRIDE]);
-        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        uint8_t* dst = &W_s[st][idx * XA_STRIDE];
+        if (s < mpad) {
+          const uint8_t* src = work + s * wpitch + k0 / 4;
+#pragma unroll
+          for (int j = 0; j < 4; j++) pg_cp_async4(dst + 4 * j, src + 4 * j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; j++) reinterpret_cast<uint32_t*>(dst)[j] = ~0u;
+        }
       }
     }
   };
 
   load_stage(0, 0);
-  __syncthreads();
+  asm volatile("cp.async.commit_group;" ::: "memory");
   for (int kb = 0; kb < nk; kb++) {
     const int st = kb & 1;
     if (kb + 1 < nk) load_stage(st ^ 1, kb + 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");      // everything but the newest group (stage kb + 1) has landed
+    __syncthreads();
 #pragma unroll 2
     for (int kk = 0; kk < PG_KT; kk += 4) {
       double a[4], b[NBLK];
