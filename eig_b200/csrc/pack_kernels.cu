@@ -24,10 +24,21 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restr
     int j = w * 16 + t;
     src[t] = j < nrows ? xindex[j] : -1;
   }
+  // 16 consecutive individuals starting on a byte boundary: the word is 4 consecutive bytes of the raw row (same MSB-first layout) -- the common case (all individuals,
+  // or long runs between a few removed outliers)
+  bool run = src[0] >= 0 && (src[0] & 3) == 0;
+#pragma unroll
+  for (int t = 1; t < 16; t++) run = run && src[t] == src[0] + t;
+  const int b0 = src[0] >> 2;
   for (int64_t s = blockIdx.y; s < mpad; s += gridDim.y) {
     uint32_t out = 0xFFFFFFFFu;
     if (s < nsnp) {
       const uint8_t* row = raw + s * raw_pitch;
+      if (run) {
+        out = (uint32_t)row[b0] | ((uint32_t)row[b0 + 1] << 8) | ((uint32_t)row[b0 + 2] << 16) | ((uint32_t)row[b0 + 3] << 24);
+        reinterpret_cast<uint32_t*>(work + s * wpitch)[w] = out;
+        continue;
+      }
       out = 0;
 #pragma unroll
       for (int t = 0; t < 16; t++) {
