@@ -4,13 +4,14 @@
 // threads elsewhere) supplies only host-side plumbing through eb_comm: an all-gather of small host records and a
 // barrier.  Device buffers are exported with CUDA IPC (or used directly when two ranks live in one process), after
 // which every exchange is one kernel that reads the peers' buffers with plain loads and writes its reduced slice into
-// every peer with plain stores:
+// every peer with plain stores (all-reduce) or lets the peers pull it (GRM):
 //
-//   grm_peer_finalize_kernel : the split-K plane sum + symit2 mirror of grm_finalize_kernel FUSED with the cross-GPU
-//       reduction of the partial GRMs.  Lower-triangle 32x32 blocks are dealt round-robin to the ranks; the owner sums
-//       rank 0's planes, then rank 1's, ... (fixed order => the result is bit-identical on every rank and from run to
-//       run) and stores the block and its mirror image into every rank's full symmetric XTX.  Only the lower triangle
-//       crosses NVLink on the way in (half of what an all-reduce of the square would move).
+//   grm_peer_reduce_kernel / grm_peer_gather_kernel : the split-K plane sum + symit2 mirror of grm_finalize_kernel FUSED
+//       with the cross-GPU reduction of the partial GRMs.  Lower-triangle 32x32 blocks are dealt round-robin to the
+//       ranks; the owner sums rank 0's planes, then rank 1's, ... (fixed order => the result is bit-identical on every
+//       rank and from run to run) into its own XTX and its own plane 0; after a barrier every rank pulls the other
+//       owners' blocks and mirrors them locally.  Only the lower triangle ever crosses NVLink (2 x 7/8 of it per rank,
+//       a quarter of what an all-reduce of the square moves) and only the plane buffers are mapped between processes.
 //   peer_allreduce_kernel    : in-place one-shot all-reduce of an FP64 buffer (fastmode's N x L sketch and N x (I+1)L
 //       projection, kjg_fpca.c:123,79): rank r owns a contiguous slice, pulls it from every rank, pushes the sum back.
 //
@@ -115,13 +116,14 @@ __device__ __forceinline__ void tri_decode32(int t, int& ti, int& tj) {
 
 struct GrmPeerArgs {
   const double* part[EB_MAX_WORLD];
-  double* xtx[EB_MAX_WORLD];
   int nsplit[EB_MAX_WORLD];
   int world, rank;
 };
 
-// CTA b of rank r finalises lower-triangle 32x32 block r + b*world.
-__global__ void __launch_bounds__(256) grm_peer_finalize_kernel(const GrmPeerArgs a, int npad, int nblocks) {
+// Phase 1 (reduce): CTA b of rank r finalises lower-triangle 32x32 block r + b*world: sum of every rank's planes in a fixed
+// order, stored (with its mirror image) into the LOCAL xtx and, for the peers to pull, into the local plane 0 in place.
+__global__ void __launch_bounds__(256) grm_peer_reduce_kernel(const GrmPeerArgs a, int npad, int nblocks, double* __restrict__ own_plane0,
+                                                              double* __restrict__ xtx) {
   __shared__ double tile[32][33];
   const int gb = a.rank + blockIdx.x * a.world;
   if (gb >= nblocks) return;
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(256) grm_peer_finalize_kernel(const GrmPeerArg
       const double* p = a.part[w] + idx;
       for (int s = 0; s < a.nsplit[w]; s++) v += p[s * plane];
     }
+    own_plane0[idx] = v;                                     // complete block (the pad / upper part of diagonal blocks included)
     if (bi == bj && tx > r) v = 0.0;
     tile[r][tx] = v;
   }
@@ -142,33 +145,53 @@ __global__ void __launch_bounds__(256) grm_peer_finalize_kernel(const GrmPeerArg
   for (int r = ty; r < 32; r += 8) {
     double v = tile[r][tx];
     if (bi == bj && tx > r) v = tile[tx][r];
-    const double vt = tile[tx][r];
-    const size_t i0 = (size_t)(bi * 32 + r) * npad + bj * 32 + tx, i1 = (size_t)(bj * 32 + r) * npad + bi * 32 + tx;
-    for (int w = 0; w < a.world; w++) {
-      double* x = a.xtx[(w + a.rank) % a.world];            // start with the local copy, spread the peers
-      x[i0] = v;
-      if (bi != bj) x[i1] = vt;
-    }
+    xtx[(size_t)(bi * 32 + r) * npad + bj * 32 + tx] = v;
+    if (bi != bj) xtx[(size_t)(bj * 32 + r) * npad + bi * 32 + tx] = tile[tx][r];
+  }
+}
+
+// Phase 2 (gather): every block owned by another rank is pulled from that rank's plane 0 into the local xtx (+ mirror).
+// CTA b handles the b-th block that is NOT owned by this rank.
+__global__ void __launch_bounds__(256) grm_peer_gather_kernel(const GrmPeerArgs a, int npad, int nblocks, double* __restrict__ xtx) {
+  __shared__ double tile[32][33];
+  // b-th non-owned block: blocks are owned round-robin, so within each group of `world` consecutive blocks exactly one is ours
+  const int grp = blockIdx.x / (a.world - 1), k = blockIdx.x % (a.world - 1);
+  const int gb = grp * a.world + (k < a.rank ? k : k + 1);
+  if (gb >= nblocks) return;
+  const int owner = gb % a.world;
+  int bi, bj; tri_decode32(gb, bi, bj);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const double* src = a.part[owner];
+  for (int r = ty; r < 32; r += 8) {
+    double v = src[(size_t)(bi * 32 + r) * npad + bj * 32 + tx];
+    if (bi == bj && tx > r) v = 0.0;
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    double v = tile[r][tx];
+    if (bi == bj && tx > r) v = tile[tx][r];
+    xtx[(size_t)(bi * 32 + r) * npad + bj * 32 + tx] = v;
+    if (bi != bj) xtx[(size_t)(bj * 32 + r) * npad + bi * 32 + tx] = tile[tx][r];
   }
 }
 
 // Reduce the per-rank split-K planes (left by grm_syrk_kernel in c->partial) across ranks into every rank's c->xtx.
-// peer_grm_prepare: publish / map the buffers (host collectives + cudaIpcOpenMemHandle, ~0.1-0.2 s per 20 GB peer buffer the
-//   first time; later passes reuse the mappings).  It is called right after the SYRK kernel has been launched, but measured
-//   on 8 x B200 the open waits for the running kernel (3.1 s for 14 x 20 GB after a 5.1 s kernel), so nothing overlaps yet:
-//   a pull-only exchange that needs the partial planes alone would halve it (round-2 item).
-// peer_grm_finalize: barrier, reduce kernel, barrier.
+// Pull only: a rank maps nothing but the peers' plane buffers (one cudaIpcOpenMemHandle per peer; measured 0.1-0.2 s per
+// 20 GB buffer the first time, and the open waits for running kernels, so it cannot be hidden behind the SYRK kernel).
+// peer_grm_prepare: publish / map the plane buffers (later passes reuse the mappings).
+// peer_grm_finalize: barrier, reduce kernel (owned blocks), barrier, gather kernel (everybody else's blocks), barrier.
 int peer_grm_prepare(eb_ctx* c) {
   const int W = c->comm.world;
   int rc;
-  if ((rc = peer_exchange(c, PEER_SLOT_PARTIAL, c->partial.p, c->partial.n * sizeof(double), c->nsplit))) return rc;
-  if ((rc = peer_exchange(c, PEER_SLOT_XTX, c->xtx.p, c->xtx.n * sizeof(double), c->npad))) return rc;
+  if (c->npad > (1 << 24)) { set_error("multi-GPU GRM: matrix too large for the exchange record"); return EB_ERR_ARG; }
+  if ((rc = peer_exchange(c, PEER_SLOT_PARTIAL, c->partial.p, c->partial.n * sizeof(double), c->nsplit + 64 * c->npad))) return rc;
   const size_t plane = (size_t)c->npad * c->npad;
   for (int r = 0; r < W; r++) {
     const PeerRecord& pr = c->peer[PEER_SLOT_PARTIAL].rec[r];
-    const PeerRecord& xr = c->peer[PEER_SLOT_XTX].rec[r];
-    if (xr.aux != c->npad || (size_t)pr.aux * plane * sizeof(double) > pr.bytes) {
-      set_error("multi-GPU GRM: rank %d has a different matrix size (npad %d vs %d): every shard must use the same rows", r, xr.aux, c->npad);
+    const int ns = pr.aux & 63, np = pr.aux >> 6;
+    if (np != c->npad || ns < 1 || (size_t)ns * plane * sizeof(double) > pr.bytes) {
+      set_error("multi-GPU GRM: rank %d has a different matrix size (npad %d vs %d): every shard must use the same rows", r, np, c->npad);
       return EB_ERR_STATE;
     }
   }
@@ -183,9 +206,8 @@ int peer_grm_finalize(eb_ctx* c) {
   a.world = W; a.rank = c->comm.rank;
   for (int r = 0; r < W; r++) {
     a.part[r] = (const double*)c->peer[PEER_SLOT_PARTIAL].mapped[r];
-    a.xtx[r] = (double*)c->peer[PEER_SLOT_XTX].mapped[r];
-    a.nsplit[r] = c->peer[PEER_SLOT_PARTIAL].rec[r].aux;
-    if (!a.part[r] || !a.xtx[r]) { set_error("peer_grm_finalize: buffers of rank %d are not mapped (peer_grm_prepare not called)", r); return EB_ERR_STATE; }
+    a.nsplit[r] = c->peer[PEER_SLOT_PARTIAL].rec[r].aux & 63;
+    if (!a.part[r]) { set_error("peer_grm_finalize: planes of rank %d are not mapped (peer_grm_prepare not called)", r); return EB_ERR_STATE; }
   }
   const bool dbg = getenv("EB_DEBUG") != nullptr;
   const auto tnow = [] { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
@@ -197,13 +219,20 @@ int peer_grm_finalize(eb_ctx* c) {
   const int mine = (nblocks - a.rank + W - 1) / W;
   EB_CUDA(cudaEventRecord(c->ev[3], c->stream));
   if (mine > 0) {
-    grm_peer_finalize_kernel<<<mine, 256, 0, c->stream>>>(a, c->npad, nblocks);
+    grm_peer_reduce_kernel<<<mine, 256, 0, c->stream>>>(a, c->npad, nblocks, c->partial.p, c->xtx.p);
+    EB_CHECK_LAUNCH(c);
+  }
+  EB_CUDA(cudaStreamSynchronize(c->stream));     // my reduced blocks are in my plane 0 ...
+  if ((rc = comm_barrier(c))) return rc;         // ... and everybody else's in theirs
+  const int groups = (nblocks + W - 1) / W;
+  if (W > 1 && groups > 0) {
+    grm_peer_gather_kernel<<<groups * (W - 1), 256, 0, c->stream>>>(a, c->npad, nblocks, c->xtx.p);
     EB_CHECK_LAUNCH(c);
   }
   EB_CUDA(cudaEventRecord(c->ev[4], c->stream));
-  EB_CUDA(cudaStreamSynchronize(c->stream));     // my stores have landed in every peer ...
-  if (dbg) fprintf(stderr, "[peer_grm_finalize] rank %d: wait for all ranks %.3f s, reduce kernel %.3f s\n", a.rank, tq1 - tq0, tnow() - tq1);
-  return peer_bury(c);                            // ... and (barrier) everybody's have landed here
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  if (dbg) fprintf(stderr, "[peer_grm_finalize] rank %d: wait for all ranks %.3f s, reduce + gather %.3f s\n", a.rank, tq1 - tq0, tnow() - tq1);
+  return peer_bury(c);                            // barrier: nobody overwrites its planes while a peer still pulls from them
 }
 
 struct AllreduceArgs {
@@ -284,7 +313,7 @@ extern "C" int eb_set_comm(eb_ctx* c, const eb_comm* comm) {
   if (!c) return EB_ERR_ARG;
   cudaSetDevice(c->device);
   eb::peer_release(c);
-  c->partial.defer = c->xtx.defer = c->fpG.defer = c->fpB.defer = c->fpS.defer = c->peer_scratch.defer = nullptr;
+  c->partial.defer = c->fpG.defer = c->fpB.defer = c->fpS.defer = c->peer_scratch.defer = nullptr;
   for (auto& reg : c->peer) { for (void* p : reg.graveyard) cudaFree(p); reg.graveyard.clear(); }
   if (!comm || comm->world <= 1) { c->has_comm = false; memset(&c->comm, 0, sizeof(c->comm)); c->comm.world = 1; return 0; }
   if (comm->world > eb::EB_MAX_WORLD || comm->rank < 0 || comm->rank >= comm->world || !comm->allgather_host || !comm->barrier) {
@@ -293,7 +322,6 @@ extern "C" int eb_set_comm(eb_ctx* c, const eb_comm* comm) {
   }
   c->comm = *comm; c->has_comm = true;
   c->partial.defer = &c->peer[eb::PEER_SLOT_PARTIAL].graveyard;
-  c->xtx.defer = &c->peer[eb::PEER_SLOT_XTX].graveyard;
   c->fpG.defer = &c->peer[eb::PEER_SLOT_A].graveyard;
   c->fpB.defer = &c->peer[eb::PEER_SLOT_B].graveyard;
   c->fpS.defer = &c->peer[eb::PEER_SLOT_C].graveyard;
