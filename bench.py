@@ -67,15 +67,20 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
-    def finish(self):
+    def mark(self):
+        """index of the next sample: call at the start / end of the timed region"""
+        return len(self.rows)
+
+    def finish(self, first=0, last=None):
         self.stop_flag = True
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[first:last] if (last is None or last > first) else self.rows[first:]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -194,12 +199,16 @@ def run_b200(args):
         return r
 
     def timed(fn, steps, warmup, sample_clocks=False):
+        # the clock sampler (an nvidia-smi child per rank) starts BEFORE the warm-up: its start-up (NVML enumeration of
+        # every GPU of the box) contends with CUDA calls and must not fall into the timed region; only the samples taken
+        # between the two marks are reported
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start(); time.sleep(1.0)
         for _ in range(warmup):
             fn()
         barrier()
-        sampler = ClockSampler(local) if sample_clocks else None
-        if sampler:
-            sampler.start(); time.sleep(0.25)
+        m0 = sampler.mark() if sampler else 0
         ctx.reset_launch_count()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         kern = []
@@ -211,13 +220,18 @@ def run_b200(args):
         barrier()
         ms = e0.elapsed_time(e1)
         launches = ctx.launch_count()
-        clocks = sampler.finish() if sampler else None
+        clocks = sampler.finish(m0, sampler.mark()) if sampler else None
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), r, kern, launches, clocks
 
     steps, warmup = max(1, args.steps), max(3, args.warmup)
+    # clock ramp (not a step of the workload): a fresh box idles at low clocks and the first second of FP64 tensor work runs
+    # up to 20 % slow (seen as 524 vs 444 ms kernels on the first run after boot); spin the DMMA issue-rate probe for ~2 s
+    t_ramp = time.perf_counter()
+    while time.perf_counter() - t_ramp < 2.0:
+        ctx.microbench_fp64()
     # resident arm
     ctx.adopt_packed_device(slab.data_ptr(), nsnp, rl, nind)
     ctx.set_rows(None)
