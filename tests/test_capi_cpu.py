@@ -54,3 +54,22 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(capi.EigB200Error):
         capi.Context(0)
+
+
+def test_header_is_plain_c_and_shim_links(tmp_path):
+    """include/eigb200.h compiles as C99 with -Wall -Werror and the integration shim (examples/smartpca_shim.c: the calls
+    INTEGRATION.md adds to smartpca.c, single- and multi-GPU) links against libeigb200.so"""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    capi.lib()
+    src = os.path.join(ROOT, "examples", "smartpca_shim.c")
+    out = str(tmp_path / "libshim.so")
+    cmd = [gcc, "-std=c99", "-D_POSIX_C_SOURCE=200809L", "-Wall", "-Werror", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), src, "-o", out,
+           "-L", os.path.join(ROOT, "eig_b200"), "-leigb200", "-lpthread", "-Wl,-rpath," + os.path.join(ROOT, "eig_b200"), "-Wl,--no-undefined"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    L = ctypes.CDLL(out)
+    assert hasattr(L, "eb_shim_full_mode") and hasattr(L, "eb_shim_threads")

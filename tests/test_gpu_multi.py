@@ -94,3 +94,46 @@ def test_in_process_communicator_threads():
     assert np.array_equal(out[0][0]["XTX"], out[1][0]["XTX"]), "reduced GRM must be bit-identical on both ranks"
     assert np.array_equal(out[0][3]["lambda_"], out[1][3]["lambda_"])
     lc.close(); single.close()
+
+
+def test_c_shim_runs(tmp_path):
+    """examples/smartpca_shim.c (plain C99 against include/eigb200.h): the single-context entry and the thread-per-GPU entry
+    give the spectrum of the Python-driven run"""
+    import ctypes
+    import shutil
+    import subprocess
+    import numpy as np
+    from eig_b200 import capi, synth
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    capi.lib()
+    out = str(tmp_path / "libshim.so")
+    cmd = [gcc, "-std=c99", "-D_POSIX_C_SOURCE=200809L", "-Wall", "-Werror", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "smartpca_shim.c"), "-o", out, "-L", os.path.join(ROOT, "eig_b200"), "-leigb200", "-lpthread",
+           "-Wl,-rpath," + os.path.join(ROOT, "eig_b200")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    L = ctypes.CDLL(out)
+    nsnp, nind, k = 3000, 200, 3
+    P = synth.packed_genotypes(8, nsnp, nind, missing=0.05, npops=3, delta=0.3)
+    ctx = capi.Context(0); ctx.upload_packed(P, nind)
+    want = ctx.pca_full(numeigs=k, numoutliter=5)
+    co_want, _, _ = ctx.evec_coords(want["evecs"])
+    ctx.close()
+    vp = ctypes.c_void_p
+    for entry in ("eb_shim_full_mode", "eb_shim_threads"):
+        xi = np.arange(nind, dtype=np.int32); lam = np.zeros(nind); vec = np.zeros((k, nind)); co = np.zeros((k, nind))
+        if entry == "eb_shim_full_mode":
+            rc = L.eb_shim_full_mode(P.ctypes.data_as(vp), ctypes.c_int64(nsnp), ctypes.c_int64(P.shape[1]), ctypes.c_int(nind), xi.ctypes.data_as(vp),
+                                     ctypes.c_int(nind), ctypes.c_int(k), ctypes.c_int(5), lam.ctypes.data_as(vp), vec.ctypes.data_as(vp), co.ctypes.data_as(vp))
+        else:
+            rc = L.eb_shim_threads(P.ctypes.data_as(vp), ctypes.c_int64(nsnp), ctypes.c_int64(P.shape[1]), ctypes.c_int(nind), xi.ctypes.data_as(vp),
+                                   ctypes.c_int(nind), ctypes.c_int(k), lam.ctypes.data_as(vp), vec.ctypes.data_as(vp))
+        assert rc == 0
+        n = len(want["lambda_"])
+        assert np.abs(lam[:n] - want["lambda_"]).max() <= 1e-12 * want["lambda_"][0], entry
+        got_vec = vec.reshape(-1)[:k * n].reshape(k, n)          # eb_pca_full packs [numeigs][nrows_final]
+        assert np.abs(np.abs(np.einsum("ij,ij->i", got_vec, want["evecs"])) - 1).max() < 1e-9
+        if entry == "eb_shim_full_mode" and n == nind:
+            assert np.abs(co - co_want).max() <= 1e-9 * np.abs(co_want).max()
