@@ -56,7 +56,7 @@ EXPORTS = [
     "eb_eig", "eb_eigvecs", "eb_ridoutlier", "eb_pca_full", "eb_fpca", "eb_gauss_matrix", "eb_project", "eb_get_timings",
     "eb_microbench_fp64", "eb_set_option", "eb_debug_tridiag", "eb_lsqproj", "eb_evec_coords", "eb_pop_counts", "eb_hash_ids", "eb_packed_file_header", "eb_upload_packed_file",
     "eb_download_packed", "eb_write_eval", "eb_write_evec", "eb_write_grm", "eb_grm_dense_begin", "eb_grm_dense_add", "eb_grm_dense_end", "eigvecs", "eigvals",
-    "eb_set_comm", "eb_peer_allreduce_test", "eb_snp_used_count", "eb_shrink_coords", "eb_debug_gemm", "eb_local_comm_create", "eb_local_comm_get", "eb_local_comm_destroy",
+    "eb_set_comm", "eb_peer_allreduce_test", "eb_snp_used_count", "eb_shrink_coords", "eb_debug_gemm", "eb_local_comm_create", "eb_local_comm_get", "eb_local_comm_destroy", "eb_numgtz", "eb_tw_stats", "eb_tw_tail",
 ]
 
 _lib = None
@@ -116,6 +116,23 @@ def packed_file_header(path):
     ni = C.c_int(0); ns = C.c_int(0); ih = C.c_int(0); sh = C.c_int(0); rl = C.c_int64(0); fb = C.c_int64(0)
     _chk(lib().eb_packed_file_header(path.encode(), C.byref(ni), C.byref(ns), C.byref(ih), C.byref(sh), C.byref(rl), C.byref(fb)))
     return dict(nind=ni.value, nsnp=ns.value, ihash=ih.value, shash=sh.value, rlen=rl.value, file_bytes=fb.value)
+
+
+def tw_stats(lam, znval=-1.0, minm=10):
+    """Tracy-Widom statistic and effective n per eigenvalue (smartpca.c:1336-1366, dotwcalc statsubs.c:1680-1725)"""
+    lam = np.ascontiguousarray(lam, np.float64)
+    m = lib().eb_numgtz(_p(lam), C.c_int(len(lam)))
+    tw = np.empty(m); zn = np.empty(m)
+    _chk(lib().eb_tw_stats(_p(lam), C.c_int(m), C.c_double(znval), C.c_int(minm), _p(tw), _p(zn)))
+    return tw, zn
+
+
+def tw_tail(tw, table):
+    """Tracy-Widom right tail ("p-value" column) from a POPGEN/twtable-style table [n][3] = x, tail, density"""
+    t = np.ascontiguousarray(table, np.float64)
+    x = np.ascontiguousarray(t[:, 0]); tl = np.ascontiguousarray(t[:, 1]); pd = np.ascontiguousarray(t[:, 2])
+    lib().eb_tw_tail.restype = C.c_double
+    return np.array([lib().eb_tw_tail(C.c_double(v), _p(x), _p(tl), _p(pd), C.c_int(len(x))) for v in np.atleast_1d(tw)])
 
 
 def write_eval(path, lam):

@@ -670,6 +670,77 @@ int eb_debug_gemm(eb_ctx* c, int a_km, int b_kn, const double* A, const double* 
   return 0;
 }
 
+// ---- Tracy-Widom statistics (host arithmetic on the spectrum): the loop smartpca.c:1336-1366 / twstats.c:58-77 around
+// dotwcalc (statsubs.c:1680-1725) and twnorm (statsubs.c:1655-1677, Johnstone 2001).  The reference re-sums the tail of the
+// spectrum for every eigenvalue (O(m^2): 2.5e9 flops at m = 50,000); suffix sums make it O(m).
+int eb_numgtz(const double* lambda, int n) {        // statsubs.c:1727-1742
+  int num = 0;
+  for (int k = 0; k < n; k++) if (lambda[k] > .000001) num++;
+  return num;
+}
+
+static double tw_norm(double lam, double p, double n) {
+  if (n < 0.0 || p < 0.0) return -10.0;
+  if (n < p) return tw_norm(lam, n, p);
+  const double y1 = sqrt(n - 1) + sqrt(p);
+  const double mu = y1 * y1;
+  const double y2 = (1.0 / sqrt(n - 1)) + 1.0 / sqrt(p);
+  const double phi = y1 * pow(y2, 1.0 / 3.0);
+  return (lam - mu) / phi;
+}
+
+int eb_tw_stats(const double* lambda, int m, double znval, int minm, double* tw, double* zn) {
+  if (!lambda || m < 0 || !tw || !zn) { set_error("eb_tw_stats: bad argument"); return EB_ERR_ARG; }
+  std::vector<double> s1((size_t)m + 1, 0.0), s2((size_t)m + 1, 0.0);
+  for (int i = m - 1; i >= 0; i--) { s1[i] = s1[i + 1] + lambda[i]; s2[i] = s2[i + 1] + lambda[i] * lambda[i]; }
+  for (int i = 0; i < m; i++) {
+    const int mm = m - i;
+    const double lsum = s1[i];
+    tw[i] = zn[i] = -1.0;
+    if (mm < minm || lsum <= 0.0) continue;
+    const double tm = (double)mm, y = tm / lsum;
+    if (znval > 0.0) {
+      zn[i] = znval;
+      tw[i] = tw_norm(lambda[i] * y * znval, tm, znval);
+    } else {
+      const double bot = s2[i] * y * y - tm;       // sum (lambda_j * y)^2 - m
+      const double z = (double)mm * (double)(mm + 2) / bot;
+      zn[i] = z;
+      tw[i] = tw_norm(lambda[i] * y * z, tm, z);
+    }
+  }
+  return 0;
+}
+
+// Tracy-Widom right tail from the caller's table (POPGEN/twtable: x, tail, density; what `twstats -t twtable` and the table
+// compiled into the reference hold): twtail -> gettw (statsubs.c:1590-1604, 1811-1860), firstgtx / fgtx (1744-1766), cinterp
+// (cubic Hermite, statsubs.c), including the reference's behaviour beyond the table (below: tail 1; above: the
+// Margetis-Edelman DENSITY formula twdensx is what gettw returns as the tail, statsubs.c:1837-1841).
+static int tw_fgtx(const double* tab, int lo, int hi, double val) {
+  if (val >= tab[hi]) return hi + 1;
+  if (val < tab[lo]) return lo;
+  const int k = (lo + hi) / 2;
+  if (val <= tab[k]) return tw_fgtx(tab, lo + 1, k, val);
+  return tw_fgtx(tab, k, hi - 1, val);
+}
+double eb_tw_tail(double x, const double* tab_x, const double* tab_tail, const double* tab_pdf, int n) {
+  if (!tab_x || !tab_tail || !tab_pdf || n < 2) return -1.0;
+  const int k = tw_fgtx(tab_x, 0, n - 1, x);
+  if (k <= 0) return 1.0;
+  if (k >= n) {
+    if (x <= 0.0) return 0.0;
+    const double sqrt_pi = 1.0 / 0.5641895835477562869480795;       // SQRT_PI, include/statsubs.h:12,17
+    const double lbot = log(sqrt_pi * 4.0);
+    return exp(-0.25 * log(x) + -2.0 * pow(x, 1.5) / 3.0 - lbot);
+  }
+  const double x0 = tab_x[k - 1], x1 = tab_x[k], f0 = tab_tail[k - 1], f0p = -tab_pdf[k - 1], f1 = tab_tail[k], f1p = -tab_pdf[k];
+  const double inc = x1 - x0, yval = (x - x0) / inc;
+  const double a0 = f0, a1 = f0p * inc, cc0 = f1 - (a0 + a1), cc1 = f1p * inc - a1, a2 = 3 * cc0 - cc1, a3 = cc1 - 2 * cc0;
+  double f = a3;
+  f *= yval; f += a2; f *= yval; f += a1; f *= yval; f += a0;
+  return f;
+}
+
 int64_t eb_snp_used_count(eb_ctx* c) { return c ? c->nused : 0; }
 
 int eb_get_timings(eb_ctx* c, eb_timings* t) {

@@ -243,6 +243,18 @@ int eb_shrink_coords (eb_ctx *, int numeigs, int newshrink, double *coords, doub
  * else [N][K] (all dense row-major host arrays) */
 int eb_debug_gemm (eb_ctx *, int a_km, int b_kn, const double *A, const double *B, double *C, int M, int N, int K);
 
+/* Tracy-Widom statistics of the spectrum: the loop smartpca.c:1336-1366 (twstats.c:58-77) around dotwcalc
+ * (statsubs.c:1680-1725) / twnorm (1655-1677).  lambda[m] descending with m = eb_numgtz(lambda, nrows) (statsubs.c:1727).
+ * znval > 0: fixed effective number of markers (smartpca passes MAX(nrows, znval)); <= 0: estimated per eigenvalue.
+ * tw[i] / zn[i]: the "twstat" / "effect. n" columns (-1 where the reference prints NA: fewer than minm eigenvalues left).
+ * The p-value stays with the caller's twtail() table lookup (statsubs.c:1590, POPGEN/twtable).  Host arithmetic, O(m) by
+ * suffix sums where the reference re-sums the tail for every eigenvalue (O(m^2)). */
+int eb_numgtz (const double *lambda, int n);
+int eb_tw_stats (const double *lambda, int m, double znval, int minm, double *tw, double *zn);
+/* the "p-value" column: twtail -> gettw (statsubs.c:1590, 1811-1860) on the caller's table (POPGEN/twtable rows: x, right
+ * tail, density; n rows, x ascending), cubic interpolation inside the table and the reference's formulas outside it */
+double eb_tw_tail (double twstat, const double *tab_x, const double *tab_tail, const double *tab_pdf, int n);
+
 /* -------- measurement helpers -------- */
 /* last pass timings measured with CUDA events on the library's stream (milliseconds) */
 typedef struct {

@@ -73,3 +73,39 @@ def test_header_is_plain_c_and_shim_links(tmp_path):
     assert r.returncode == 0, r.stderr
     L = ctypes.CDLL(out)
     assert hasattr(L, "eb_shim_full_mode") and hasattr(L, "eb_shim_threads")
+
+
+def test_tw_stats_reproduce_twexample_golden():
+    """POPGEN/twexample.eval -> twexample.out (the reference's own fixture for twstats / the Tracy-Widom block of smartpca):
+    twstat and effective n columns at print precision; suffix-sum formulation vs the reference's per-eigenvalue re-summation"""
+    gold = os.path.join(ROOT, "tests", "golden")
+    lam = np.loadtxt(os.path.join(gold, "twexample.eval"))
+    lam = -np.sort(-lam)
+    rows = [l.split() for l in open(os.path.join(gold, "twexample.out")) if l.strip() and not l.strip().startswith("#")]
+    tw, zn = capi.tw_stats(lam, znval=-1.0, minm=10)
+    assert len(rows) == len(tw) == capi.lib().eb_numgtz(lam.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(len(lam)))
+    checked = 0
+    for i, r in enumerate(rows):
+        assert abs(float(r[1]) - lam[i]) < 5.1e-7
+        if r[3] == "NA":
+            assert tw[i] == -1.0 and zn[i] == -1.0
+            continue
+        assert abs(float(r[3]) - tw[i]) <= 5.1e-4, (i, r[3], tw[i])
+        assert abs(float(r[5]) - zn[i]) <= 5.1e-4 * max(1.0, abs(zn[i]) * 1e-3), (i, r[5], zn[i])
+        checked += 1
+    assert checked > 100
+    # p-value column through the table the reference ships (POPGEN/twtable == include/twtable.h), 6 significant digits
+    table = np.loadtxt(os.path.join(gold, "twtable"), comments="#")
+    assert table.shape == (161, 3)
+    pv = capi.tw_tail(tw, table)
+    for i, r in enumerate(rows):
+        if r[3] == "NA":
+            continue
+        want = float(r[4])
+        assert abs(pv[i] - want) <= 6e-6 * max(abs(want), 1e-300) + (1e-12 if want > 1e-6 else 0.0), (i, r[4], pv[i])
+    # plain re-summation (the reference's order of operations) agrees to rounding
+    m = len(tw)
+    for i in (0, 1, 57, m - 11):
+        ev = lam[i:m] * ((m - i) / lam[i:m].sum())
+        z = (m - i) * (m - i + 2) / ((ev * ev).sum() - (m - i))
+        assert abs(z - zn[i]) <= 1e-9 * abs(z)
