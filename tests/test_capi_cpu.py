@@ -109,3 +109,14 @@ def test_tw_stats_reproduce_twexample_golden():
         ev = lam[i:m] * ((m - i) / lam[i:m].sum())
         z = (m - i) * (m - i + 2) / ((ev * ev).sum() - (m - i))
         assert abs(z - zn[i]) <= 1e-9 * abs(z)
+
+
+def test_scripts_parse():
+    """bench.py, the driver entry and every probe under tools/ are at least syntactically valid (they only run on a GPU box)"""
+    import ast
+    import glob
+    files = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")] + sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))) + \
+        [os.path.join(ROOT, "tests", "multi_worker.py")]
+    assert len(files) > 10
+    for f in files:
+        ast.parse(open(f).read(), filename=f)
