@@ -1,26 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- smartpca hot path on B200: GRM accumulation throughput (SNP*indiv^2/s) on synthetic Hardy-Weinberg genotypes.
+"""bench.py -- smartpca hot path on B200: GRM accumulation throughput (SNP*indiv^2/s) at the shape BASELINE.json's metric is
+quoted on, 50,000 individuals x 600,000 SNPs (configs[3], "C4"), plus one complete full-mode smartpca run of that shape.
 
 Contract: python bench.py --gpus N --steps K --warmup W [--impl reference]   (torchrun launches N>1, one rank per GPU)
 
-Workload (BASELINE.json configs[1]): 5,000 individuals x 600,000 SNPs, no missing data, full-mode smartpca,
-numoutevec=10, no outlier removal.  A "step" = one pass of the region smartpca.c:1088-1236 over one packed slab:
-per-SNP allele counts + normalisation + drop rule, the packed->FP64 symmetric rank-M update, mirror + trace.
-  value : inputs resident in HBM when the timed region starts (library entry eb_grm on an adopted device slab)
-  e2e   : the same pass through the C-ABI with HOST buffers (eb_upload_packed from pinned memory, eb_set_rows,
-          eb_grm, per-SNP outputs copied back) -- H2D/D2H inside the timed region
-N>1: SNPs shard across ranks (each rank owns its own 600k-SNP slab: weak scaling); the one exchange step is the
-reduction of the partial N x N FP64 GRMs, fused with the split-K finalize/mirror in the library's own kernel over peer
-memory (NVLink; CUDA IPC between the torchrun ranks), inside the timed region.  --reduce nccl (or a box without IPC)
-uses an NCCL all-reduce on the library's buffer instead and says so in config.parallelism.
-The reference arm (--impl reference) times the reference's own CPU code for the same region (oracle/_ref, built from
-/root/reference by oracle/Makefile) with all host threads on a bounded SNP sample of the same workload.
+Workload: synthetic Hardy-Weinberg genotypes, 50,000 x 600,000, no missing data, fancynorm + altnormstyle YES.
+A "step" = one pass of the region smartpca.c:1088-1236 over one 60,000-SNP slab of that matrix (1/10 of it; step i takes
+slab i mod 10): row selection (loadindx -> working matrix), per-SNP allele counts + normalisation + drop rule, the
+packed -> FP64 symmetric rank-M update of the 50,000 x 50,000 matrix, mirror (symit2) + trace.
+  value : the slab resident in HBM when the timed region starts (eb_adopt_packed_device / eb_set_rows / eb_grm)
+  e2e   : the same pass through the C-ABI with HOST buffers (eb_upload_packed from pinned memory, eb_set_rows, eb_grm,
+          per-SNP outputs copied back) -- H2D / D2H inside the timed region
+N>1 is STRONG scaling: the slab's SNPs are split over the ranks; every rank accumulates a partial 50,000 x 50,000 GRM whose
+128 x 128 tiles go straight from the SYRK kernel's epilogue into the owning rank's receive buffer over NVLink (peer memory,
+CUDA IPC); a stream-ordered flag barrier, the owner's fixed-order sum and an all-gather of the reduced tiles complete the
+step -- the 20 GB exchange is inside the timed region, with no host collective in it.
+`smartpca_e2e_s`: after the timed steps, ONE complete run of the named configuration on the N GPUs, host buffers to output
+files: upload of the 600,000-SNP matrix -> eb_pca_full (numoutevec 10, numoutlieriter 5, all 50,000 eigenvalues) ->
+eb_evec_coords (loadings, projections, lsqproj) -> Tracy-Widom table -> .eval / .evec files.
+The reference arm (--impl reference) times the reference's own CPU code for the step's region (oracle/_ref, built from
+/root/reference by oracle/Makefile) with all host threads on a bounded SNP sample of the same 50,000-row matrix.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -29,26 +35,29 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_IND = 5000
-N_SNP = 600000
+N_IND = int(os.environ.get("EB_BENCH_NIND", 50000))
+N_SNP = int(os.environ.get("EB_BENCH_NSNP", 600000))
+N_SLABS = 10
+STEP_SNPS = N_SNP // N_SLABS
 SEED = 1
 METRIC = "grm_snp_indiv2_per_s"
 UNIT = "SNP*indiv^2/s"
-CPU_SAMPLE_SNPS = 20000
 
 
 def workload_config(extra=None):
-    cfg = {"workload": "smartpca full mode 5000 indiv x 600000 SNPs (BASELINE configs[1]), synthetic Hardy-Weinberg p~U(0.05,0.95), "
-                       "no missing, fancynorm+altnormstyle YES, no outlier removal",
-           "nindiv": N_IND, "nsnp_per_gpu": N_SNP, "seed": SEED,
-           "l2": "packed input 750 MB per step > 126 MB L2 (no explicit flush needed)"}
+    cfg = {"workload": "smartpca full mode %d indiv x %d SNPs (BASELINE configs[3]; the shape the metric is quoted on), synthetic "
+                       "Hardy-Weinberg p~U(0.05,0.95), no missing, fancynorm+altnormstyle YES; step = region smartpca.c:1088-1236 over one "
+                       "%d-SNP slab (1/%d of the matrix, slabs rotate)" % (N_IND, N_SNP, STEP_SNPS, N_SLABS),
+           "nindiv": N_IND, "nsnp": N_SNP, "nsnp_per_step": STEP_SNPS, "seed": SEED,
+           "l2": "every step streams a different %.0f MB slab and writes a %.1f GB FP64 accumulator per GPU (>> 126 MB L2): no explicit flush needed"
+                 % (STEP_SNPS * max(48, (N_IND + 3) // 4) / 1e6, 8.0 * N_IND * N_IND / 1e9)}
     if extra:
         cfg.update(extra)
     return cfg
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / power / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -77,40 +86,60 @@ class ClockSampler(threading.Thread):
             self.proc.terminate()
         self.join(timeout=2)
         rows = self.rows[first:last] if (last is None or last > first) else self.rows[first:]
-        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in rows if r and num(r[0]) is not None]
+        mx = [num(r[1]) for r in rows if len(r) > 1 and num(r[1]) is not None]
+        pw = [num(r[2]) for r in rows if len(r) > 2 and num(r[2]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_mhz_min": min(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_median": float(np.median(pw)) if pw else None, "power_w_max": max(pw) if pw else None, "reasons": reasons,
                 "samples": len(sm)}
 
 
 def cpu_baseline_run(steps, warmup, budget_s=100.0, nthreads=None):
-    """Reference CPU implementation of the same region on a bounded SNP sample (sized by a short calibration so that
-    warmup+steps passes fit in ~budget_s of wall time)."""
+    """Reference CPU implementation of the step's region on a bounded SNP sample of the same 50,000-row matrix (sized by a
+    short calibration so that warmup+steps passes fit in ~budget_s of wall time).  The reference's per-SNP loop
+    (getcolxz_binary1/2 + domult_increment_lookup, smartpca.c:1116-1221) is what is timed; symit2 / trace run once per pass in
+    the reference and would dominate a bounded sample, so they are left out (in the reference's favour)."""
     from eig_b200 import synth
     from oracle import bindings as ob
     nthreads = nthreads or os.cpu_count()
     kind = "reference" if ob.ref() is not None else "port"
-    fn = (lambda P: ob.ref_grm(P, N_IND, nthreads=nthreads)) if kind == "reference" else (lambda P: ob.port_grm(P, N_IND))
-    cal = 1000 if kind == "reference" else 100
+    tri = None
+    if kind == "reference":
+        tri = np.zeros(N_IND * (N_IND + 1) // 2)
+
+        def fn(P):
+            r = ob.ref_grm_loop(P, N_IND, nthreads=nthreads, tri=tri)
+            return int(r["used"].sum()), r["secs_loop"]
+    else:
+        def fn(P):
+            t0 = time.perf_counter(); r = ob.port_grm(P, N_IND)
+            return int(r["used"].sum()), time.perf_counter() - t0
+    cal = 40 if kind == "reference" else 4
     Pc = synth.packed_genotypes(SEED, cal, N_IND)
-    t0 = time.perf_counter(); fn(Pc); rate = cal / (time.perf_counter() - t0)          # SNPs per second
-    nsnp = int(min(CPU_SAMPLE_SNPS, max(cal, rate * budget_s / (steps + warmup))))
+    _, sec = fn(Pc)
+    rate = cal / max(sec, 1e-6)                                               # SNPs per second
+    nsnp = int(min(STEP_SNPS, max(20, rate * budget_s / (steps + warmup))))
+    nsnp = max(20, nsnp // 20 * 20)                                           # whole 20-SNP blocks
     P = synth.packed_genotypes(SEED, nsnp, N_IND)
-    times = []
+    times = []; used = 0
     for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        r = fn(P)
-        dt = time.perf_counter() - t0
+        used, dt = fn(P)
         if it >= warmup:
             times.append(dt)
-    used = int(r["used"].sum())
     sec = float(np.mean(times))
     threads_used = min(nthreads, 127) if kind == "reference" else 1
     return {"value": used * float(N_IND) ** 2 / sec, "unit": UNIT, "cores": threads_used, "kind": kind,
-            "sample": "first %d of 600000 SNPs x %d individuals per step, %.2f s/step, %d threads, region smartpca.c:1088-1236 "
-                      "(getcolxz_binary1/2 + domult_increment_lookup + symit2)" % (nsnp, N_IND, sec, threads_used), "secs_per_step": sec}
+            "sample": "first %d of the step's %d SNPs x %d individuals per step, %.2f s/step, %d threads, per-SNP loop smartpca.c:1116-1221 "
+                      "(getcolxz_binary1/2 + domult_increment_lookup; symit2/trace, once per pass, not included)"
+                      % (nsnp, STEP_SNPS, N_IND, sec, threads_used), "secs_per_step": sec}
 
 
 def run_reference(args):
@@ -120,11 +149,16 @@ def run_reference(args):
     steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
     cb = cpu_baseline_run(steps, warmup)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-            "ms_per_step": cb["secs_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": cb["secs_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config({"host_cpus": os.cpu_count()}),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def _stats(v):
+    v = np.asarray(v, dtype=np.float64).reshape(-1)
+    return {"min": float(v.min()), "median": float(np.median(v)), "max": float(v.max())}
 
 
 def run_b200(args):
@@ -136,67 +170,71 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     ctx = capi.Context(local)          # raises if the CUDA library / a B200 is missing: no fallback
-
-    nind, nsnp = N_IND, N_SNP
-    rl = synth.rlen_for(nind)
-    slab = torch.empty((nsnp, rl), dtype=torch.uint8, device=dev)
-    ctx.synth_packed_device(slab.data_ptr(), nsnp, rl, nind, seed=SEED, s0=rank * nsnp)     # each rank: its own SNP shard
-    ctx.sync()
-    host = torch.empty((nsnp, rl), dtype=torch.uint8, pin_memory=True)
-    host.copy_(slab); torch.cuda.synchronize()
-    host_np = host.numpy()
+    lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)      # CUDA events go on the stream the library launches on
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # exchange step: the library's peer-memory kernel unless asked otherwise / unavailable on this box (all ranks agree)
-    reduce_mode = "none"
+    nind = N_IND
+    rl = synth.rlen_for(nind)
+    s0, s1 = parallel.shard_snps(STEP_SNPS, rank, world)       # this rank's part of every slab (strong scaling)
+    per = s1 - s0
+
+    # ---- multi-GPU parity, before anything is timed: the sharded pass == the single-GPU pass on a small matrix
+    parity = None
     if world > 1:
-        reduce_mode = args.reduce
-        if reduce_mode == "peer":
-            ok = 1.0
-            try:
-                ctx.set_comm(parallel.TorchComm(device=dev))
-                chk = ctx.peer_allreduce_test(np.full(64, float(rank + 1)))
-                ok = 1.0 if np.all(chk == world * (world + 1) / 2) else 0.0
-            except capi.EigB200Error as ex:
-                print("rank %d: peer path unavailable: %s" % (rank, ex), file=sys.stderr)
-                ok = 0.0
-            t = torch.tensor([ok], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            if t.item() < 1.0:
-                ctx.set_comm(None)
-                reduce_mode = "nccl"
+        ctx.set_comm(parallel.TorchComm(device=dev))
+        pn, pm = 1000, 4096 * world
+        prl = synth.rlen_for(pn)
+        small = torch.empty((pm, prl), dtype=torch.uint8, device=dev)
+        ctx.synth_packed_device(small.data_ptr(), pm, prl, pn, seed=7, s0=0, missing=0.05, npops=3, delta=0.2); ctx.sync()
+        one = capi.Context(local)
+        one.adopt_packed_device(small.data_ptr(), pm, prl, pn); one.set_rows(None)
+        want = one.grm(want_snp=False, want_xtx=True)
+        a0, a1 = parallel.shard_snps(pm, rank, world)
+        ctx.adopt_packed_device(small.data_ptr() + a0 * prl, a1 - a0, prl, pn); ctx.set_rows(None)
+        got = None
+        for _ in range(2):                                       # the second pass reuses the mapped buffers and the flag epochs
+            got = ctx.grm(want_snp=False, want_xtx=True)
+        err = float(np.abs(got["XTX"] - want["XTX"]).max() / np.abs(want["XTX"]).max())
+        mine = torch.from_numpy(got["XTX"].view(np.int64).copy()).to(dev)
+        allx = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allx, mine)
+        same = all(bool(torch.equal(allx[0], t)) for t in allx)
+        flag = torch.tensor([1.0 if (err <= 1e-12 and same and got["nused"] == want["nused"]) else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = {"checked": True, "ok": bool(flag.item() == 1.0), "shape": "%d indiv x %d SNPs, 5%% missing, %d shards" % (pn, pm, world),
+                  "max_rel_err_vs_single_gpu": err, "bit_identical_across_ranks": same, "tolerance": 1e-12}
+        one.close(); del small, mine, allx
+        if not parity["ok"]:
+            raise SystemExit("bench: sharded GRM disagrees with the single-GPU pass: %r" % (parity,))
 
-    def reduce_partials():
-        ptr, ld, n = ctx.grm_device_ptr()
-        t = parallel.device_view(ptr, (ld, ld), dev)
-        dist.all_reduce(t)             # every rank ends with the full GRM (the eigensolver then runs replicated / row-distributed)
-        torch.cuda.synchronize()
+    # ---- inputs: this rank's shard of all ten slabs, generated on the device, mirrored in pinned host memory
+    slab = torch.empty((N_SLABS * per, rl), dtype=torch.uint8, device=dev)
+    for k in range(N_SLABS):
+        ctx.synth_packed_device(slab.data_ptr() + k * per * rl, per, rl, nind, seed=SEED, s0=k * STEP_SNPS + s0)
+    ctx.sync()
+    host = torch.empty((N_SLABS * per, rl), dtype=torch.uint8, pin_memory=True)
+    host.copy_(slab); torch.cuda.synchronize()
+    host_np = host.numpy()
 
-    def step_resident():
-        if world == 1 or reduce_mode == "peer":
-            return ctx.grm(want_snp=False)
-        r = ctx.grm(want_snp=False, partial=True)
-        reduce_partials()
-        r["y"], _ = ctx.grm_finish()
-        return r
-
-    def step_e2e():
-        ctx.upload_packed(host_np, nind)
+    def step_resident(i):
+        k = i % N_SLABS
+        ctx.adopt_packed_device(slab.data_ptr() + k * per * rl, per, rl, nind)
         ctx.set_rows(None)
-        if world == 1 or reduce_mode == "peer":
-            return ctx.grm(want_snp=True)
-        r = ctx.grm(want_snp=True, partial=True)
-        reduce_partials()
-        r["y"], _ = ctx.grm_finish()
-        return r
+        return ctx.grm(want_snp=False)
+
+    def step_e2e(i):
+        k = i % N_SLABS
+        ctx.upload_packed(host_np[k * per:(k + 1) * per], nind)
+        ctx.set_rows(None)
+        return ctx.grm(want_snp=True)
 
     def timed(fn, steps, warmup, sample_clocks=False):
         # the clock sampler (an nvidia-smi child per rank) starts BEFORE the warm-up: its start-up (NVML enumeration of
@@ -205,18 +243,18 @@ def run_b200(args):
         sampler = ClockSampler(local) if sample_clocks else None
         if sampler:
             sampler.start(); time.sleep(1.0)
-        for _ in range(warmup):
-            fn()
+        for i in range(warmup):
+            fn(i)
         barrier()
         m0 = sampler.mark() if sampler else 0
         ctx.reset_launch_count()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        kern = []
-        e0.record()
-        for _ in range(steps):
-            r = fn()
-            kern.append(ctx.timings())
-        e1.record()
+        kern = []; used = []
+        e0.record(lib_stream)
+        for i in range(steps):
+            r = fn(warmup + i)
+            kern.append(ctx.timings()); used.append((int(ctx.snp_used_count()), int(r["nused"])))
+        e1.record(lib_stream)
         barrier()
         ms = e0.elapsed_time(e1)
         launches = ctx.launch_count()
@@ -224,37 +262,77 @@ def run_b200(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), r, kern, launches, clocks
+        return float(t.item()), r, kern, used, launches, clocks
 
     steps, warmup = max(1, args.steps), max(3, args.warmup)
-    # clock ramp (not a step of the workload): a fresh box idles at low clocks and the first second of FP64 tensor work runs
-    # up to 20 % slow (seen as 524 vs 444 ms kernels on the first run after boot); spin the DMMA issue-rate probe for ~2 s
-    t_ramp = time.perf_counter()
-    while time.perf_counter() - t_ramp < 2.0:
-        ctx.microbench_fp64()
-    # resident arm
-    ctx.adopt_packed_device(slab.data_ptr(), nsnp, rl, nind)
-    ctx.set_rows(None)
-    ms, r, kern, launches, clocks = timed(step_resident, steps, warmup, sample_clocks=True)
-    own_used = int(ctx.snp_used_count())           # this shard's SNPs that entered XTX
-    used = torch.tensor([own_used], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(used)
-    if reduce_mode == "peer":
-        assert int(used.item()) == int(r["nused"]), "library total of used SNPs disagrees with the per-shard sum"
-    units = float(used.item()) * float(nind) ** 2
+    # ---- resident arm
+    ms, r, kern, used, launches, clocks = timed(step_resident, steps, warmup, sample_clocks=True)
+    total_used = float(np.mean([u[1] for u in used]))          # SNPs of the whole slab (all shards) that entered XTX, per step
+    own_used = float(np.mean([u[0] for u in used]))
+    units = total_used * float(nind) ** 2
     ms_per_step = ms / steps
     value = units / (ms_per_step * 1e-3)
-    grm_ms = float(np.mean([k["grm_ms"] for k in kern]))
+    keys = ("gather_ms", "stats_ms", "grm_ms", "exchange_wait_ms", "finalize_ms", "grm_sm_mhz", "grm_sms", "grm_cta_min_ms", "grm_cta_max_ms", "grm_span_ms")
+    mine = torch.tensor([[float(k[q]) for q in keys] for k in kern], dtype=torch.float64, device=dev)      # [steps][keys]
+    if world > 1:
+        allk = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allk, mine)
+        allk = torch.stack(allk).cpu().numpy()                  # [world][steps][keys]
+    else:
+        allk = mine.cpu().numpy()[None]
+    grm_ms = float(allk[0, :, 2].mean())                       # rank 0's kernel (the roofline line); all ranks below
     flops = float(nind) * (nind + 1.0) * own_used
     achieved = flops / (grm_ms * 1e-3) / 1e12
+    per_rank = {q: _stats(allk[:, :, j]) for j, q in enumerate(keys)}
+    per_rank["grm_ms_by_rank_median"] = [float(np.median(allk[w, :, 2])) for w in range(world)]
+    nonkernel_ms = ms_per_step - float(np.mean(allk[:, :, 2].max(axis=0)))
 
-    # e2e arm (host buffers through the C-ABI)
-    ems, er, _, _, _ = timed(step_e2e, max(1, min(steps, 5)), 1)
+    # ---- e2e arm (host buffers through the C-ABI)
     esteps = max(1, min(steps, 5))
+    ems, er, _, _, _, _ = timed(step_e2e, esteps, 1)
     e2e_value = units / (ems / esteps * 1e-3)
-    h2d = int(nsnp * rl + 4 * nind)
-    d2h = int(nsnp * (4 * 3 + 1 + 8 * 2) + 16)
+    h2d = int(STEP_SNPS * rl + 4 * nind * world)
+    d2h = int(STEP_SNPS * (4 * 3 + 1 + 8 * 2) + 16 * world)
+
+    # ---- one complete full-mode smartpca run of the named configuration (host matrix -> output files), all ranks
+    del slab
+    torch.cuda.empty_cache()
+    e2e_run = None
+    if not args.no_full_run:
+        outdir = tempfile.mkdtemp(prefix="eb_bench_")
+        barrier()
+        t0 = time.perf_counter()
+        ctx.upload_packed(host_np, nind)
+        t_up = time.perf_counter() - t0; t1 = time.perf_counter()
+        res = ctx.pca_full(numeigs=10, numoutliter=5)
+        t_pca = time.perf_counter() - t1; t1 = time.perf_counter()
+        coords, es, ok = ctx.evec_coords(res["evecs"])
+        t_co = time.perf_counter() - t1; t1 = time.perf_counter()
+        if rank == 0:
+            lam = res["lambda_"]
+            tw, zn = capi.tw_stats(lam)
+            tab = np.loadtxt(os.path.join(ROOT, "tests", "golden", "twtable"))
+            pv = capi.tw_tail(tw[:64], tab)
+            t_tw = time.perf_counter() - t1; t1 = time.perf_counter()
+            ids = ["ind%d" % i for i in res["xindex"]]; groups = ["Pop%d" % k for k in synth.pop_of(nind, 4)[res["xindex"]]]
+            capi.write_eval(os.path.join(outdir, "bench.eval"), lam)
+            capi.write_evec(os.path.join(outdir, "bench.evec"), lam[:10], ids, groups, coords[:, res["xindex"]])
+            t_wr = time.perf_counter() - t1
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tm = ctx.timings()
+        if rank == 0:
+            e2e_run = {"seconds": float(tt.item()), "upload_s": t_up, "pca_full_s": t_pca, "grm_s": res["secs_grm"], "eig_s": res["secs_eig"],
+                       "evec_coords_s": t_co, "tracy_widom_s": t_tw, "write_s": t_wr, "passes": int(res["niter"]), "removed": int(len(res["removed_index"])),
+                       "nused": int(res["nused"]), "lambda_top": [float(x) for x in lam[:3]], "lambda_sum": float(lam.sum()), "tw_top": float(tw[0]),
+                       "tw_pvalue_top": float(pv[0]), "coords_ok": bool(ok.all()), "eval_bytes": os.path.getsize(os.path.join(outdir, "bench.eval")),
+                       "evec_bytes": os.path.getsize(os.path.join(outdir, "bench.evec")),
+                       "eig_ms": {k: tm[k] for k in ("tridiag_ms", "bisect_ms", "vectors_ms")}, "chfsi_converged": int(tm["chfsi_converged"]),
+                       "chfsi_resid": float(tm["chfsi_resid"]),
+                       "what": "host matrix (pinned) -> eb_upload_packed -> eb_pca_full(numoutevec 10, numoutlieriter 5, all eigenvalues) -> eb_evec_coords -> "
+                               "Tracy-Widom -> .eval/.evec files; wall clock, max over ranks"}
 
     line = None
     if rank == 0:
@@ -270,19 +348,14 @@ def run_b200(args):
         peak = 2.0 * n ** 3 / (best * 1e-3) / 1e12
         del a, b
         dmma, dfma = ctx.microbench_fp64()
-        # full pipeline once (adds the eigensolver): upload -> rows -> GRM -> all eigenvalues + 10 vectors
-        if world == 1:
-            t0 = time.perf_counter()
-            ctx.upload_packed(host_np, nind); ctx.set_rows(None); ctx.grm(want_snp=True); lam, vec = ctx.eig(10)
-            pipeline_s = time.perf_counter() - t0
-            eig_t = ctx.timings()
-        else:
-            pipeline_s, eig_t = None, {}
-        traffic = None
+        # DRAM traffic of the dominant kernel: from the committed ncu capture of THIS launch shape, else null
+        traffic = None; traffic_src = None
         tp = os.path.join(ROOT, "profiles", "grm_syrk_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                if tj.get("nindiv") == nind and tj.get("nsnp_per_launch") == per:
+                    traffic = tj.get("dram_bytes_per_launch"); traffic_src = tj.get("source")
             except Exception:
                 traffic = None
         cb = None
@@ -292,26 +365,33 @@ def run_b200(args):
                 cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as ex:      # the checker is optional for the product line
                 cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
+        par = "single GPU" if world == 1 else ("strong scaling: the step's %d SNPs split over %d GPUs; partial-GRM tiles pushed from the SYRK epilogue into the "
+                                               "owner's receive buffer over NVLink (peer memory, CUDA IPC), stream-ordered flag barrier, fixed-order reduce + "
+                                               "all-gather of the tiles; no host collective inside the step" % (STEP_SNPS, world))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config({"parallelism": ("snp-shard x%d + %s" % (world, "fused finalize+reduce kernel over peer memory (CUDA IPC / NVLink)" if reduce_mode == "peer"
-                                                            else "nccl all_reduce of partial GRM")) if world > 1 else "single GPU",
-                                           "nsplit": kern[-1]["nsplit"]}),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config({"parallelism": par, "nsplit": kern[-1]["nsplit"], "nsnp_per_gpu_per_step": per}),
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ems / esteps},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ems / esteps, "steps": esteps},
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "tensor", "kernel": "grm_syrk_kernel (FP64 DMMA.8x8x4)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": achieved / peak, "traffic": traffic, "kernel_ms": grm_ms,
-                             "peak_source": "cuBLAS DGEMM fp64 8192^3 best-of-5 measured in this run (MEASURED_PEAKS.json has no FP64 entry); "
-                                            "microbench issue rates: DMMA %.1f, DFMA %.1f TFLOP/s" % (dmma, dfma),
-                             "algorithmic": "N(N+1)*M_used flops per launch (lower triangle incl. diagonal, FMA=2)"},
+                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": grm_ms,
+                             "peak_source": "cuBLAS DGEMM fp64 8192^3 best-of-5 measured in this run on rank 0 (MEASURED_PEAKS.json has no FP64 entry); "
+                                            "issue-rate microbenchmarks after the run: DMMA %.1f, DFMA %.1f TFLOP/s" % (dmma, dfma),
+                             "algorithmic": "N(N+1)*M_used flops per launch (lower triangle incl. diagonal, FMA=2), M_used = this rank's SNPs of the slab",
+                             "kernel_clock": "grm_sm_mhz = median over CTAs of clock64 cycles / globaltimer ns, measured by the kernel itself; grm_sms = "
+                                             "distinct SMs its CTAs ran on"},
                 "cpu_baseline": cb,
-                "kernel_ms": {k: float(np.mean([q[k] for q in kern])) for k in ("stats_ms", "grm_ms", "finalize_ms")},
-                "smartpca_core_s": pipeline_s,
-                "eig_ms": {k: eig_t.get(k) for k in ("tridiag_ms", "bisect_ms", "vectors_ms")} if eig_t else None}
+                "kernel_ms": {k: float(allk[0, :, j].mean()) for j, k in enumerate(keys[:5])},
+                "per_rank_per_step": per_rank,
+                "nonkernel_ms_per_step": nonkernel_ms,
+                "parity_checked": parity,
+                "smartpca_e2e_s": e2e_run["seconds"] if e2e_run else None,
+                "smartpca_e2e": e2e_run}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        ctx.set_comm(None)
         dist.destroy_process_group()
 
 
@@ -322,7 +402,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"], help="N>1 exchange step: library peer-memory kernel | NCCL all-reduce")
+    ap.add_argument("--no-full-run", action="store_true", help="skip the complete 50,000 x 600,000 smartpca run (smartpca_e2e_s)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -37,7 +37,9 @@ class Timings(C.Structure):
     _fields_ = [("gather_ms", C.c_float), ("stats_ms", C.c_float), ("grm_ms", C.c_float), ("finalize_ms", C.c_float),
                 ("tridiag_ms", C.c_float), ("bisect_ms", C.c_float), ("vectors_ms", C.c_float),
                 ("grm_launches", C.c_int), ("nsplit", C.c_int), ("eig_method", C.c_int), ("chfsi_iters", C.c_int),
-                ("chfsi_matvecs", C.c_int)]
+                ("chfsi_matvecs", C.c_int), ("grm_sm_mhz", C.c_float), ("grm_cta_min_ms", C.c_float), ("grm_cta_max_ms", C.c_float),
+                ("grm_span_ms", C.c_float), ("grm_sms", C.c_int), ("chfsi_converged", C.c_int), ("chfsi_resid", C.c_float),
+                ("exchange_wait_ms", C.c_float)]
 
 
 ALLGATHER_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)

@@ -61,6 +61,8 @@ void eb_destroy(eb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  peer_release(c);                                           // close the IPC mappings of the peers' buffers
+  for (auto& reg : c->peer) { for (void* p : reg.graveyard) cudaFree(p); reg.graveyard.clear(); }
   for (int i = 0; i < 12; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -186,9 +188,35 @@ static int fetch_snp_outputs(eb_ctx* c, int* c0, int* c1, int* nmiss, uint8_t* u
   if (xfancy) EB_CUDA(cudaMemcpyAsync(xfancy, c->xfancy_d.p, sizeof(double) * m, cudaMemcpyDeviceToHost, c->stream));
   long long nu = 0;
   EB_CUDA(cudaMemcpyAsync(&nu, c->nused_d.p, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  // the GRM kernel's self-measurement (4 words per CTA)
+  std::vector<unsigned long long> prof;
+  if (c->grm_grid > 0 && c->grmprof_d.p) {
+    prof.resize((size_t)4 * c->grm_grid);
+    EB_CUDA(cudaMemcpyAsync(prof.data(), c->grmprof_d.p, sizeof(unsigned long long) * prof.size(), cudaMemcpyDeviceToHost, c->stream));
+  }
   EB_CUDA(cudaStreamSynchronize(c->stream));
   c->nused = nu;
   if (nused) *nused = nu;
+  if (!prof.empty()) {
+    const int g = c->grm_grid;
+    std::vector<double> mhz(g);
+    std::vector<unsigned long long> sms(g);
+    unsigned long long tmin = ~0ull, tmax = 0;
+    double dmin = 1e300, dmax = 0.0;
+    for (int b = 0; b < g; b++) {
+      const unsigned long long t0 = prof[4 * b + 1], t1 = prof[4 * b + 2];
+      const double ns = (double)(t1 - t0);
+      sms[b] = prof[4 * b];
+      mhz[b] = ns > 0 ? (double)prof[4 * b + 3] / ns * 1e3 : 0.0;
+      tmin = std::min(tmin, t0); tmax = std::max(tmax, t1);
+      dmin = std::min(dmin, ns); dmax = std::max(dmax, ns);
+    }
+    std::sort(mhz.begin(), mhz.end()); std::sort(sms.begin(), sms.end());
+    c->tm.grm_sm_mhz = (float)mhz[g / 2];
+    c->tm.grm_sms = (int)(std::unique(sms.begin(), sms.end()) - sms.begin());
+    c->tm.grm_cta_min_ms = (float)(dmin * 1e-6); c->tm.grm_cta_max_ms = (float)(dmax * 1e-6);
+    c->tm.grm_span_ms = (float)((double)(tmax - tmin) * 1e-6);
+  }
   return 0;
 }
 
@@ -260,32 +288,26 @@ static int grm_pass(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* n
   if ((rc = need_rows(c, "eb_grm"))) return rc;
   if (!opts) { set_error("eb_grm: opts is NULL"); return EB_ERR_ARG; }
   if (c->nrows < 2) { set_error("eb_grm: need at least 2 rows"); return EB_ERR_ARG; }
-  const bool dbg = getenv("EB_DEBUG") != nullptr;
-  const double t0 = now_s();
   if ((rc = stage_opts(c, opts))) return rc;
+  // SNPs sharded over several GPUs: receive buffers sized / mapped for this matrix (host collectives only when it grew: normally
+  // once, here, before any kernel of the pass is in flight), then everything below is stream-ordered
+  if (peer && (rc = peer_grm_setup(c, grm_nsplit_for(c, true)))) return rc;
   EB_CUDA(cudaEventRecord(c->ev[0], c->stream));
   if ((rc = launch_stats(c, opts))) return rc;
   EB_CUDA(cudaEventRecord(c->ev[1], c->stream));
-  if ((rc = grm_accumulate(c, !peer))) return rc;
-  // publish / map the peer buffers (first pass only does real work; see peer_grm_prepare)
-  if (peer && (rc = peer_grm_prepare(c))) return rc;
-  const double t1 = now_s();
+  if (peer && (rc = peer_grm_wait_idle(c))) return rc;           // nobody still pulls the previous pass out of my receive buffer
+  if ((rc = grm_accumulate(c, !peer, peer))) return rc;
+  if (peer && (rc = peer_grm_finalize(c, c->nsplit))) return rc; // signal / wait / reduce / signal / wait / gather (peer.cu)
   if ((rc = fetch_snp_outputs(c, c0, c1, nmiss, used, xmean, xfancy, nused_out))) return rc;
-  const double t2 = now_s();
   cudaEventElapsedTime(&c->tm.stats_ms, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->tm.grm_ms, c->ev[2], c->ev[3]);
+  c->tm.exchange_wait_ms = 0.f;
   if (peer) {
-    // exchange step: split-K plane sum + mirror fused with the cross-GPU reduction over peer memory (peer.cu)
-    if ((rc = peer_grm_finalize(c))) return rc;
-    if (dbg) fprintf(stderr, "[grm_pass] launch + peer mapping %.3f s, kernels + per-SNP outputs %.3f s, peer finalize %.3f s\n",
-                     t1 - t0, t2 - t1, now_s() - t2);
-    std::vector<long long> all(c->comm.world);
-    long long mine = c->nused;
-    if ((rc = peer_allgather_host(c, &mine, all.data(), sizeof(long long)))) return rc;
     long long tot = 0;
-    for (long long v : all) tot += v;
+    if ((rc = peer_grm_collect(c, &tot))) return rc;
     c->nused_total = tot;
     if (nused_out) *nused_out = tot;
+    cudaEventElapsedTime(&c->tm.exchange_wait_ms, c->ev[5], c->ev[6]);   // spinning for the slowest rank's tiles
   } else {
     c->nused_total = c->nused;
   }
@@ -440,11 +462,8 @@ static eb_ctx* dropin_ctx() {
 }
 void eigvecs(double* mat, double* evals, double* evecs, int n) {
   eb_ctx* c = dropin_ctx();
-  // all n vectors up to n = 8192 (1.3 s there; the remaining callers are 2 x 2 ellipses, smartpca.c:1751, and mkorth); beyond that the
-  // leading block only -- what smartpca.c:4087,4298 consume -- and zeros for the rest
-  const int nvec = n <= 8192 ? n : 40;
-  if (n > 8192) memset(evecs, 0, sizeof(double) * (size_t)n * n);
-  if (eb_eigvecs(c, mat, evals, evecs, n, nvec) != 0) { fprintf(stderr, "eigvecs (libeigb200): %s\n", eb_last_error()); exit(1); }
+  // the reference fills all n vectors (eigsubs.c:39-55): so does this, at any n (full-basis path of the one-stage solver)
+  if (eb_eigvecs(c, mat, evals, evecs, n, n) != 0) { fprintf(stderr, "eigvecs (libeigb200): %s\n", eb_last_error()); exit(1); }
 }
 void eigvals(double* mat, double* evals, int n) {
   eb_ctx* c = dropin_ctx();

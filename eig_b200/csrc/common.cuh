@@ -52,7 +52,16 @@ struct DevBuf {
 
 // multi-GPU exchange over peer memory (peer.cu)
 constexpr int EB_MAX_WORLD = 16;
-enum { PEER_SLOT_PARTIAL = 0, PEER_SLOT_XTX = 1, PEER_SLOT_A = 2, PEER_SLOT_B = 3, PEER_SLOT_C = 4, PEER_SLOT_T = 5, PEER_SLOTS = 6 };
+enum { PEER_SLOT_PARTIAL = 0, PEER_SLOT_FLAGS = 1, PEER_SLOT_A = 2, PEER_SLOT_B = 3, PEER_SLOT_C = 4, PEER_SLOT_T = 5, PEER_SLOTS = 6 };
+// Where grm_syrk_kernel stores a finished 128 x 128 tile when the SNPs are sharded over `world` GPUs: lower-triangle tile t
+// belongs to rank t % world, and every rank stores its partial tile STRAIGHT INTO THE OWNER'S receive buffer over NVLink
+// (slot [t / world][rank * nsplit + chunk], a dense 128 x 128 block), so the reduce-scatter traffic overlaps the DMMA work
+// of the tiles that follow.  world <= 1: tiles go to the local split-K planes.
+struct GrmPush {
+  double* recv[EB_MAX_WORLD];
+  int world, rank;
+};
+constexpr int GRM_FLAG_WORDS = 256;   // per rank: flags[3][16], mailbox[2][16][2], error word (unsigned long long each)
 struct PeerRecord {             // what a rank publishes about one exported allocation
   unsigned char handle[64];     // cudaIpcMemHandle_t
   uint64_t ptr, bytes;          // device address in the owner's process, size of the allocation
@@ -87,6 +96,7 @@ struct eb_ctx {
   // working matrix: selected rows only, SNP-major, pitch = npad/4 bytes, pad genotypes = 3
   eb::DevBuf<uint8_t> work;
   eb::DevBuf<int> xindex_d;
+  eb::DevBuf<int> wsrc_d;         // per 32-bit word of the working row: raw byte offset of a 16-individual run | -1 mixed | -2 pad
   std::vector<int> xindex_h;
   int nrows = 0;        // selected individuals
   int npad = 0;         // nrows rounded up to TILE
@@ -106,6 +116,9 @@ struct eb_ctx {
   eb::DevBuf<double> xtx;         // npad * npad, full symmetric, UNNORMALISED
   eb::DevBuf<double> trace_d;     // 1
   eb::DevBuf<int> workctr_d;      // 1
+  eb::DevBuf<unsigned long long> grmprof_d;   // [num_sms][4]: smid, globaltimer at CTA start / end, SM cycles (grm_syrk_kernel)
+  int grm_grid = 0;               // CTAs of the last grm_syrk_kernel launch
+  int dt_slots = 0;               // resident CTAs per SM of the DMMA tile kernels on this context's device (eig2_gemm.cu)
   eb::DevBuf<double> dense_blk;   // dense path staging: [1024][npad]
   bool dense_open = false;
   int nsplit = 1;
@@ -131,6 +144,11 @@ struct eb_ctx {
   bool has_comm = false;
   eb::PeerRegion peer[eb::PEER_SLOTS];
   eb::DevBuf<double> peer_scratch;
+  eb::DevBuf<double> grm_recv;              // sharded GRM: [owned tiles][world * nsplit][128 x 128] partial tiles pushed by every rank
+  eb::DevBuf<unsigned long long> grm_flags; // sharded GRM: device-side flags / mailbox written by the peers (GRM_FLAG_WORDS)
+  unsigned long long grm_epoch = 0;         // one per sharded GRM pass (all ranks in lockstep)
+  size_t grm_recv_need = 0;                 // doubles the current geometry needs in grm_recv
+  int grm_geom_npad = 0, grm_geom_nsplit = 0;   // geometry the peers have agreed on
   eb::DevBuf<double> fpG, fpB, fpS;   // fastmode buffers that take part in an exchange (persistent: peers map them)
 
   eb_timings tm = {};
@@ -147,7 +165,8 @@ int launch_indiv_counts(eb_ctx* c, const uint8_t* keep_d, int* out_d);
 int launch_synth(eb_ctx* c, uint8_t* dst, int64_t nsnp, int64_t pitch, int numindivs, uint64_t seed, int64_t s0,
                  double missing, int npops, double delta);
 // grm_kernel.cu
-int grm_accumulate(eb_ctx* c, bool finalize_local = true);   // work+table -> split-K planes [-> xtx (full symmetric, unnormalised)]
+int grm_accumulate(eb_ctx* c, bool finalize_local = true, bool push = false);   // work+table -> split-K planes [-> xtx] | -> owners' receive buffers
+int grm_nsplit_for(const eb_ctx* c, bool sharded);
 int grm_trace(eb_ctx* c);        // recompute trace_d / y from xtx
 int microbench_fp64(eb_ctx* c, double* dmma, double* dfma);
 // eig_kernels.cu
@@ -161,7 +180,8 @@ int launch_gemm(eb_ctx* c, bool a_km, bool b_kn, const double* A, int64_t lda, c
 int grm_dense_finalize(eb_ctx* c);
 // eig2_kernels.cu
 int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, double* e);
-int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* theta_h, double* vec_d, int* iters_out, int* matvecs_out);
+int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* theta_h, double* vec_d, int* iters_out, int* matvecs_out,
+              double lo0 = 0.0);
 // fpca_kernels.cu
 int fpca_run(eb_ctx* c, int fancynorm, int altnormstyle, size_t K, size_t L, size_t I, long seed, double* eval, double* evec);
 int project_run(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, double* fxvecs, double* fxscal);
@@ -171,8 +191,11 @@ int lsqproj_run(eb_ctx* c, const int* indiv, int nlist, const double* ffvecs, co
 // peer.cu
 int peer_allgather_host(eb_ctx* c, const void* src, void* dst, int64_t bytes);
 int peer_exchange(eb_ctx* c, int slot, void* local, size_t bytes, int aux);
-int peer_grm_prepare(eb_ctx* c);
-int peer_grm_finalize(eb_ctx* c);
+int peer_grm_setup(eb_ctx* c, int nsplit);      // collective only when the matrix outgrew the mapped buffers
+int peer_grm_push_args(eb_ctx* c, GrmPush* out);
+int peer_grm_wait_idle(eb_ctx* c);              // stream-ordered: peers finished pulling the previous pass
+int peer_grm_finalize(eb_ctx* c, int nsplit);   // stream-ordered: signal, wait, reduce, signal, wait, gather, signal
+int peer_grm_collect(eb_ctx* c, long long* nused_total);   // after a stream sync: mailbox + error word
 int peer_allreduce(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64_t count);
 int peer_allreduce_any(eb_ctx* c, double* buf, int64_t count);
 int peer_sum_host(eb_ctx* c, double* v, int count);

@@ -306,11 +306,9 @@ static int launch_gemm_t(eb_ctx* c, const double* A, int64_t lda, const double* 
   else { if ((rc = make_f64_tensormap(&ma, A, M, K, lda, DT_LD_K, DT_M))) return rc; }
   if (B_KN) { if ((rc = make_f64_tensormap(&mb, B, K, N, ldb, DT_LD_N, DT_KC))) return rc; }
   else { if ((rc = make_f64_tensormap(&mb, B, N, K, ldb, DT_LD_K, DT_N))) return rc; }
-  static bool attr = false;
-  if (!attr) {
-    EB_CUDA(cudaFuncSetAttribute(dt_gemm_kernel<A_KM, B_KN>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
-    attr = true;
-  }
+  // function attributes are per device: set on every launch (microseconds) rather than behind a process-wide flag, so that several
+  // contexts on different GPUs of one process (eb_local_comm) all get the shared-memory opt-in
+  EB_CUDA(cudaFuncSetAttribute(dt_gemm_kernel<A_KM, B_KN>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM));
   const int mt = (M + DT_M - 1) / DT_M, nt = (N + DT_N - 1) / DT_N;
   const int grid = std::min(mt * nt, 2 * c->num_sms);
   dt_gemm_kernel<A_KM, B_KN><<<grid, DT_THREADS, DT_SMEM, c->stream>>>(ma, mb, C, ldc, M, N, K, mt, nt, alpha, beta);
@@ -330,17 +328,17 @@ int launch_gemm(eb_ctx* c, bool a_km, bool b_kn, const double* A, int64_t lda, c
 }
 
 int dt_resident_ctas(eb_ctx* c) {
-  static int cached = 0;
-  if (!cached) {
+  // per context (= per device): the opt-in and the occupancy belong to the device the context lives on
+  if (!c->dt_slots) {
     cudaFuncSetAttribute(sym_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM);
     cudaFuncSetAttribute(syr2k_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM);
     int a = 0, b = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, sym_skinny_kernel, DT_THREADS, DT_SMEM);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, syr2k_lower_kernel, DT_THREADS, DT_SMEM);
-    cached = std::max(1, std::min(a, b));
-    if (const char* e = getenv("EB_DBG_SLOTS")) cached = std::max(1, atoi(e));
+    c->dt_slots = std::max(1, std::min(a, b));
+    if (const char* e = getenv("EB_DBG_SLOTS")) c->dt_slots = std::max(1, atoi(e));
   }
-  return cached * c->num_sms;
+  return c->dt_slots * c->num_sms;
 }
 
 // Wpart[ks][64][ldw] (ks < ksplit_out) = A[:, t0*128:] * Bt^T restricted to row tiles >= t0.  A: n x n (lda), Bt: 64 x n (ldb).

@@ -831,13 +831,10 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
   EB_CUDA(cudaMemsetAsync(w.VZ, 0, sizeof(double) * 128 * ldv, st));
   EB_CUDA(cudaMemsetAsync(w.prog, 0, sizeof(int) * ((size_t)n + 16), st));
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    EB_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    EB_CUDA(cudaFuncSetAttribute(left_mult_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-    EB_CUDA(cudaFuncSetAttribute(sbr_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 8));
-    attr_set = true;
-  }
+  // per device, not per process: set on every call (several contexts on different GPUs may live in one process)
+  EB_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  EB_CUDA(cudaFuncSetAttribute(left_mult_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+  EB_CUDA(cudaFuncSetAttribute(sbr_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 12288 * 8));
 
   const bool dbg_sync = getenv("EB_DBG_SYNC") != nullptr, dbg_ref_w = getenv("EB_DBG_REF_W") != nullptr,
              dbg_ref_syr2k = getenv("EB_DBG_REF_SYR2K") != nullptr;
@@ -936,7 +933,11 @@ __global__ void __launch_bounds__(256) defl_coef_kernel(const double* __restrict
 
 // Leading nvec eigenpairs of the symmetric matrix A (n x n, lda; lower triangle + complete diagonal tiles valid, preserved).
 // theta_h[nvec] (unscaled), vec_d: device [nvec][n] unit vectors.
-int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* theta_h, double* vec_d, int* iters_out, int* matvecs_out) {
+// lo0: lower end of the spectrum when the caller knows it (the bisection's smallest eigenvalue), else 0 (a GRM is positive
+// semi-definite); the damped interval of the filter starts there, so an indefinite matrix needs it.
+// c->tm.chfsi_converged / chfsi_resid tell the caller whether the strict tolerance was reached (see eb_timings).
+int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* theta_h, double* vec_d, int* iters_out, int* matvecs_out,
+              double lo0) {
   cudaStream_t st = c->stream;
   int rc;
   const int64_t ld = ((int64_t)n + 7) & ~7ll;
@@ -960,13 +961,9 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
   EB_CUDA(cudaMemsetAsync(err_d, 0, sizeof(int), st));
   for (int i = 0; i < 5; i++) EB_CUDA(cudaMemsetAsync(Y[i], 0, sizeof(double) * 64 * ld, st));
   constexpr int SM64x2 = 2 * 64 * 65 * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EB_CUDA(cudaFuncSetAttribute(left_mult_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-    EB_CUDA(cudaFuncSetAttribute(jacobi64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM64x2));
-    EB_CUDA(cudaFuncSetAttribute(cholinv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM64x2));
-    attr_set = true;
-  }
+  EB_CUDA(cudaFuncSetAttribute(left_mult_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+  EB_CUDA(cudaFuncSetAttribute(jacobi64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM64x2));
+  EB_CUDA(cudaFuncSetAttribute(cholinv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM64x2));
   const dim3 cgrid((n + 255) / 256, 64);
   const int lm_grid = (n + 63) / 64;
   int nmat = 0;
@@ -1018,9 +1015,9 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
   const bool debug = getenv("EB_DEBUG") != nullptr;
   const double tol = std::max(2e-14, 6e-16 * sqrt((double)n));
   double prev_worst = 1e300, prev2_worst = 1e300, last_worst = 1e300;
-  double lo = 0.0;
+  double lo = std::min(0.0, lo0);
   int outer = 0;
-  bool converged = false;
+  bool converged = false, strict = false;
   const int maxouter = 80;
   for (outer = 0; outer < maxouter; outer++) {
     // Rayleigh-Ritz (on A itself)
@@ -1054,7 +1051,7 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
                        th[std::max(nvec - 1, 0)], th[63], worst / anorm);
     // converged: residual at the rounding floor of an n-term FP64 mat-vec, or stagnating just above it
     last_worst = anorm > 0.0 ? worst / anorm : 0.0;
-    if (!(anorm > 0.0) || nlock >= nvec || worst <= tol * anorm) { converged = true; break; }
+    if (!(anorm > 0.0) || nlock >= nvec || worst <= tol * anorm) { converged = true; strict = true; break; }
     if (worst <= 1e-11 * anorm && worst > 0.5 * prev_worst && prev_worst > 0.5 * prev2_worst) { converged = true; break; }
     prev2_worst = prev_worst; prev_worst = worst;
     // Chebyshev filter damping [lo, cut]
@@ -1111,6 +1108,10 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
     // resolves (the .evec prints 4-6 decimals, ridoutlier compares z-scores with 6.0); otherwise let the caller fall back
     if (!(last_worst <= 1e-9)) { set_error("chfsi_top: no convergence after %d outer iterations (worst residual / |A| = %.2e)", maxouter, last_worst); return EB_ERR_NUMERIC; }
   }
+  // the caller is told when the pairs were accepted above the strict tolerance (stagnation just above the rounding floor, or the
+  // relaxed 1e-9 bar after maxouter filters): eb_timings.chfsi_converged = 0 and chfsi_resid = worst |A v - theta v| / |A|
+  c->tm.chfsi_converged = strict ? 1 : 0;
+  c->tm.chfsi_resid = (float)last_worst;
   normalize_rows_kernel<<<nvec, 256, 0, st>>>(V, ld, n);
   EB_CHECK_LAUNCH(c);
   EB_CUDA(cudaMemcpy2DAsync(vec_d, sizeof(double) * n, V, sizeof(double) * ld, sizeof(double) * n, nvec, cudaMemcpyDeviceToDevice, st));

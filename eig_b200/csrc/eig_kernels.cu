@@ -786,6 +786,8 @@ static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, do
   int rc;
   c->tm.tridiag_ms = c->tm.bisect_ms = c->tm.vectors_ms = 0.f;
   c->tm.chfsi_iters = c->tm.chfsi_matvecs = 0;
+  c->tm.chfsi_converged = 1; c->tm.chfsi_resid = 0.f;
+  double lo0 = 0.0;                 // smallest eigenvalue (unscaled) when the spectrum was computed: the filter's lower end
   if ((rc = c->lambda_d.ensure(n))) return rc;
   if (lambda_h) {
     const int64_t lda = ((int64_t)n + 15) & ~15ll;
@@ -805,13 +807,14 @@ static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, do
     EB_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&c->tm.tridiag_ms, c->ev[5], c->ev[6]);
     cudaEventElapsedTime(&c->tm.bisect_ms, c->ev[6], c->ev[7]);
+    if (scale > 0.0) lo0 = lambda_h[n - 1] / scale;
   }
   if (nvec > 0) {
     if ((rc = c->zvec_d.ensure((size_t)nvec * n))) return rc;
     c->zvec_ld = n;
     std::vector<double> th(nvec);
     EB_CUDA(cudaEventRecord(c->ev[8], st));
-    if ((rc = chfsi_top(c, A_d, lda_in, n, nvec, th.data(), c->zvec_d.p, &c->tm.chfsi_iters, &c->tm.chfsi_matvecs))) {
+    if ((rc = chfsi_top(c, A_d, lda_in, n, nvec, th.data(), c->zvec_d.p, &c->tm.chfsi_iters, &c->tm.chfsi_matvecs, lo0))) {
       if (rc != EB_ERR_NUMERIC) return rc;
       // the subspace iteration gave up: take the vectors from the one-stage path (slower, direct)
       const int keep = c->opt_eig_method;

@@ -467,6 +467,9 @@ int fpca_run(eb_ctx* c, int fancynorm, int altnormstyle, size_t K, size_t L, siz
   return 0;
 }
 
+__global__ void mm_table_kernel(int64_t nsnp, int64_t mpad, int nrows, const int* __restrict__ c0, const int* __restrict__ nmiss,
+                                const double* __restrict__ xfancy, const uint8_t* __restrict__ used, double* __restrict__ table);
+
 // ------------------------------------------------------------------------------------------ projections (smartpca.c:1485-1525)
 int project_run(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, double* fxvecs, double* fxscal) {
   int rc;
@@ -481,8 +484,11 @@ int project_run(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, dou
   for (int j = 0; j < numeigs; j++) for (int i = 0; i < n; i++) T[(size_t)j * npad + i] = 10.0 * evecs[(size_t)j * n + i];
   EB_CUDA(cudaMemcpyAsync(Ft.p, T.data(), sizeof(double) * T.size(), cudaMemcpyHostToDevice, c->stream));
   EB_CUDA(cudaMemsetAsync(FFt.p, 0, sizeof(double) * (size_t)numeigs * mpad, c->stream));
-  // ffvecs[j][s] = sum_k fvecs[j][k] x_ks with the GRM decode table (dropped / ignored SNPs contribute zero columns)
-  if ((rc = launch_packed_gemm<MODE_XA>(c, c->table_d.p, Ft.p, npad, FFt.p, mpad, numeigs, 1.0))) return rc;
+  // ffvecs[j][s] = sum_k fvecs[j][k] x_ks with the columns of getcolxf (smartpca.c:1487, 3564-3597): (g - ymean) * yfancy WITHOUT the
+  // SNP weight (weightname only enters the GRM columns, smartpca.c:1178-1180); dropped / ignored SNPs contribute zero columns
+  mm_table_kernel<<<(unsigned)((mpad + 255) / 256), 256, 0, c->stream>>>(m, mpad, n, c->c0_d.p, c->nmiss_d.p, c->xfancy_d.p, c->used_d.p, ftab.p);
+  EB_CHECK_LAUNCH(c);
+  if ((rc = launch_packed_gemm<MODE_XA>(c, ftab.p, Ft.p, npad, FFt.p, mpad, numeigs, 1.0))) return rc;
   fix_table_kernel<<<(unsigned)((mpad + 255) / 256), 256, 0, c->stream>>>(m, mpad, c->xmean_d.p, c->xfancy_d.p, c->used_d.p, ftab.p);
   EB_CHECK_LAUNCH(c);
   if ((rc = launch_packed_gemm<MODE_XTB>(c, ftab.p, FFt.p, mpad, FXt.p, npad, numeigs, 1.0))) return rc;

@@ -15,6 +15,7 @@
 //     its 8 / 4 fragment elements of SNP k, extracts the 2-bit codes with shifts and reads the FP64 value
 //     from the per-SNP 4-entry table in shared memory (bank-conflict free: 4 SNPs x 4 entries x 8 B = 128 B).
 //   * Algorithmic work: N*(N+1)*M flops ~ N^2 M; bytes are negligible (2 bits / element) => FP64-pipe bound.
+#include <string.h>
 #include <algorithm>
 #include "common.cuh"
 
@@ -96,7 +97,8 @@ __device__ __forceinline__ void tri_decode(int t, int& ti, int& tj) {
 template <int WARPS_M, int WARPS_N, int TB, int UB, int UNROLL>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, 1)
 grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restrict__ table, double* __restrict__ partial,
-                   int npad, int nrows, int ntiles_tri, int nsplit, int nkblocks) {
+                   int npad, int nrows, int ntiles_tri, int nsplit, int nkblocks, unsigned long long* __restrict__ prof,
+                   const __grid_constant__ GrmPush push) {
   static_assert(WARPS_M * TB * 8 == TILE && WARPS_N * UB * 8 == TILE, "tile must be 128 x 128");
   static_assert(TB == 4 || TB == 8, "A segment is 8 or 16 bytes");
   static_assert(UB == 4 || UB == 8, "B segment is 8 or 16 bytes");
@@ -113,6 +115,13 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restri
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  // self-measurement (4 words per CTA): which SM, wall-clock span (globaltimer, ns) and SM cycles of this CTA, so that the host
+  // can report the EFFECTIVE SM clock of the launch and the number of SMs it really ran on (bench.py: roofline.kernel_clock)
+  unsigned long long prof_t0 = 0, prof_c0 = 0;
+  if (threadIdx.x == 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_t0));
+    prof_c0 = (unsigned long long)clock64();
+  }
 
   const int nitems = ntiles_tri * nsplit;
   // producer cursor (meaningful in thread 0 only)
@@ -129,6 +138,7 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restri
         tri_decode(t, p_ti, p_tj);
         p_kb = (int)(((long long)nkblocks * chunk) / nsplit);
         p_kb1 = (int)(((long long)nkblocks * (chunk + 1)) / nsplit);
+        if (p_kb >= p_kb1) { p_item += gridDim.x; continue; }      // empty chunk (fewer SNP blocks than chunks): nothing to load
         p_open = true;
       }
       mbar_wait(empty + p_stage, p_phase ^ 1);
@@ -243,17 +253,35 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restri
       if (threadIdx.x == 0) ahead--;
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
-    double* out = partial + (size_t)chunk * npad * npad;
+    // single GPU: the tile goes to its place in split-K plane `chunk`.  SNPs sharded over several GPUs: it goes straight into the
+    // receive buffer of the rank that owns tile t_ (plain stores over NVLink when that is a peer), see GrmPush
+    double* out;
+    size_t ldo;
+    if (push.world > 1) {
+      const int owner = t_ % push.world;
+      out = push.recv[owner] + ((size_t)(t_ / push.world) * (size_t)(push.world * nsplit) + (size_t)(push.rank * nsplit + chunk)) * (TILE * TILE);
+      ldo = TILE;
+    } else {
+      out = partial + (size_t)chunk * npad * npad + (size_t)ti * TILE * npad + (size_t)tj * TILE;
+      ldo = (size_t)npad;
+    }
 #pragma unroll
     for (int t = 0; t < TB; t++) {
-      const size_t row = (size_t)ti * TILE + wm * (TB * 8) + t * 8 + g;
+      const size_t row = (size_t)(wm * (TB * 8) + t * 8 + g);
 #pragma unroll
       for (int u = 0; u < UB; u++) {
-        const size_t col = (size_t)tj * TILE + wn * (UB * 8) + u * 8 + q * 2;
-        *reinterpret_cast<double2*>(out + row * npad + col) = make_double2(acc[t][u][0], acc[t][u][1]);
+        const size_t col = (size_t)(wn * (UB * 8) + u * 8 + q * 2);
+        *reinterpret_cast<double2*>(out + row * ldo + col) = make_double2(acc[t][u][0], acc[t][u][1]);
         acc[t][u][0] = acc[t][u][1] = 0.0;
       }
     }
+  }
+  if (threadIdx.x == 0 && prof) {
+    unsigned long long t1; unsigned int smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned long long c1 = (unsigned long long)clock64();
+    prof[4 * blockIdx.x + 0] = smid; prof[4 * blockIdx.x + 1] = prof_t0; prof[4 * blockIdx.x + 2] = t1; prof[4 * blockIdx.x + 3] = c1 - prof_c0;
   }
 }
 
@@ -334,40 +362,55 @@ int grm_trace(eb_ctx* c) {
   return 0;
 }
 
-int grm_accumulate(eb_ctx* c, bool finalize_local) {
+// split-K factor: enough (tile, chunk) items for ~40 waves over the SMs.  Sharded: a function of the matrix size alone, so that every
+// rank derives the same receive-buffer geometry without talking (a chunk may then be empty on a rank with few SNP blocks: it
+// stores a zero tile).  Single GPU: also bounded by the number of SNP blocks and by free memory.
+int grm_nsplit_for(const eb_ctx* c, bool sharded) {
   const int T = c->npad / TILE;
   const int ntri = T * (T + 1) / 2;
-  const int nkb = (int)(c->mpad / KT);
-  // enough (tile, chunk) items for ~40 waves over the SMs, bounded by the number of SNP blocks and by memory
   int nsplit = (40 * c->num_sms + ntri - 1) / ntri;
+  if (sharded) return std::max(1, std::min(nsplit, 16));
+  const int nkb = (int)(c->mpad / KT);
   nsplit = std::max(1, std::min(nsplit, std::min(nkb, 32)));
   size_t freeb = 0, totalb = 0;
   cudaMemGetInfo(&freeb, &totalb);
   const size_t plane = (size_t)c->npad * c->npad * sizeof(double);
   const size_t have = c->partial.n * sizeof(double);
   while (nsplit > 1 && (size_t)nsplit * plane > have + freeb / 2) nsplit--;
+  return nsplit;
+}
+
+int grm_accumulate(eb_ctx* c, bool finalize_local, bool push_mode) {
+  const int T = c->npad / TILE;
+  const int ntri = T * (T + 1) / 2;
+  const int nkb = (int)(c->mpad / KT);
+  const int nsplit = push_mode ? c->grm_geom_nsplit : grm_nsplit_for(c, false);
   c->nsplit = nsplit;
   int rc;
-  if ((rc = c->partial.ensure((size_t)nsplit * c->npad * c->npad))) return rc;
+  GrmPush push;
+  memset(&push, 0, sizeof(push));
+  push.world = 1;
+  if (push_mode) { if ((rc = peer_grm_push_args(c, &push))) return rc; }
+  else if ((rc = c->partial.ensure((size_t)nsplit * c->npad * c->npad))) return rc;
   if ((rc = c->xtx.ensure((size_t)c->npad * c->npad))) return rc;
   if ((rc = c->trace_d.ensure(1))) return rc;
 
   CUtensorMap map;
   if ((rc = make_work_tensormap(c, &map))) return rc;
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("EB_GRM_VARIANT");          // 1 = non-pipelined decode (debug / A-B only)
-    variant = e ? atoi(e) : 2;
-    EB_CUDA(cudaFuncSetAttribute(grm_syrk_kernel<2, 4, 8, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRM_SMEM));
-    EB_CUDA(cudaFuncSetAttribute(grm_syrk_kernel<2, 4, 8, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRM_SMEM));
-  }
+  const char* ev = getenv("EB_GRM_VARIANT");            // 1 = non-pipelined decode (debug / A-B only)
+  const int variant = ev ? atoi(ev) : 2;
+  // per device (not per process): several contexts on different GPUs may live in one process (eb_local_comm)
+  EB_CUDA(cudaFuncSetAttribute(grm_syrk_kernel<2, 4, 8, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRM_SMEM));
+  EB_CUDA(cudaFuncSetAttribute(grm_syrk_kernel<2, 4, 8, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GRM_SMEM));
   const int nitems = ntri * nsplit;
   const int grid = std::min(nitems, c->num_sms);
+  if ((rc = c->grmprof_d.ensure((size_t)4 * c->num_sms))) return rc;
+  c->grm_grid = grid;
   EB_CUDA(cudaEventRecord(c->ev[2], c->stream));
   if (variant == 1)
-    grm_syrk_kernel<2, 4, 8, 4, 1><<<grid, GRM_THREADS, GRM_SMEM, c->stream>>>(map, c->table_d.p, c->partial.p, c->npad, c->nrows, ntri, nsplit, nkb);
+    grm_syrk_kernel<2, 4, 8, 4, 1><<<grid, GRM_THREADS, GRM_SMEM, c->stream>>>(map, c->table_d.p, c->partial.p, c->npad, c->nrows, ntri, nsplit, nkb, c->grmprof_d.p, push);
   else
-    grm_syrk_kernel<2, 4, 8, 4, 2><<<grid, GRM_THREADS, GRM_SMEM, c->stream>>>(map, c->table_d.p, c->partial.p, c->npad, c->nrows, ntri, nsplit, nkb);
+    grm_syrk_kernel<2, 4, 8, 4, 2><<<grid, GRM_THREADS, GRM_SMEM, c->stream>>>(map, c->table_d.p, c->partial.p, c->npad, c->nrows, ntri, nsplit, nkb, c->grmprof_d.p, push);
   EB_CHECK_LAUNCH(c);
   EB_CUDA(cudaEventRecord(c->ev[3], c->stream));
   c->tm.grm_launches = 2;

@@ -6,6 +6,8 @@
 //                          (smartpca.c:1131-1144) and the 4-entry decode table the GRM kernel consumes
 //   indiv_counts_kernel  : numvalidgtallind (admutils.c:1075-1097)
 //   synth_kernel         : synthetic Hardy-Weinberg generator (eig_b200/synth.py is the host twin)
+#include <algorithm>
+#include <vector>
 #include "common.cuh"
 
 namespace eb {
@@ -52,11 +54,66 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const uint8_t* __restr
   }
 }
 
+// Fast path of the same gather for the working matrix of the PCA rows: the host has classified every 32-bit word of the working
+// row once per row selection (wsrc[w] >= 0: the word is the 4 consecutive raw bytes starting at wsrc[w], i.e. 16 consecutive
+// individuals that start on a byte boundary -- all individuals, or the long runs between a few removed outliers; -1: mixed word,
+// gathered genotype by genotype; -2: pad word).  One thread builds one 16-byte vector (64 individuals) per SNP row.
+__global__ void __launch_bounds__(256) gather_rows_fast_kernel(const uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t nsnp, int64_t mpad,
+                                                               const int* __restrict__ xindex, int nrows, const int4* __restrict__ wsrc,
+                                                               uint8_t* __restrict__ work, int64_t wpitch) {
+  const int vecs = (int)(wpitch >> 4);
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= vecs) return;
+  const int4 src4 = wsrc[v];
+  const int src[4] = {src4.x, src4.y, src4.z, src4.w};
+  const bool rows_aligned = ((raw_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(raw) & 3) == 0);
+  for (int64_t s = blockIdx.y; s < mpad; s += gridDim.y) {
+    uint32_t out[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    if (s < nsnp) {
+      const uint8_t* row = raw + s * raw_pitch;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (src[k] >= 0) {
+          const uint8_t* p = row + src[k];
+          if (rows_aligned && (src[k] & 3) == 0) out[k] = __ldg(reinterpret_cast<const uint32_t*>(p));
+          else out[k] = (uint32_t)__ldg(p) | ((uint32_t)__ldg(p + 1) << 8) | ((uint32_t)__ldg(p + 2) << 16) | ((uint32_t)__ldg(p + 3) << 24);
+        } else if (src[k] == -1) {
+          uint32_t o = 0;
+          const int j0 = (v * 4 + k) * 16;
+#pragma unroll
+          for (int t = 0; t < 16; t++) {
+            uint32_t code = 3;
+            const int j = j0 + t;
+            if (j < nrows) { const int q = xindex[j]; code = (__ldg(row + (q >> 2)) >> ((3 - (q & 3)) << 1)) & 3u; }
+            o |= code << (((t >> 2) << 3) + ((3 - (t & 3)) << 1));
+          }
+          out[k] = o;
+        }
+      }
+    }
+    reinterpret_cast<uint4*>(work + s * wpitch)[v] = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+
 int launch_gather(eb_ctx* c) {
-  const int wordsPerRow = (int)(c->wpitch >> 2);
-  dim3 block(256), grid((wordsPerRow + 255) / 256, (unsigned)std::min<int64_t>(c->mpad, 65535));
-  gather_rows_kernel<<<grid, block, 0, c->stream>>>(c->raw, c->raw_pitch, c->nsnp, c->mpad, c->xindex_d.p, c->nrows,
-                                                    c->work.p, c->wpitch);
+  // classify the words of the working row (host, once per row selection)
+  const int words = (int)(c->wpitch >> 2);
+  std::vector<int> wsrc((size_t)words);
+  for (int w = 0; w < words; w++) {
+    const int j0 = w * 16;
+    if (j0 >= c->nrows) { wsrc[w] = -2; continue; }
+    bool run = j0 + 16 <= c->nrows && (c->xindex_h[j0] & 3) == 0;
+    for (int t = 1; run && t < 16; t++) run = c->xindex_h[j0 + t] == c->xindex_h[j0] + t;
+    wsrc[w] = run ? (c->xindex_h[j0] >> 2) : -1;
+  }
+  int rc;
+  if ((rc = c->wsrc_d.ensure((size_t)words))) return rc;
+  EB_CUDA(cudaMemcpyAsync(c->wsrc_d.p, wsrc.data(), sizeof(int) * words, cudaMemcpyHostToDevice, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));      // wsrc is a local
+  const int vecs = (int)(c->wpitch >> 4);
+  dim3 block(256), grid((vecs + 255) / 256, (unsigned)std::min<int64_t>(c->mpad, 65535));
+  gather_rows_fast_kernel<<<grid, block, 0, c->stream>>>(c->raw, c->raw_pitch, c->nsnp, c->mpad, c->xindex_d.p, c->nrows,
+                                                         reinterpret_cast<const int4*>(c->wsrc_d.p), c->work.p, c->wpitch);
   EB_CHECK_LAUNCH(c);
   return 0;
 }

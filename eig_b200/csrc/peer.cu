@@ -107,6 +107,19 @@ int peer_exchange(eb_ctx* c, int slot, void* local, size_t bytes, int aux) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ sharded GRM exchange
+// grm_syrk_kernel's epilogue has already stored every partial 128 x 128 tile into its owner's receive buffer (GrmPush,
+// common.cuh): the reduce-scatter traffic rode under the DMMA work.  What is left, all of it STREAM-ORDERED (no host
+// barrier, no host collective in the steady state):
+//   signal(0)  my pushes are complete (kernel boundary + fence.sys) -> flag in every peer, with my used-SNP count
+//   wait(0)    every rank's pushes have landed in my receive buffer
+//   reduce     owned tiles: sum of the world * nsplit slots in a fixed order (bit-identical everywhere and from run to run)
+//              -> slot 0 in place (for the peers to pull) and my XTX (+ mirror image: symit2)
+//   signal(1) / wait(1), gather: pull every other owner's reduced tiles from its slot 0 into my XTX (+ mirror)
+//   signal(2)  done pulling; the NEXT pass waits for everybody's (2) before its first tile store (peer_grm_wait_idle)
+// Flags are monotone epochs in a small exported buffer; a wait gives up after GRM_WAIT_TIMEOUT_NS and raises the error
+// word instead of wedging the GPU when a peer died.
+
 __device__ __forceinline__ void tri_decode32(int t, int& ti, int& tj) {
   int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
   while ((r + 1) * (r + 2) / 2 <= t) r++;
@@ -114,125 +127,231 @@ __device__ __forceinline__ void tri_decode32(int t, int& ti, int& tj) {
   ti = r; tj = t - r * (r + 1) / 2;
 }
 
-struct GrmPeerArgs {
-  const double* part[EB_MAX_WORLD];
-  int nsplit[EB_MAX_WORLD];
+constexpr unsigned long long GRM_WAIT_TIMEOUT_NS = 60ull * 1000000000ull;
+constexpr int FLAG_ERR = 3 * 16 + 2 * 16 * 2;     // word index of the error flag
+
+struct GrmFlagArgs {
+  unsigned long long* flags[EB_MAX_WORLD];         // every rank's flag buffer (mine included)
   int world, rank;
 };
 
-// Phase 1 (reduce): CTA b of rank r finalises lower-triangle 32x32 block r + b*world: sum of every rank's planes in a fixed
-// order, stored (with its mirror image) into the LOCAL xtx and, for the peers to pull, into the local plane 0 in place.
-__global__ void __launch_bounds__(256) grm_peer_reduce_kernel(const GrmPeerArgs a, int npad, int nblocks, double* __restrict__ own_plane0,
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// one warp: lane w tells rank w "phase `phase` of epoch `epoch` is complete on rank a.rank" (optionally with a payload word)
+__global__ void __launch_bounds__(32) grm_signal_kernel(const GrmFlagArgs a, int phase, unsigned long long epoch,
+                                                        const unsigned long long* __restrict__ payload) {
+  const int w = threadIdx.x;
+  if (w >= a.world) return;
+  __threadfence_system();
+  if (payload) {
+    a.flags[w][3 * 16 + ((epoch & 1) * 16 + a.rank) * 2] = payload[0];
+    __threadfence_system();
+  }
+  st_release_sys(a.flags[w] + phase * 16 + a.rank, epoch);
+}
+
+// one warp: lane w waits until rank w has signalled `phase` of `epoch` into MY flag buffer
+__global__ void __launch_bounds__(32) grm_wait_kernel(unsigned long long* mine, int world, int phase, unsigned long long epoch) {
+  const int w = threadIdx.x;
+  if (w < world) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(mine + phase * 16 + w) < epoch) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > GRM_WAIT_TIMEOUT_NS) { mine[FLAG_ERR] = 1ull + (unsigned long long)w; break; }
+      __nanosleep(200);
+    }
+  }
+  __syncwarp();
+  __threadfence_system();
+}
+
+// 32 x 32 block (bi, bj) of a dense 128 x 128 lower-triangle tile (ti, tj) -> xtx and its mirror image.  `diag`: the tile lies on the
+// diagonal, so blocks above its own diagonal are skipped and the diagonal blocks are mirrored inside themselves.
+__device__ __forceinline__ void emit_block(double (&tile)[32][33], int ti, int tj, int bi, int bj, bool diag, int npad, double* __restrict__ xtx) {
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const bool dblk = diag && bi == bj;
+  const size_t r0 = (size_t)ti * TILE + bi * 32, c0 = (size_t)tj * TILE + bj * 32;
+  for (int r = ty; r < 32; r += 8) {
+    double v = tile[r][tx];
+    if (dblk && tx > r) v = tile[tx][r];
+    xtx[(r0 + r) * npad + c0 + tx] = v;
+    if (!dblk) xtx[(c0 + r) * npad + r0 + tx] = tile[tx][r];
+  }
+}
+
+struct GrmReduceArgs {
+  const double* recv[EB_MAX_WORLD];     // every rank's receive buffer (mine at [rank])
+  int world, rank;
+};
+
+// CTA b of rank r finalises its b-th owned tile (global tile r + b * world)
+__global__ void __launch_bounds__(256) grm_push_reduce_kernel(double* __restrict__ recv, int world, int rank, int nslots, int ntri, int npad,
                                                               double* __restrict__ xtx) {
   __shared__ double tile[32][33];
-  const int gb = a.rank + blockIdx.x * a.world;
-  if (gb >= nblocks) return;
-  int bi, bj; tri_decode32(gb, bi, bj);
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  const size_t plane = (size_t)npad * npad;
-  for (int r = ty; r < 32; r += 8) {
-    const size_t idx = (size_t)(bi * 32 + r) * npad + bj * 32 + tx;
-    double v = 0.0;
-    for (int w = 0; w < a.world; w++) {
-      const double* p = a.part[w] + idx;
-      for (int s = 0; s < a.nsplit[w]; s++) v += p[s * plane];
-    }
-    own_plane0[idx] = v;                                     // complete block (the pad / upper part of diagonal blocks included)
-    if (bi == bj && tx > r) v = 0.0;
-    tile[r][tx] = v;
-  }
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    double v = tile[r][tx];
-    if (bi == bj && tx > r) v = tile[tx][r];
-    xtx[(size_t)(bi * 32 + r) * npad + bj * 32 + tx] = v;
-    if (bi != bj) xtx[(size_t)(bj * 32 + r) * npad + bi * 32 + tx] = tile[tx][r];
-  }
-}
-
-// Phase 2 (gather): every block owned by another rank is pulled from that rank's plane 0 into the local xtx (+ mirror).
-// CTA b handles the b-th block that is NOT owned by this rank.
-__global__ void __launch_bounds__(256) grm_peer_gather_kernel(const GrmPeerArgs a, int npad, int nblocks, double* __restrict__ xtx) {
-  __shared__ double tile[32][33];
-  // b-th non-owned block: blocks are owned round-robin, so within each group of `world` consecutive blocks exactly one is ours
-  const int grp = blockIdx.x / (a.world - 1), k = blockIdx.x % (a.world - 1);
-  const int gb = grp * a.world + (k < a.rank ? k : k + 1);
-  if (gb >= nblocks) return;
-  const int owner = gb % a.world;
-  int bi, bj; tri_decode32(gb, bi, bj);
+  const int t = rank + blockIdx.x * world;
+  if (t >= ntri) return;
+  int ti, tj; tri_decode32(t, ti, tj);
+  const bool diag = ti == tj;
+  double* slot0 = recv + (size_t)blockIdx.x * nslots * (TILE * TILE);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const double* src = a.part[owner];
-  for (int r = ty; r < 32; r += 8) {
-    double v = src[(size_t)(bi * 32 + r) * npad + bj * 32 + tx];
-    if (bi == bj && tx > r) v = 0.0;
-    tile[r][tx] = v;
-  }
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    double v = tile[r][tx];
-    if (bi == bj && tx > r) v = tile[tx][r];
-    xtx[(size_t)(bi * 32 + r) * npad + bj * 32 + tx] = v;
-    if (bi != bj) xtx[(size_t)(bj * 32 + r) * npad + bi * 32 + tx] = tile[tx][r];
-  }
+  for (int bi = 0; bi < 4; bi++)
+    for (int bj = 0; bj < 4; bj++) {
+      if (diag && bj > bi) continue;
+      __syncthreads();
+      for (int r = ty; r < 32; r += 8) {
+        const size_t idx = (size_t)(bi * 32 + r) * TILE + bj * 32 + tx;
+        double v = 0.0;
+        for (int s = 0; s < nslots; s++) v += slot0[(size_t)s * (TILE * TILE) + idx];
+        slot0[idx] = v;
+        tile[r][tx] = v;
+      }
+      __syncthreads();
+      emit_block(tile, ti, tj, bi, bj, diag, npad, xtx);
+    }
 }
 
-// Reduce the per-rank split-K planes (left by grm_syrk_kernel in c->partial) across ranks into every rank's c->xtx.
-// Pull only: a rank maps nothing but the peers' plane buffers (one cudaIpcOpenMemHandle per peer; measured 0.1-0.2 s per
-// 20 GB buffer the first time, and the open waits for running kernels, so it cannot be hidden behind the SYRK kernel).
-// peer_grm_prepare: publish / map the plane buffers (later passes reuse the mappings).
-// peer_grm_finalize: barrier, reduce kernel (owned blocks), barrier, gather kernel (everybody else's blocks), barrier.
-int peer_grm_prepare(eb_ctx* c) {
-  const int W = c->comm.world;
-  int rc;
-  if (c->npad > (1 << 24)) { set_error("multi-GPU GRM: matrix too large for the exchange record"); return EB_ERR_ARG; }
-  if ((rc = peer_exchange(c, PEER_SLOT_PARTIAL, c->partial.p, c->partial.n * sizeof(double), c->nsplit + 64 * c->npad))) return rc;
-  const size_t plane = (size_t)c->npad * c->npad;
-  for (int r = 0; r < W; r++) {
-    const PeerRecord& pr = c->peer[PEER_SLOT_PARTIAL].rec[r];
-    const int ns = pr.aux & 63, np = pr.aux >> 6;
-    if (np != c->npad || ns < 1 || (size_t)ns * plane * sizeof(double) > pr.bytes) {
-      set_error("multi-GPU GRM: rank %d has a different matrix size (npad %d vs %d): every shard must use the same rows", r, np, c->npad);
-      return EB_ERR_STATE;
+// CTA b pulls the b-th tile NOT owned by this rank from its owner's slot 0
+__global__ void __launch_bounds__(256) grm_push_gather_kernel(const GrmReduceArgs a, int nslots, int ntri, int npad, double* __restrict__ xtx) {
+  __shared__ double tile[32][33];
+  const int grp = blockIdx.x / (a.world - 1), k = blockIdx.x % (a.world - 1);
+  const int t = grp * a.world + (k < a.rank ? k : k + 1);
+  if (t >= ntri) return;
+  const int owner = t % a.world;
+  int ti, tj; tri_decode32(t, ti, tj);
+  const bool diag = ti == tj;
+  const double* src = a.recv[owner] + (size_t)(t / a.world) * nslots * (TILE * TILE);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int bi = 0; bi < 4; bi++)
+    for (int bj = 0; bj < 4; bj++) {
+      if (diag && bj > bi) continue;
+      __syncthreads();
+      for (int r = ty; r < 32; r += 8) tile[r][tx] = src[(size_t)(bi * 32 + r) * TILE + bj * 32 + tx];
+      __syncthreads();
+      emit_block(tile, ti, tj, bi, bj, diag, npad, xtx);
     }
+}
+
+static int flag_args(eb_ctx* c, GrmFlagArgs* a) {
+  memset(a, 0, sizeof(*a));
+  a->world = c->comm.world; a->rank = c->comm.rank;
+  for (int r = 0; r < a->world; r++) {
+    a->flags[r] = (unsigned long long*)c->peer[PEER_SLOT_FLAGS].mapped[r];
+    if (!a->flags[r]) { set_error("sharded GRM: flag buffer of rank %d is not mapped (peer_grm_setup not called)", r); return EB_ERR_STATE; }
   }
   return 0;
 }
 
-int peer_grm_finalize(eb_ctx* c) {
+// Make sure every rank's receive buffer is large enough for the current matrix and mapped everywhere.  The geometry is a function
+// of (npad, world, nsplit) alone and every rank calls with the same rows, so ranks agree without talking; the host collectives
+// below run only when the matrix outgrew what is mapped (normally once, before the first kernel of the run is launched, so
+// cudaIpcOpenMemHandle does not wait behind a running SYRK).
+int peer_grm_setup(eb_ctx* c, int nsplit) {
   const int W = c->comm.world;
+  const int T = c->npad / TILE, ntri = T * (T + 1) / 2;
+  const size_t owned_max = (size_t)(ntri + W - 1) / W;
+  const size_t need = owned_max * (size_t)(W * nsplit) * (TILE * TILE);
+  c->grm_geom_npad = c->npad; c->grm_geom_nsplit = nsplit; c->grm_recv_need = need;
+  const bool mapped = (int)c->peer[PEER_SLOT_PARTIAL].mapped.size() == W && (int)c->peer[PEER_SLOT_FLAGS].mapped.size() == W;
+  if (mapped && c->grm_recv.p && c->grm_recv.n >= need) return 0;
   int rc;
-  GrmPeerArgs a;
-  memset(&a, 0, sizeof(a));
-  a.world = W; a.rank = c->comm.rank;
-  for (int r = 0; r < W; r++) {
-    a.part[r] = (const double*)c->peer[PEER_SLOT_PARTIAL].mapped[r];
-    a.nsplit[r] = c->peer[PEER_SLOT_PARTIAL].rec[r].aux & 63;
-    if (!a.part[r]) { set_error("peer_grm_finalize: planes of rank %d are not mapped (peer_grm_prepare not called)", r); return EB_ERR_STATE; }
-  }
-  const bool dbg = getenv("EB_DEBUG") != nullptr;
-  const auto tnow = [] { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
-  const double tq0 = tnow();
-  EB_CUDA(cudaStreamSynchronize(c->stream));     // my planes are complete ...
-  if ((rc = comm_barrier(c))) return rc;         // ... and so are everybody else's
-  const double tq1 = tnow();
-  const int T32 = c->npad / 32, nblocks = T32 * (T32 + 1) / 2;
-  const int mine = (nblocks - a.rank + W - 1) / W;
-  EB_CUDA(cudaEventRecord(c->ev[3], c->stream));
-  if (mine > 0) {
-    grm_peer_reduce_kernel<<<mine, 256, 0, c->stream>>>(a, c->npad, nblocks, c->partial.p, c->xtx.p);
-    EB_CHECK_LAUNCH(c);
-  }
-  EB_CUDA(cudaStreamSynchronize(c->stream));     // my reduced blocks are in my plane 0 ...
-  if ((rc = comm_barrier(c))) return rc;         // ... and everybody else's in theirs
-  const int groups = (nblocks + W - 1) / W;
-  if (W > 1 && groups > 0) {
-    grm_peer_gather_kernel<<<groups * (W - 1), 256, 0, c->stream>>>(a, c->npad, nblocks, c->xtx.p);
-    EB_CHECK_LAUNCH(c);
-  }
-  EB_CUDA(cudaEventRecord(c->ev[4], c->stream));
+  // grow only (outlier passes shrink the matrix and keep the mapping)
   EB_CUDA(cudaStreamSynchronize(c->stream));
-  if (dbg) fprintf(stderr, "[peer_grm_finalize] rank %d: wait for all ranks %.3f s, reduce + gather %.3f s\n", a.rank, tq1 - tq0, tnow() - tq1);
-  return peer_bury(c);                            // barrier: nobody overwrites its planes while a peer still pulls from them
+  if ((rc = c->grm_recv.ensure(need))) return rc;
+  if (!c->grm_flags.p) {
+    if ((rc = c->grm_flags.ensure(GRM_FLAG_WORDS))) return rc;
+    EB_CUDA(cudaMemsetAsync(c->grm_flags.p, 0, sizeof(unsigned long long) * GRM_FLAG_WORDS, c->stream));
+    EB_CUDA(cudaStreamSynchronize(c->stream));
+    c->grm_epoch = 0;
+  }
+  if ((rc = peer_exchange(c, PEER_SLOT_PARTIAL, c->grm_recv.p, c->grm_recv.n * sizeof(double), 0))) return rc;
+  if ((rc = peer_exchange(c, PEER_SLOT_FLAGS, c->grm_flags.p, c->grm_flags.n * sizeof(unsigned long long), 0))) return rc;
+  for (int r = 0; r < W; r++)
+    if (c->peer[PEER_SLOT_PARTIAL].rec[r].bytes < need * sizeof(double)) {
+      set_error("sharded GRM: rank %d holds a smaller receive buffer (%llu < %llu bytes): every shard must use the same rows", r,
+                (unsigned long long)c->peer[PEER_SLOT_PARTIAL].rec[r].bytes, (unsigned long long)(need * sizeof(double)));
+      return EB_ERR_STATE;
+    }
+  return peer_bury(c);       // barrier: everybody has re-mapped, superseded allocations can go
+}
+
+int peer_grm_push_args(eb_ctx* c, GrmPush* out) {
+  memset(out, 0, sizeof(*out));
+  out->world = c->comm.world; out->rank = c->comm.rank;
+  for (int r = 0; r < out->world; r++) {
+    out->recv[r] = (double*)c->peer[PEER_SLOT_PARTIAL].mapped[r];
+    if (!out->recv[r]) { set_error("sharded GRM: receive buffer of rank %d is not mapped (peer_grm_setup not called)", r); return EB_ERR_STATE; }
+  }
+  return 0;
+}
+
+int peer_grm_wait_idle(eb_ctx* c) {
+  if (c->grm_epoch == 0) return 0;
+  grm_wait_kernel<<<1, 32, 0, c->stream>>>(c->grm_flags.p, c->comm.world, 2, c->grm_epoch);
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
+int peer_grm_finalize(eb_ctx* c, int nsplit) {
+  const int W = c->comm.world, me = c->comm.rank;
+  int rc;
+  GrmFlagArgs fa;
+  if ((rc = flag_args(c, &fa))) return rc;
+  GrmReduceArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.world = W; ra.rank = me;
+  for (int r = 0; r < W; r++) ra.recv[r] = (const double*)c->peer[PEER_SLOT_PARTIAL].mapped[r];
+  const unsigned long long ep = ++c->grm_epoch;
+  const int T = c->npad / TILE, ntri = T * (T + 1) / 2, nslots = W * nsplit;
+  grm_signal_kernel<<<1, 32, 0, c->stream>>>(fa, 0, ep, reinterpret_cast<const unsigned long long*>(c->nused_d.p));   // payload: my used-SNP count
+  EB_CHECK_LAUNCH(c);
+  EB_CUDA(cudaEventRecord(c->ev[5], c->stream));
+  grm_wait_kernel<<<1, 32, 0, c->stream>>>(c->grm_flags.p, W, 0, ep);
+  EB_CHECK_LAUNCH(c);
+  EB_CUDA(cudaEventRecord(c->ev[6], c->stream));
+  const int mine = (ntri - me + W - 1) / W;
+  if (mine > 0) {
+    grm_push_reduce_kernel<<<mine, 256, 0, c->stream>>>(c->grm_recv.p, W, me, nslots, ntri, c->npad, c->xtx.p);
+    EB_CHECK_LAUNCH(c);
+  }
+  grm_signal_kernel<<<1, 32, 0, c->stream>>>(fa, 1, ep, nullptr);
+  EB_CHECK_LAUNCH(c);
+  grm_wait_kernel<<<1, 32, 0, c->stream>>>(c->grm_flags.p, W, 1, ep);
+  EB_CHECK_LAUNCH(c);
+  const int groups = (ntri + W - 1) / W;
+  if (W > 1 && groups > 0) {
+    grm_push_gather_kernel<<<groups * (W - 1), 256, 0, c->stream>>>(ra, nslots, ntri, c->npad, c->xtx.p);
+    EB_CHECK_LAUNCH(c);
+  }
+  grm_signal_kernel<<<1, 32, 0, c->stream>>>(fa, 2, ep, nullptr);
+  EB_CHECK_LAUNCH(c);
+  EB_CUDA(cudaEventRecord(c->ev[4], c->stream));
+  return 0;
+}
+
+// after the stream has been synchronised: total of the ranks' used-SNP counts (mailbox of this epoch) and the error word
+int peer_grm_collect(eb_ctx* c, long long* nused_total) {
+  unsigned long long h[GRM_FLAG_WORDS];
+  EB_CUDA(cudaMemcpyAsync(h, c->grm_flags.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  EB_CUDA(cudaStreamSynchronize(c->stream));
+  if (h[FLAG_ERR]) {
+    set_error("sharded GRM: rank %d never signalled (waited %d s): a peer died or the ranks do not run the same passes", (int)h[FLAG_ERR] - 1,
+              (int)(GRM_WAIT_TIMEOUT_NS / 1000000000ull));
+    EB_CUDA(cudaMemsetAsync(c->grm_flags.p + FLAG_ERR, 0, sizeof(unsigned long long), c->stream));
+    return EB_ERR_STATE;
+  }
+  long long tot = 0;
+  for (int r = 0; r < c->comm.world; r++) tot += (long long)h[3 * 16 + ((c->grm_epoch & 1) * 16 + r) * 2];
+  if (nused_total) *nused_total = tot;
+  return 0;
 }
 
 struct AllreduceArgs {
@@ -313,15 +432,16 @@ extern "C" int eb_set_comm(eb_ctx* c, const eb_comm* comm) {
   if (!c) return EB_ERR_ARG;
   cudaSetDevice(c->device);
   eb::peer_release(c);
-  c->partial.defer = c->fpG.defer = c->fpB.defer = c->fpS.defer = c->peer_scratch.defer = nullptr;
+  c->grm_recv.defer = c->fpG.defer = c->fpB.defer = c->fpS.defer = c->peer_scratch.defer = nullptr;
   for (auto& reg : c->peer) { for (void* p : reg.graveyard) cudaFree(p); reg.graveyard.clear(); }
+  c->grm_epoch = 0; c->grm_recv.release(); c->grm_flags.release();
   if (!comm || comm->world <= 1) { c->has_comm = false; memset(&c->comm, 0, sizeof(c->comm)); c->comm.world = 1; return 0; }
   if (comm->world > eb::EB_MAX_WORLD || comm->rank < 0 || comm->rank >= comm->world || !comm->allgather_host || !comm->barrier) {
     eb::set_error("eb_set_comm: need 0 <= rank < world <= %d and both callbacks", eb::EB_MAX_WORLD);
     return EB_ERR_ARG;
   }
   c->comm = *comm; c->has_comm = true;
-  c->partial.defer = &c->peer[eb::PEER_SLOT_PARTIAL].graveyard;
+  c->grm_recv.defer = &c->peer[eb::PEER_SLOT_PARTIAL].graveyard;
   c->fpG.defer = &c->peer[eb::PEER_SLOT_A].graveyard;
   c->fpB.defer = &c->peer[eb::PEER_SLOT_B].graveyard;
   c->fpS.defer = &c->peer[eb::PEER_SLOT_C].graveyard;

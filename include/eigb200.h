@@ -166,8 +166,8 @@ int eb_eig (eb_ctx *, int nvec, double *lambda, double *evecs);
 int eb_eigvecs (eb_ctx *, const double *mat, double *evals, double *evecs, int n, int nvec);
 
 /* drop-in symbols under the reference's own names (include/eigsubs.h:6-7): same contract as eigsubs.c:21,39 (mat
- * preserved, eigenvalues descending, row i of evecs = vector i, fatal on failure).  eigvecs fills all n vectors for
- * n <= 8192 and the leading 40 (zeros elsewhere) beyond -- every reference caller reads at most numeigs of them. */
+ * preserved, eigenvalues descending, row i of evecs = vector i, fatal on failure).  eigvecs fills all n vectors at any n
+ * (callers that only need the leading ones should use eb_eigvecs with nvec, which is much cheaper at large n). */
 void eigvecs (double *mat, double *evals, double *evecs, int n);
 void eigvals (double *mat, double *evals, int n);
 
@@ -262,6 +262,14 @@ typedef struct {
   int grm_launches; int nsplit;
   int eig_method;               /* 1 = one-stage Householder, 2 = two-stage (band) + subspace iteration */
   int chfsi_iters, chfsi_matvecs;
+  /* self-measurement of the last grm_syrk_kernel launch (every CTA records %smid, %globaltimer and clock64):
+   * effective SM clock = median over CTAs of cycles / wall time; distinct SMs the CTAs ran on; shortest / longest CTA;
+   * first CTA start -> last CTA end.  Explains a slow launch without a profiler: clock, SM count or a late CTA. */
+  float grm_sm_mhz, grm_cta_min_ms, grm_cta_max_ms, grm_span_ms;
+  int grm_sms;
+  int chfsi_converged;          /* 1: every requested pair reached the strict residual tolerance; 0: accepted at the relaxed one */
+  float chfsi_resid;            /* largest relative residual |A v - theta v| / |A| among the returned pairs */
+  float exchange_wait_ms;       /* multi-GPU: host time spent waiting for the other ranks before the exchange kernels */
 } eb_timings;
 int eb_get_timings (eb_ctx *, eb_timings * t);
 /* FP64 DMMA / DFMA issue-rate microbenchmarks (TFLOP/s) used as roofline cross-checks */

@@ -177,6 +177,24 @@ def ref_grm(packed, numindivs, xindex=None, fancynorm=1, altnormstyle=1, minalle
     return r
 
 
+def ref_grm_loop(packed, numindivs, nthreads=None, tri=None):
+    """Timing arm: the reference's per-SNP loop (smartpca.c:1116-1221) into a packed lower triangle, without symit2 / trace.
+    Returns used flags, the loop's wall seconds and the triangle (reused between calls when given)."""
+    nsnp, rlen = packed.shape; n = numindivs
+    xi = np.arange(n, dtype=np.int32)
+    if tri is None:
+        tri = np.zeros(n * (n + 1) // 2)
+    r = dict(c0=np.empty(nsnp, np.int32), c1=np.empty(nsnp, np.int32), nmiss=np.empty(nsnp, np.int32),
+             used=np.empty(nsnp, np.uint8), xmean=np.zeros(nsnp), xfancy=np.zeros(nsnp))
+    secs = np.zeros(2)
+    ref().refh_grm_loop(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen), C.c_int(n), xi.ctypes.data_as(C.c_void_p),
+                        C.c_int(n), C.c_int(1), C.c_int(1), C.c_int(1), C.c_int(9999999), C.c_int(nthreads or os.cpu_count()),
+                        *[r[k].ctypes.data_as(C.c_void_p) for k in ("c0", "c1", "nmiss", "used", "xmean", "xfancy")],
+                        tri.ctypes.data_as(C.c_void_p), secs.ctypes.data_as(C.c_void_p))
+    r["secs_loop"], r["secs_lookup"], r["tri"] = float(secs[0]), float(secs[1]), tri
+    return r
+
+
 def ref_eigvecs(mat):
     mat = np.ascontiguousarray(mat, np.float64).copy(); n = mat.shape[0]
     ev = np.empty(n); vec = np.empty((n, n))

@@ -46,10 +46,10 @@ static void hbuild (const unsigned char *packed, long nsnp, long rl, int nind)
  * c0,c1 (=n0,n1; -1 if all missing), nmiss (-1 if all missing), used (1 if it entered XTX), xmean,xfancy.
  * XTX_out: nrows*nrows row-major after symit2, NOT yet divided by y; *y_out = trace/(nrows-1).
  * secs[0] = wall seconds of the per-SNP loop (stats+pack+lookup), secs[1] = seconds inside domult_increment_lookup. */
-int refh_grm (const unsigned char *packed, long nsnp, long rl, int nind, const int *xindex_in, int nrows,
+static int grm_core (const unsigned char *packed, long nsnp, long rl, int nind, const int *xindex_in, int nrows,
               int fancy, int altnorm, int minac, int maxmiss, const double *weights, int nthreads,
               int *c0, int *c1, int *nmiss, unsigned char *used, double *xmean_o, double *xfancy_o,
-              double *XTX_out, double *y_out, double *secs)
+              double *XTX_out, double *y_out, double *secs, int finish)
 {
   long i; int n0, n1, t, tt, xblock = 0, blocksize = 20; uint32_t thread_ct; double y, t0, t1, tl = 0;
   pthread_t threads[MAX_THREADS];
@@ -83,11 +83,34 @@ int refh_grm (const unsigned char *packed, long nsnp, long rl, int nind, const i
   }
   if (xblock > 0) { t1 = now_s (); domult_increment_lookup (threads, thread_ct, XTX_out, tblock, bc, bm, xblock, nrows, lut); tl += now_s () - t1; }
   if (secs) { secs[0] = now_s () - t0; secs[1] = tl; }
-  symit2 (XTX_out, nrows);
-  y = trace (XTX_out, nrows) / (double) (nrows - 1);
-  *y_out = y;
+  if (finish) {
+    symit2 (XTX_out, nrows);
+    y = trace (XTX_out, nrows) / (double) (nrows - 1);
+    *y_out = y;
+  }
   free (rawcol); free (bc); free (bm); free (tblock); free (lut); free (xidx); hfree ();
   return 0;
+}
+
+int refh_grm (const unsigned char *packed, long nsnp, long rl, int nind, const int *xindex_in, int nrows,
+              int fancy, int altnorm, int minac, int maxmiss, const double *weights, int nthreads,
+              int *c0, int *c1, int *nmiss, unsigned char *used, double *xmean_o, double *xfancy_o,
+              double *XTX_out, double *y_out, double *secs)
+{
+  return grm_core (packed, nsnp, rl, nind, xindex_in, nrows, fancy, altnorm, minac, maxmiss, weights, nthreads, c0, c1, nmiss, used,
+                   xmean_o, xfancy_o, XTX_out, y_out, secs, 1);
+}
+
+/* the per-SNP loop alone (smartpca.c:1116-1221) into a caller-provided packed lower triangle of nrows(nrows+1)/2 doubles:
+ * the timing arm for matrices whose square (symit2 needs nrows^2 doubles, once per pass) is not worth allocating for a
+ * bounded SNP sample -- bench.py's CPU baseline at 50,000 individuals. */
+int refh_grm_loop (const unsigned char *packed, long nsnp, long rl, int nind, const int *xindex_in, int nrows,
+                   int fancy, int altnorm, int minac, int maxmiss, int nthreads,
+                   int *c0, int *c1, int *nmiss, unsigned char *used, double *xmean_o, double *xfancy_o, double *XTX_tri, double *secs)
+{
+  double y;
+  return grm_core (packed, nsnp, rl, nind, xindex_in, nrows, fancy, altnorm, minac, maxmiss, NULL, nthreads, c0, c1, nmiss, used,
+                   xmean_o, xfancy_o, XTX_tri, &y, secs, 0);
 }
 
 void refh_eigvecs (double *mat, double *evals, double *evecs, int n) { eigvecs (mat, evals, evecs, n); }

@@ -62,3 +62,26 @@ def test_evec_coords_requires_pca_rows_in_list(ctx):
     ctx.grm(); lam, vec = ctx.eig(2)
     with pytest.raises(EigB200Error):
         ctx.evec_coords(vec, indiv=np.arange(1, 40, dtype=np.int32))
+
+
+def test_evec_coords_with_snp_weights(ctx):
+    """weightname (smartpca.c:1178-1180) scales the GRM columns only: the SNP loadings come from getcolxf (smartpca.c:1487,
+    3564-3597), which never applies cupt->weight, so the .evec coordinates of a weighted run must match the reference's
+    sequence fed with the same eigenvectors."""
+    nsnp, nind, k = 3000, 150, 4
+    P = _case(5, nsnp, nind, 0.1)
+    w = 0.25 + 1.5 * np.random.default_rng(2).random(nsnp)
+    ctx.upload_packed(P, nind); ctx.set_rows(None)
+    r = ctx.grm(snp_weight=w)
+    r0 = ctx.grm()
+    assert np.abs(r["y"] - r0["y"]) > 1e-3 * r0["y"]          # the weights did change the GRM
+    r = ctx.grm(snp_weight=w)
+    lam, vec = ctx.eig(k)
+    co, es, ok = ctx.evec_coords(vec)
+    pc, pes, pok, ff, sc = ob.port_evec_coords(P, nind, r["used"], r["xmean"], r["xfancy"], vec)
+    assert np.array_equal(ok, pok)
+    assert np.abs(co - pc).max() <= 1e-9 * max(1.0, np.abs(pc).max())
+    if ob.ref() is not None:
+        rr = ob.ref_evec_coords(P, nind, r["used"], r["xmean"], r["xfancy"], vec)
+        assert np.abs(co - rr["coords"]).max() <= EVEC_ATOL * 1e-3
+        assert np.abs(es - rr["eigscale"]).max() <= 1e-9 * np.abs(rr["eigscale"]).max()
