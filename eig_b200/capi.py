@@ -59,6 +59,7 @@ EXPORTS = [
     "eb_microbench_fp64", "eb_set_option", "eb_debug_tridiag", "eb_lsqproj", "eb_evec_coords", "eb_pop_counts", "eb_hash_ids", "eb_packed_file_header", "eb_upload_packed_file",
     "eb_download_packed", "eb_write_eval", "eb_write_evec", "eb_write_grm", "eb_grm_dense_begin", "eb_grm_dense_add", "eb_grm_dense_end", "eigvecs", "eigvals",
     "eb_set_comm", "eb_peer_allreduce_test", "eb_snp_used_count", "eb_shrink_coords", "eb_debug_gemm", "eb_local_comm_create", "eb_local_comm_get", "eb_local_comm_destroy", "eb_numgtz", "eb_tw_stats", "eb_tw_tail",
+    "eb_setgval_packed", "eb_unsetgval", "kjg_fpca", "eb_write_grm_bin",
 ]
 
 _lib = None
@@ -152,6 +153,11 @@ def write_evec(path, lam, ids, groups, coords, hiprec=False):
 def write_grm(path, xtx, numsnps):
     xtx = np.ascontiguousarray(xtx, np.float64)
     _chk(lib().eb_write_grm(path.encode(), _p(xtx), C.c_int(xtx.shape[0]), C.c_int(numsnps)))
+
+
+def write_grm_bin(prefix, xtx, numsnps):
+    xtx = np.ascontiguousarray(xtx, np.float64)
+    _chk(lib().eb_write_grm_bin(prefix.encode(), _p(xtx), C.c_int(xtx.shape[0]), C.c_int(numsnps)))
 
 
 class LocalComm:

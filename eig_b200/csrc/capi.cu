@@ -60,6 +60,7 @@ eb_ctx* eb_create(int device) {
 void eb_destroy(eb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->has_comm && c->grm_epoch > 0 && c->grm_flags.p) peer_grm_wait_idle(c);   // peers may still pull from my receive buffer
   cudaStreamSynchronize(c->stream);
   peer_release(c);                                           // close the IPC mappings of the peers' buffers
   for (auto& reg : c->peer) { for (void* p : reg.graveyard) cudaFree(p); reg.graveyard.clear(); }
@@ -468,6 +469,39 @@ void eigvecs(double* mat, double* evals, double* evecs, int n) {
 void eigvals(double* mat, double* evals, int n) {
   eb_ctx* c = dropin_ctx();
   if (eb_eigvecs(c, mat, evals, nullptr, n, 0) != 0) { fprintf(stderr, "eigvals (libeigb200): %s\n", eb_last_error()); exit(1); }
+}
+
+// ---- fastmode under the reference's own name: kjg_fpca (include/kjg_fpca.h:22, kjg_fpca.c:24) after the hand-over that
+// setgval (gval.c:31-87) does through file statics.  setgval itself takes the reference's SNP / Indiv structs, so it lives in the
+// few lines of glue a maintainer compiles against the reference headers (integration/eb_gval.c: setgval -> eb_setgval_packed);
+// everything behind it is plain pointers.  Failure = message on stderr + exit(1), as kjg_fpca.c:26-29 does.
+static struct { bool set; int fancynorm, altnormstyle; long seed; } g_gval = {false, 1, 1, 0};
+int eb_setgval_packed(const uint8_t* const* snp_pbuff, int64_t ncols, int64_t rlen, int numindivs, const int* xindex, int nrows,
+                      int fancynorm, int altnormstyle, long seed, uint8_t* mono_out) {
+  eb_ctx* c = dropin_ctx();
+  int rc;
+  for (int i = 1; i < nrows; i++)
+    if (xindex[i] < xindex[i - 1]) { fprintf(stderr, "xindex not sorted\n"); exit(1); }     // gval.c:49-54
+  if ((rc = eb_upload_packed_rows(c, snp_pbuff, ncols, rlen, numindivs))) return rc;
+  if ((rc = eb_set_rows(c, xindex, nrows))) return rc;
+  if (mono_out) {
+    // side effect of setgval: SNPs with min(n0, n1) == 0 over the PCA rows get ignore = YES (gval.c:80-82); the row stays in the table
+    std::vector<int> c0(ncols), c1(ncols);
+    if ((rc = eb_snp_counts(c, c0.data(), c1.data(), nullptr))) return rc;
+    for (int64_t s = 0; s < ncols; s++) mono_out[s] = std::min(c0[s], c1[s]) == 0 ? 1 : 0;
+  }
+  g_gval.set = true; g_gval.fancynorm = fancynorm; g_gval.altnormstyle = altnormstyle; g_gval.seed = seed;
+  return 0;
+}
+void eb_unsetgval(void) { g_gval.set = false; }
+void kjg_fpca(size_t K, size_t L, size_t I, double* eval, double* evec) {
+  if (K >= L) { fprintf(stderr, "kjg_fpca (libeigb200): K >= L\n"); exit(1); }
+  if (I == 0) { fprintf(stderr, "kjg_fpca (libeigb200): I == 0\n"); exit(1); }
+  if (!g_gval.set) { fprintf(stderr, "kjg_fpca (libeigb200): setgval has not handed over the genotypes\n"); exit(1); }
+  if (eb_fpca(dropin_ctx(), g_gval.fancynorm, g_gval.altnormstyle, K, L, I, g_gval.seed, eval, evec) != 0) {
+    fprintf(stderr, "kjg_fpca (libeigb200): %s\n", eb_last_error());
+    exit(1);
+  }
 }
 
 int eb_set_option(eb_ctx* c, const char* key, int value) {

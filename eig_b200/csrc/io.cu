@@ -202,4 +202,32 @@ int eb_write_grm(const char* path, const double* XTX, int nrows, int numsnps) {
   return 0;
 }
 
+// grmbinary: YES -- dumpgrmbin, smartpca.c:3704-3766 (GCTA layout): <prefix>.N.bin holds the SNP count as a 4-byte int for every
+// lower-triangle entry, <prefix>.bin the entries XTX[a][b] / (trace / nrows) as 4-byte floats, rows a = 0.., b <= a.
+int eb_write_grm_bin(const char* prefix, const double* XTX, int nrows, int numsnps) {
+  if (!prefix || !XTX || nrows <= 0) { set_error("eb_write_grm_bin: bad argument"); return EB_ERR_ARG; }
+  const size_t numout = (size_t)nrows * ((size_t)nrows + 1) / 2;
+  std::string pn = std::string(prefix) + ".N.bin", pb = std::string(prefix) + ".bin";
+  FILE* f = fopen(pn.c_str(), "wb");
+  if (!f) { set_error("open failed for %s", pn.c_str()); return EB_ERR_ARG; }
+  {
+    std::vector<int32_t> buf(std::min<size_t>(numout, 1 << 20), (int32_t)numsnps);
+    for (size_t done = 0; done < numout; done += buf.size())
+      if (fwrite(buf.data(), 4, std::min(buf.size(), numout - done), f) == 0) { fclose(f); set_error("(outpack) bad write"); return EB_ERR_ARG; }
+  }
+  fclose(f);
+  f = fopen(pb.c_str(), "wb");
+  if (!f) { set_error("open failed for %s", pb.c_str()); return EB_ERR_ARG; }
+  double tr = 0.0;
+  for (int a = 0; a < nrows; a++) tr += XTX[(size_t)a * nrows + a];
+  const double y_norm = tr / (double)nrows;
+  std::vector<float> row((size_t)nrows);
+  for (int a = 0; a < nrows; a++) {
+    for (int b = 0; b <= a; b++) row[b] = (float)(XTX[(size_t)a * nrows + b] / y_norm);
+    if (fwrite(row.data(), 4, (size_t)a + 1, f) != (size_t)a + 1) { fclose(f); set_error("(outpack) bad write"); return EB_ERR_ARG; }
+  }
+  fclose(f);
+  return 0;
+}
+
 }  // extern "C"

@@ -119,6 +119,9 @@ int peer_exchange(eb_ctx* c, int slot, void* local, size_t bytes, int aux) {
 //   signal(2)  done pulling; the NEXT pass waits for everybody's (2) before its first tile store (peer_grm_wait_idle)
 // Flags are monotone epochs in a small exported buffer; a wait gives up after GRM_WAIT_TIMEOUT_NS and raises the error
 // word instead of wedging the GPU when a peer died.
+// One configuration cannot spin on the device: two ranks that are contexts of ONE process on ONE GPU (the single-GPU test
+// set-up of eb_local_comm).  There a lagging rank's cudaFree synchronises the whole device and would wait for the leading
+// rank's spinning kernel, which waits for the lagging rank: the waits then go through the host (stream sync + eb_comm.barrier).
 
 __device__ __forceinline__ void tri_decode32(int t, int& ti, int& tj) {
   int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
@@ -280,7 +283,25 @@ int peer_grm_setup(eb_ctx* c, int nsplit) {
                 (unsigned long long)c->peer[PEER_SLOT_PARTIAL].rec[r].bytes, (unsigned long long)(need * sizeof(double)));
       return EB_ERR_STATE;
     }
+  // every rank sees every record, so all ranks take the same decision
+  c->grm_host_sync = false;
+  for (int r = 0; r < W; r++)
+    for (int q = r + 1; q < W; q++) {
+      const PeerRecord &a = c->peer[PEER_SLOT_FLAGS].rec[r], &b = c->peer[PEER_SLOT_FLAGS].rec[q];
+      if (a.pid == b.pid && a.device == b.device) c->grm_host_sync = true;
+    }
   return peer_bury(c);       // barrier: everybody has re-mapped, superseded allocations can go
+}
+
+// wait until every rank has signalled `phase` of `epoch`: a spinning warp on the stream, or (grm_host_sync) through the host
+static int grm_wait(eb_ctx* c, int phase, unsigned long long epoch) {
+  if (c->grm_host_sync) {
+    EB_CUDA(cudaStreamSynchronize(c->stream));
+    return comm_barrier(c);
+  }
+  grm_wait_kernel<<<1, 32, 0, c->stream>>>(c->grm_flags.p, c->comm.world, phase, epoch);
+  EB_CHECK_LAUNCH(c);
+  return 0;
 }
 
 int peer_grm_push_args(eb_ctx* c, GrmPush* out) {
@@ -294,10 +315,8 @@ int peer_grm_push_args(eb_ctx* c, GrmPush* out) {
 }
 
 int peer_grm_wait_idle(eb_ctx* c) {
-  if (c->grm_epoch == 0) return 0;
-  grm_wait_kernel<<<1, 32, 0, c->stream>>>(c->grm_flags.p, c->comm.world, 2, c->grm_epoch);
-  EB_CHECK_LAUNCH(c);
-  return 0;
+  if (c->grm_epoch == 0 || !c->grm_flags.p || c->grm_host_sync) return 0;   // host-sync mode closes every pass with its own barrier
+  return grm_wait(c, 2, c->grm_epoch);
 }
 
 int peer_grm_finalize(eb_ctx* c, int nsplit) {
@@ -314,8 +333,7 @@ int peer_grm_finalize(eb_ctx* c, int nsplit) {
   grm_signal_kernel<<<1, 32, 0, c->stream>>>(fa, 0, ep, reinterpret_cast<const unsigned long long*>(c->nused_d.p));   // payload: my used-SNP count
   EB_CHECK_LAUNCH(c);
   EB_CUDA(cudaEventRecord(c->ev[5], c->stream));
-  grm_wait_kernel<<<1, 32, 0, c->stream>>>(c->grm_flags.p, W, 0, ep);
-  EB_CHECK_LAUNCH(c);
+  if ((rc = grm_wait(c, 0, ep))) return rc;
   EB_CUDA(cudaEventRecord(c->ev[6], c->stream));
   const int mine = (ntri - me + W - 1) / W;
   if (mine > 0) {
@@ -324,8 +342,7 @@ int peer_grm_finalize(eb_ctx* c, int nsplit) {
   }
   grm_signal_kernel<<<1, 32, 0, c->stream>>>(fa, 1, ep, nullptr);
   EB_CHECK_LAUNCH(c);
-  grm_wait_kernel<<<1, 32, 0, c->stream>>>(c->grm_flags.p, W, 1, ep);
-  EB_CHECK_LAUNCH(c);
+  if ((rc = grm_wait(c, 1, ep))) return rc;
   const int groups = (ntri + W - 1) / W;
   if (W > 1 && groups > 0) {
     grm_push_gather_kernel<<<groups * (W - 1), 256, 0, c->stream>>>(ra, nslots, ntri, c->npad, c->xtx.p);
@@ -334,6 +351,7 @@ int peer_grm_finalize(eb_ctx* c, int nsplit) {
   grm_signal_kernel<<<1, 32, 0, c->stream>>>(fa, 2, ep, nullptr);
   EB_CHECK_LAUNCH(c);
   EB_CUDA(cudaEventRecord(c->ev[4], c->stream));
+  if (c->grm_host_sync) return grm_wait(c, 2, ep);      // nothing left outstanding between passes in this mode
   return 0;
 }
 
@@ -431,6 +449,8 @@ int peer_sum_host(eb_ctx* c, double* v, int count) {
 extern "C" int eb_set_comm(eb_ctx* c, const eb_comm* comm) {
   if (!c) return EB_ERR_ARG;
   cudaSetDevice(c->device);
+  // leaving a communicator: the peers may still be pulling the last pass out of my receive buffer
+  if (c->has_comm && c->grm_epoch > 0 && c->grm_flags.p) { eb::peer_grm_wait_idle(c); cudaStreamSynchronize(c->stream); }
   eb::peer_release(c);
   c->grm_recv.defer = c->fpG.defer = c->fpB.defer = c->fpS.defer = c->peer_scratch.defer = nullptr;
   for (auto& reg : c->peer) { for (void* p : reg.graveyard) cudaFree(p); reg.graveyard.clear(); }

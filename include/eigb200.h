@@ -72,6 +72,9 @@ int eb_write_eval (const char *path, const double *lambda, int n);
 int eb_write_evec (const char *path, const double *lambda, int numeigs, const char *const *ids, const char *const *groups,
                    const double *coords, int nout, int hiprec);
 int eb_write_grm (const char *path, const double *XTX, int nrows, int numsnps);
+/* grmbinary: YES (dumpgrmbin, smartpca.c:3704-3766): <prefix>.N.bin = numsnps as int32 per lower-triangle entry, <prefix>.bin =
+ * the entries scaled to mean diagonal 1 as float32 (GCTA layout) */
+int eb_write_grm_bin (const char *prefix, const double *XTX, int nrows, int numsnps);
 
 /* rows used = xindex[0..nrows) ascending into 0..numindivs-1 (loadindx, qpsubs.c:202-219).
  * xindex == NULL selects all individuals.  Re-gathers the working matrix on the device. */
@@ -214,6 +217,16 @@ int eb_pca_full (eb_ctx *, const eb_pca_opts * opts, int *xindex_io, int nrows,
 int eb_fpca (eb_ctx *, int fancynorm, int altnormstyle, size_t K, size_t L, size_t I, long seed,
              double *eval, double *evec);
 void eb_gauss_matrix (long seed, size_t n, size_t L, double *out);
+/* fastmode drop-in under the reference's own name (include/kjg_fpca.h:22; kjg_fpca.c:24): same arguments, same outputs, exit(1)
+ * on K >= L or I == 0 (kjg_fpca.c:26-29).  The reference hands the data over through gval.c's file statics (setgval, gval.c:31-87);
+ * here the hand-over is eb_setgval_packed with plain pointers (snp_pbuff[i] = xsnplist[i]->pbuff, the PCA rows xindex, the
+ * globals fancynorm / altnormstyle / seed of smartpca.c), called by the setgval replacement a maintainer compiles against the
+ * reference headers (integration/eb_gval.c).  mono_out[ncols] (may be NULL) = 1 where setgval's side effect sets
+ * cupt->ignore (min(n0, n1) == 0, gval.c:80-82).  Both run on the process-wide context of the eigvecs() drop-in. */
+int eb_setgval_packed (const uint8_t * const *snp_pbuff, int64_t ncols, int64_t rlen, int numindivs, const int *xindex, int nrows,
+                       int fancynorm, int altnormstyle, long seed, uint8_t * mono_out);
+void eb_unsetgval (void);
+void kjg_fpca (size_t K, size_t L, size_t I, double *eval, double *evec);
 
 /* -------- next rows: SNP loadings / sample projections, smartpca.c:1485-1525 -------- */
 int eb_project (eb_ctx *, const double *evecs, int numeigs, double *ffvecs /* [numeigs][nsnp] */ ,

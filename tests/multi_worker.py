@@ -105,6 +105,17 @@ def main():
         assert np.abs(ev1 - ev0).max() <= 1e-9 * ev0[0], (ev0, ev1)
         for k in range(4):
             assert abs(abs(vec0[:, k] @ vec1[:, k]) - 1) < 1e-8, k
+    # 5. fastmode at smartpca's defaults (K = 10, L = 20, I = 10) on a spectrum whose ten leading eigenvalues are separated:
+    #    SNP shards (all-reduced sketch, TSQR) == single GPU to the north_star bar
+    g12 = synth.genotypes(5, 4000, 400, missing=0.02, npops=12, pop_delta=np.linspace(0.15, 0.5, 12))
+    P12 = synth.pack(g12)
+    t0, t1 = parallel.shard_snps(4000, rank, world)
+    single.upload_packed(P12, 400); single.set_rows(None)
+    ctx.upload_packed(P12[t0:t1], 400); ctx.set_rows(None)
+    ev0, vec0 = single.fpca(10, 20, 10, seed=7)
+    ev1, vec1 = ctx.fpca(10, 20, 10, seed=7)
+    assert (np.abs(ev1 - ev0) / ev0).max() <= 1e-9, (ev0, ev1)
+    assert np.abs(np.abs((vec0 * vec1).sum(0)) - 1).max() <= 1e-9
     dist.barrier()
     ctx.close(); single.close()
     dist.destroy_process_group()

@@ -69,3 +69,16 @@ def test_grm_writer_reproduces_golden_bytes(tmp_path):
     assert got.splitlines()[0].split()[:3] == want.splitlines()[0].split()[:3]
     g = np.array([float(l.split()[3]) for l in got.splitlines()]); w = np.array([float(l.split()[3]) for l in want.splitlines()])
     assert np.abs(g - w).max() <= 2e-6        # printed values carry 6 decimals
+
+
+def test_grm_bin_writer_layout(tmp_path):
+    """grmbinary: YES (dumpgrmbin, smartpca.c:3704-3766): int32 SNP count per lower-triangle entry, float32 entries / (trace / n)"""
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((7, 7)); x = a @ a.T
+    capi.write_grm_bin(str(tmp_path / "g"), x, 1234)
+    n = 7 * 8 // 2
+    cnt = np.fromfile(str(tmp_path / "g.N.bin"), dtype=np.int32)
+    val = np.fromfile(str(tmp_path / "g.bin"), dtype=np.float32)
+    assert cnt.shape == (n,) and (cnt == 1234).all()
+    want = np.array([(x[i, j] / (np.trace(x) / 7)) for i in range(7) for j in range(i + 1)], dtype=np.float64).astype(np.float32)
+    assert np.array_equal(val, want)
