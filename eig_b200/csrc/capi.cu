@@ -314,6 +314,7 @@ static int grm_pass(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* n
   }
   cudaEventElapsedTime(&c->tm.finalize_ms, c->ev[3], c->ev[4]);
   c->grm_valid = true;
+  c->grm_collective = peer;
   return 0;
 }
 
@@ -413,13 +414,14 @@ int eb_grm_dense_end(eb_ctx* c, double* y_out, double* XTX_host) {
   if ((rc = grm_dense_finalize(c))) return rc;
   c->dense_open = false;
   c->grm_valid = true;
+  c->grm_collective = false;
   return eb_grm_finish(c, y_out, XTX_host);
 }
 
 int eb_eig(eb_ctx* c, int nvec, double* lambda, double* evecs) {
   if (!c || !c->grm_valid || c->y <= 0.0) { set_error("eb_eig: no normalised GRM resident (call eb_grm first)"); return EB_ERR_STATE; }
   EB_CUDA(cudaSetDevice(c->device));
-  return eig_resident(c, c->xtx.p, c->npad, c->nrows, 1.0 / c->y, nvec, lambda, evecs);
+  return eig_resident(c, c->xtx.p, c->npad, c->nrows, 1.0 / c->y, nvec, lambda, evecs, c->has_comm && c->grm_collective);
 }
 
 int eb_eigvecs(eb_ctx* c, const double* mat, double* evals, double* evecs, int n, int nvec) {

@@ -52,7 +52,7 @@ struct DevBuf {
 
 // multi-GPU exchange over peer memory (peer.cu)
 constexpr int EB_MAX_WORLD = 16;
-enum { PEER_SLOT_PARTIAL = 0, PEER_SLOT_FLAGS = 1, PEER_SLOT_A = 2, PEER_SLOT_B = 3, PEER_SLOT_C = 4, PEER_SLOT_T = 5, PEER_SLOTS = 6 };
+enum { PEER_SLOT_PARTIAL = 0, PEER_SLOT_FLAGS = 1, PEER_SLOT_A = 2, PEER_SLOT_B = 3, PEER_SLOT_C = 4, PEER_SLOT_T = 5, PEER_SLOT_W = 6, PEER_SLOTS = 7 };
 // Where grm_syrk_kernel stores a finished 128 x 128 tile when the SNPs are sharded over `world` GPUs: lower-triangle tile t
 // belongs to rank t % world, and every rank stores its partial tile STRAIGHT INTO THE OWNER'S receive buffer over NVLink
 // (slot [t / world][rank * nsplit + chunk], a dense 128 x 128 block), so the reduce-scatter traffic overlaps the DMMA work
@@ -123,6 +123,7 @@ struct eb_ctx {
   bool dense_open = false;
   int nsplit = 1;
   bool grm_valid = false;
+  bool grm_collective = false;    // the resident GRM is the reduced matrix of a sharded pass: identical on every rank of the communicator
   double y = 0.0;                 // trace/(nrows-1)
   int64_t nused = 0;              // SNPs of THIS shard that entered XTX
   int64_t nused_total = 0;        // over all shards (== nused without a communicator)
@@ -144,6 +145,8 @@ struct eb_ctx {
   bool has_comm = false;
   eb::PeerRegion peer[eb::PEER_SLOTS];
   eb::DevBuf<double> peer_scratch;
+  eb::DevBuf<double> chfsi_sum;             // collective subspace iteration: the 64 x n product block that is summed over the ranks
+  unsigned long long ar_epoch = 0;          // stream-ordered all-reduces done (all ranks in lockstep)
   eb::DevBuf<double> grm_recv;              // sharded GRM: [owned tiles][world * nsplit][128 x 128] partial tiles pushed by every rank
   eb::DevBuf<unsigned long long> grm_flags; // sharded GRM: device-side flags / mailbox written by the peers (GRM_FLAG_WORDS)
   unsigned long long grm_epoch = 0;         // one per sharded GRM pass (all ranks in lockstep)
@@ -171,7 +174,7 @@ int grm_nsplit_for(const eb_ctx* c, bool sharded);
 int grm_trace(eb_ctx* c);        // recompute trace_d / y from xtx
 int microbench_fp64(eb_ctx* c, double* dmma, double* dfma);
 // eig_kernels.cu
-int eig_resident(eb_ctx* c, const double* A_d, int64_t lda, int n, double scale, int nvec, double* lambda_h, double* evecs_h);
+int eig_resident(eb_ctx* c, const double* A_d, int64_t lda, int n, double scale, int nvec, double* lambda_h, double* evecs_h, bool collective = false);
 bool eig_uses_two_stage(const eb_ctx* c, int n, int nvec);
 // eig2_gemm.cu
 int launch_syrk_lower_add(eb_ctx* c, double* A, int64_t lda, int n, const double* T, int64_t ldt, int krows);
@@ -182,7 +185,7 @@ int grm_dense_finalize(eb_ctx* c);
 // eig2_kernels.cu
 int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, double* e);
 int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* theta_h, double* vec_d, int* iters_out, int* matvecs_out,
-              double lo0 = 0.0);
+              double lo0 = 0.0, bool collective = false);
 // fpca_kernels.cu
 int fpca_run(eb_ctx* c, int fancynorm, int altnormstyle, size_t K, size_t L, size_t I, long seed, double* eval, double* evec);
 int project_run(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, double* fxvecs, double* fxscal);
@@ -198,6 +201,8 @@ int peer_grm_wait_idle(eb_ctx* c);              // stream-ordered: peers finishe
 int peer_grm_finalize(eb_ctx* c, int nsplit);   // stream-ordered: signal, wait, reduce, signal, wait, gather, signal
 int peer_grm_collect(eb_ctx* c, long long* nused_total);   // after a stream sync: mailbox + error word
 int peer_allreduce(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64_t count);
+int peer_allreduce_stream(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64_t count, bool exchange);   // stream-ordered (device flags)
+int peer_flags_setup(eb_ctx* c);
 int peer_allreduce_any(eb_ctx* c, double* buf, int64_t count);
 int peer_sum_host(eb_ctx* c, double* v, int count);
 void peer_release(eb_ctx* c);

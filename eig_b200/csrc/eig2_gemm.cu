@@ -65,10 +65,12 @@ __device__ __forceinline__ DtSmem dt_setup(uint8_t* raw) {
 }
 
 // ------------------------------------------------------------------------------------------------ W = A * B^T
-// items = ntile * ksplit; item -> (ks = item / ntile, T = t0 + item % ntile).  k chunks of 32 cover [t0*128, n).
+// items = ntile * ksplit; item -> (ks = item / ntile, T = t0 + tile_first + (item % ntile) * tile_stride): a rank of a row-tile-sharded
+// product owns every tile_stride-th row tile (single GPU: first 0, stride 1).  k chunks of 32 cover [t0*128, n).
 __global__ void __launch_bounds__(DT_THREADS, 2)
 sym_skinny_kernel(const __grid_constant__ CUtensorMap mapA_mk, const __grid_constant__ CUtensorMap mapA_km,
-                  const __grid_constant__ CUtensorMap mapB, double* __restrict__ Wpart, int64_t ldw, int n, int t0, int ntile, int ksplit) {
+                  const __grid_constant__ CUtensorMap mapB, double* __restrict__ Wpart, int64_t ldw, int n, int t0, int ntile, int ksplit,
+                  int tile_first, int tile_stride) {
   extern __shared__ __align__(128) uint8_t dt_raw[];
   const DtSmem sm = dt_setup(dt_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,7 +81,7 @@ sym_skinny_kernel(const __grid_constant__ CUtensorMap mapA_mk, const __grid_cons
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int ks = item / ntile, T = t0 + item % ntile;
+        const int ks = item / ntile, T = t0 + tile_first + (item % ntile) * tile_stride;
         const int c0 = (int)(((long long)nchunks * ks) / ksplit), c1 = (int)(((long long)nchunks * (ks + 1)) / ksplit);
         for (int kc = c0; kc < c1; kc++) {
           const int k0 = t0 * DT_M + kc * DT_KC;
@@ -104,7 +106,7 @@ sym_skinny_kernel(const __grid_constant__ CUtensorMap mapA_mk, const __grid_cons
     for (int u = 0; u < 4; u++) acc[t][u][0] = acc[t][u][1] = 0.0;
   uint32_t stage = 0, phase = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int ks = item / ntile, T = t0 + item % ntile;
+    const int ks = item / ntile, T = t0 + tile_first + (item % ntile) * tile_stride;
     const int c0 = (int)(((long long)nchunks * ks) / ksplit), c1 = (int)(((long long)nchunks * (ks + 1)) / ksplit);
     for (int kc = c0; kc < c1; kc++) {
       const int k0 = t0 * DT_M + kc * DT_KC;
@@ -343,14 +345,15 @@ int dt_resident_ctas(eb_ctx* c) {
 
 // Wpart[ks][64][ldw] (ks < ksplit_out) = A[:, t0*128:] * Bt^T restricted to row tiles >= t0.  A: n x n (lda), Bt: 64 x n (ldb).
 int launch_sym_skinny(eb_ctx* c, const double* A, int64_t lda, int n, int t0, const double* Bt, int64_t ldb, double* Wpart, int64_t ldw,
-                      int max_ksplit, int* ksplit_out) {
+                      int max_ksplit, int* ksplit_out, int tile_first, int tile_stride) {
   CUtensorMap mk, km, mb;
   int rc;
   if ((rc = make_f64_tensormap(&mk, A, n, n, lda, DT_LD_K, DT_M))) return rc;
   if ((rc = make_f64_tensormap(&km, A, n, n, lda, DT_LD_M, DT_KC))) return rc;
   if ((rc = make_f64_tensormap(&mb, Bt, DT_N, n, ldb, DT_LD_K, DT_N))) return rc;
   const int slots = dt_resident_ctas(c);
-  const int ntile = (n + DT_M - 1) / DT_M - t0;
+  const int ntile_all = (n + DT_M - 1) / DT_M - t0;
+  const int ntile = ntile_all > tile_first ? (ntile_all - tile_first + tile_stride - 1) / tile_stride : 0;     // row tiles of this rank
   if (ntile <= 0) { *ksplit_out = 0; return 0; }
   const int nchunks = (n - t0 * DT_M + DT_KC - 1) / DT_KC;
   // pick the k split that fills the resident CTA slots best (each split needs >= 8 chunks of work)
@@ -364,7 +367,7 @@ int launch_sym_skinny(eb_ctx* c, const double* A, int64_t lda, int n, int t0, co
   if (const char* e = getenv("EB_DBG_KSPLIT")) best = std::max(1, std::min(atoi(e), max_ksplit));
   *ksplit_out = best;
   const int grid = std::min(ntile * best, slots);
-  sym_skinny_kernel<<<grid, DT_THREADS, DT_SMEM, c->stream>>>(mk, km, mb, Wpart, ldw, n, t0, ntile, best);
+  sym_skinny_kernel<<<grid, DT_THREADS, DT_SMEM, c->stream>>>(mk, km, mb, Wpart, ldw, n, t0, ntile, best, tile_first, tile_stride);
   EB_CHECK_LAUNCH(c);
   return 0;
 }

@@ -25,7 +25,7 @@ namespace cg = cooperative_groups;
 namespace eb {
 
 int launch_sym_skinny(eb_ctx* c, const double* A, int64_t lda, int n, int t0, const double* Bt, int64_t ldb, double* Wpart, int64_t ldw,
-                      int max_ksplit, int* ksplit_out);
+                      int max_ksplit, int* ksplit_out, int tile_first = 0, int tile_stride = 1);
 int launch_syr2k_lower(eb_ctx* c, double* A, int64_t lda, int n, int t0, const double* VZ, int64_t ldv);
 
 constexpr int BW = 64;             // band width after stage 1 == panel width
@@ -936,8 +936,23 @@ __global__ void __launch_bounds__(256) defl_coef_kernel(const double* __restrict
 // lo0: lower end of the spectrum when the caller knows it (the bisection's smallest eigenvalue), else 0 (a GRM is positive
 // semi-definite); the damped interval of the filter starts there, so an indefinite matrix needs it.
 // c->tm.chfsi_converged / chfsi_resid tell the caller whether the strict tolerance was reached (see eb_timings).
+// collective: every rank of the communicator holds the SAME matrix (the reduced GRM of a sharded pass) and calls this together; the
+// block mat-vecs are then split by row tiles of A over the ranks and the 64 x n result block is summed (= gathered: the other
+// ranks' rows are zero) by the stream-ordered all-reduce over peer memory, bit-identical on every rank.  Everything else of the
+// iteration is O(n 64^2) and runs replicated.
+__global__ void __launch_bounds__(256) combine_own_kernel(const double* __restrict__ Wpart, int ksplit, int64_t ldw, double* __restrict__ Out,
+                                                          int64_t ldo, int n, int tile_first, int tile_stride) {
+  const int i = blockIdx.x * 256 + threadIdx.x, c = blockIdx.y;
+  if (i >= n) return;
+  const int T = i >> 7;
+  if (T < tile_first || (T - tile_first) % tile_stride != 0) return;        // not my row tile: stays zero
+  double v = 0.0;
+  for (int ks = 0; ks < ksplit; ks++) v += Wpart[((size_t)ks * 64 + c) * ldw + i];
+  Out[(size_t)c * ldo + i] = v;
+}
+
 int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* theta_h, double* vec_d, int* iters_out, int* matvecs_out,
-              double lo0) {
+              double lo0, bool collective) {
   cudaStream_t st = c->stream;
   int rc;
   const int64_t ld = ((int64_t)n + 7) & ~7ll;
@@ -973,8 +988,36 @@ int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* 
   // interval: outlier eigenvalues (population structure puts them 100-1000x above the bulk) then no longer bound the
   // filter degree through the 1e8 dynamic-range budget, and rounding-level components along them cannot grow.
   int nlock = 0;
+  const bool shard = collective && c->has_comm && c->comm.world > 1;
+  bool first_exchange = true;
+  if (shard && (rc = c->chfsi_sum.ensure((size_t)64 * ld))) return rc;
   auto matvec = [&](const double* X, double* Out, double a1, const double* Y1, double a2, const double* Y0, double a3) -> int {
     int ks = 1, r;
+    if (shard) {
+      const int W = c->comm.world, me = c->comm.rank;
+      if ((r = launch_sym_skinny(c, A, lda, n, 0, X, ld, Wpart, ld, MAX_KSPLIT, &ks, me, W))) return r;
+      EB_CUDA(cudaMemsetAsync(c->chfsi_sum.p, 0, sizeof(double) * 64 * ld, st));
+      if (ks > 0) {
+        combine_own_kernel<<<cgrid, 256, 0, st>>>(Wpart, ks, ld, c->chfsi_sum.p, ld, n, me, W);
+        EB_CHECK_LAUNCH(c);
+      }
+      if ((r = peer_allreduce_stream(c, PEER_SLOT_W, c->chfsi_sum.p, c->chfsi_sum.n, (int64_t)64 * ld, first_exchange))) return r;
+      first_exchange = false;
+      if (nlock > 0) {
+        gram64_kernel<<<nchunk, 256, 0, st>>>(Lk, ld, X, ld, 0, n, gch, Gpart);
+        EB_CHECK_LAUNCH(c);
+        defl_coef_kernel<<<16, 256, 0, st>>>(Gpart, nchunk, dvec_d, Cm);
+        EB_CHECK_LAUNCH(c);
+        left_mult_kernel<<<lm_grid, 256, 16384 * 8, st>>>(Cm, Lk, nullptr, nullptr, ld, Corr, ld, 0, n);
+        EB_CHECK_LAUNCH(c);
+        combine_kernel<<<cgrid, 256, 0, st>>>(c->chfsi_sum.p, 1, ld, Out, ld, n, 0, 0, a1, Y1, a2, Y0, a3, ld, Corr, -a1);
+      } else {
+        combine_kernel<<<cgrid, 256, 0, st>>>(c->chfsi_sum.p, 1, ld, Out, ld, n, 0, 0, a1, Y1, a2, Y0, a3, ld);
+      }
+      EB_CHECK_LAUNCH(c);
+      nmat++;
+      return 0;
+    }
     if ((r = launch_sym_skinny(c, A, lda, n, 0, X, ld, Wpart, ld, MAX_KSPLIT, &ks))) return r;
     if (nlock > 0) {
       gram64_kernel<<<nchunk, 256, 0, st>>>(Lk, ld, X, ld, 0, n, gch, Gpart);

@@ -781,7 +781,31 @@ static int tridiag_spectrum(eb_ctx* c, int n, double* d, double* e, double* e2, 
 }
 
 // large-n path: spectrum by two-stage tridiagonalisation (only if lambda_h), leading vectors by subspace iteration
-static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, double scale, int nvec, double* lambda_h, double* evecs_h) {
+// Deterministic sign: every returned eigenvector has its entry of largest magnitude positive (first such entry on ties).  LAPACK's sign
+// is whatever dsteqr's rotations leave (the reference fixes one only with `topright:`, smartpca.c:1267-1281); a fixed convention makes
+// the one-stage, full-basis and subspace-iteration paths -- and every GPU of a sharded run -- agree, and it is the sign the reference's
+// own example outputs carry (POPGEN/example.evec, EIGENSTRAT/example.pca.evec).
+__global__ void __launch_bounds__(256) sign_fix_kernel(double* __restrict__ Z, int64_t ldz, int n) {
+  __shared__ double sv[256];
+  __shared__ int si[256];
+  double* z = Z + (size_t)blockIdx.x * ldz;
+  double best = -1.0; int bi = 0;
+  for (int i = threadIdx.x; i < n; i += 256) { const double a = fabs(z[i]); if (a > best) { best = a; bi = i; } }
+  sv[threadIdx.x] = best; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const double a = sv[threadIdx.x + o]; const int ia = si[threadIdx.x + o];
+      if (a > sv[threadIdx.x] || (a == sv[threadIdx.x] && ia < si[threadIdx.x])) { sv[threadIdx.x] = a; si[threadIdx.x] = ia; }
+    }
+    __syncthreads();
+  }
+  const bool flip = z[si[0]] < 0.0;
+  __syncthreads();
+  if (flip) for (int i = threadIdx.x; i < n; i += 256) z[i] = -z[i];
+}
+
+static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, double scale, int nvec, double* lambda_h, double* evecs_h, bool collective) {
   cudaStream_t st = c->stream;
   int rc;
   c->tm.tridiag_ms = c->tm.bisect_ms = c->tm.vectors_ms = 0.f;
@@ -814,7 +838,7 @@ static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, do
     c->zvec_ld = n;
     std::vector<double> th(nvec);
     EB_CUDA(cudaEventRecord(c->ev[8], st));
-    if ((rc = chfsi_top(c, A_d, lda_in, n, nvec, th.data(), c->zvec_d.p, &c->tm.chfsi_iters, &c->tm.chfsi_matvecs, lo0))) {
+    if ((rc = chfsi_top(c, A_d, lda_in, n, nvec, th.data(), c->zvec_d.p, &c->tm.chfsi_iters, &c->tm.chfsi_matvecs, lo0, collective && n >= 4096))) {
       if (rc != EB_ERR_NUMERIC) return rc;
       // the subspace iteration gave up: take the vectors from the one-stage path (slower, direct)
       const int keep = c->opt_eig_method;
@@ -824,6 +848,8 @@ static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, do
       c->tm.eig_method = 2;
       return rc;
     }
+    sign_fix_kernel<<<nvec, 256, 0, st>>>(c->zvec_d.p, n, n);
+    EB_CHECK_LAUNCH(c);
     EB_CUDA(cudaEventRecord(c->ev[9], st));
     if (evecs_h) EB_CUDA(cudaMemcpyAsync(evecs_h, c->zvec_d.p, sizeof(double) * (size_t)nvec * n, cudaMemcpyDeviceToHost, st));
     EB_CUDA(cudaStreamSynchronize(st));
@@ -840,12 +866,12 @@ bool eig_uses_two_stage(const eb_ctx* c, int n, int nvec) {
   return method == 2 && nvec <= 40 && n >= 256;      // block width 64 bounds the subspace iteration
 }
 
-int eig_resident(eb_ctx* c, const double* A_d, int64_t lda_in, int n, double scale, int nvec, double* lambda_h, double* evecs_h) {
+int eig_resident(eb_ctx* c, const double* A_d, int64_t lda_in, int n, double scale, int nvec, double* lambda_h, double* evecs_h, bool collective) {
   if (n <= 0) return 0;
   nvec = std::max(0, std::min(nvec, n));
   const int method = (eig_uses_two_stage(c, n, nvec) && !(lda_in & 1)) ? 2 : 1;
   c->tm.eig_method = method;
-  if (method == 2) return eig_two_stage(c, A_d, lda_in, n, scale, nvec, lambda_h, evecs_h);
+  if (method == 2) return eig_two_stage(c, A_d, lda_in, n, scale, nvec, lambda_h, evecs_h, collective);
   cudaStream_t st = c->stream;
   int rc;
   const int64_t lda = (n + 15) & ~15;
@@ -918,6 +944,10 @@ int eig_resident(eb_ctx* c, const double* A_d, int64_t lda_in, int n, double sca
     tri_invit_kernel<<<1, 1024, 0, st>>>(n, nvec, d, e, c->lambda_d.p, bounds, work, ipiv, c->zvec_d.p);
     EB_CHECK_LAUNCH(c);
     tri_backtransform_kernel<<<nvec, 1024, 0, st>>>(A, lda, n, tau, c->zvec_d.p);
+    EB_CHECK_LAUNCH(c);
+  }
+  if (nvec > 0) {
+    sign_fix_kernel<<<nvec, 256, 0, st>>>(c->zvec_d.p, ldz, n);
     EB_CHECK_LAUNCH(c);
   }
   EB_CUDA(cudaEventRecord(c->ev[1], st));

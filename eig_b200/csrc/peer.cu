@@ -147,8 +147,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-// one warp: lane w tells rank w "phase `phase` of epoch `epoch` is complete on rank a.rank" (optionally with a payload word)
-__global__ void __launch_bounds__(32) grm_signal_kernel(const GrmFlagArgs a, int phase, unsigned long long epoch,
+// one warp: lane w tells rank w "step `word0 / 16` of epoch `epoch` is complete on rank a.rank" (optionally with a payload word).
+// Flag rows (16 words each): 0-2 the three phases of the sharded GRM, 8 / 9 the two phases of the stream-ordered all-reduce.
+__global__ void __launch_bounds__(32) grm_signal_kernel(const GrmFlagArgs a, int word0, unsigned long long epoch,
                                                         const unsigned long long* __restrict__ payload) {
   const int w = threadIdx.x;
   if (w >= a.world) return;
@@ -157,16 +158,16 @@ __global__ void __launch_bounds__(32) grm_signal_kernel(const GrmFlagArgs a, int
     a.flags[w][3 * 16 + ((epoch & 1) * 16 + a.rank) * 2] = payload[0];
     __threadfence_system();
   }
-  st_release_sys(a.flags[w] + phase * 16 + a.rank, epoch);
+  st_release_sys(a.flags[w] + word0 + a.rank, epoch);
 }
 
 // one warp: lane w waits until rank w has signalled `phase` of `epoch` into MY flag buffer
-__global__ void __launch_bounds__(32) grm_wait_kernel(unsigned long long* mine, int world, int phase, unsigned long long epoch) {
+__global__ void __launch_bounds__(32) grm_wait_kernel(unsigned long long* mine, int world, int word0, unsigned long long epoch) {
   const int w = threadIdx.x;
   if (w < world) {
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (ld_acquire_sys(mine + phase * 16 + w) < epoch) {
+    while (ld_acquire_sys(mine + word0 + w) < epoch) {
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
       if (t1 - t0 > GRM_WAIT_TIMEOUT_NS) { mine[FLAG_ERR] = 1ull + (unsigned long long)w; break; }
@@ -269,20 +270,29 @@ int peer_grm_setup(eb_ctx* c, int nsplit) {
   // grow only (outlier passes shrink the matrix and keep the mapping)
   EB_CUDA(cudaStreamSynchronize(c->stream));
   if ((rc = c->grm_recv.ensure(need))) return rc;
-  if (!c->grm_flags.p) {
-    if ((rc = c->grm_flags.ensure(GRM_FLAG_WORDS))) return rc;
-    EB_CUDA(cudaMemsetAsync(c->grm_flags.p, 0, sizeof(unsigned long long) * GRM_FLAG_WORDS, c->stream));
-    EB_CUDA(cudaStreamSynchronize(c->stream));
-    c->grm_epoch = 0;
-  }
   if ((rc = peer_exchange(c, PEER_SLOT_PARTIAL, c->grm_recv.p, c->grm_recv.n * sizeof(double), 0))) return rc;
-  if ((rc = peer_exchange(c, PEER_SLOT_FLAGS, c->grm_flags.p, c->grm_flags.n * sizeof(unsigned long long), 0))) return rc;
+  if ((rc = peer_flags_setup(c))) return rc;
   for (int r = 0; r < W; r++)
     if (c->peer[PEER_SLOT_PARTIAL].rec[r].bytes < need * sizeof(double)) {
       set_error("sharded GRM: rank %d holds a smaller receive buffer (%llu < %llu bytes): every shard must use the same rows", r,
                 (unsigned long long)c->peer[PEER_SLOT_PARTIAL].rec[r].bytes, (unsigned long long)(need * sizeof(double)));
       return EB_ERR_STATE;
     }
+  return peer_bury(c);       // barrier: everybody has re-mapped, superseded allocations can go
+}
+
+// The small flag / mailbox buffer every rank exports once per communicator (collective; a no-op once it is mapped).
+int peer_flags_setup(eb_ctx* c) {
+  const int W = c->comm.world;
+  if (c->grm_flags.p && (int)c->peer[PEER_SLOT_FLAGS].mapped.size() == W && c->peer[PEER_SLOT_FLAGS].mapped[c->comm.rank]) return 0;
+  int rc;
+  if (!c->grm_flags.p) {
+    if ((rc = c->grm_flags.ensure(GRM_FLAG_WORDS))) return rc;
+    EB_CUDA(cudaMemsetAsync(c->grm_flags.p, 0, sizeof(unsigned long long) * GRM_FLAG_WORDS, c->stream));
+    EB_CUDA(cudaStreamSynchronize(c->stream));
+    c->grm_epoch = 0; c->ar_epoch = 0;
+  }
+  if ((rc = peer_exchange(c, PEER_SLOT_FLAGS, c->grm_flags.p, c->grm_flags.n * sizeof(unsigned long long), 0))) return rc;
   // every rank sees every record, so all ranks take the same decision
   c->grm_host_sync = false;
   for (int r = 0; r < W; r++)
@@ -290,7 +300,7 @@ int peer_grm_setup(eb_ctx* c, int nsplit) {
       const PeerRecord &a = c->peer[PEER_SLOT_FLAGS].rec[r], &b = c->peer[PEER_SLOT_FLAGS].rec[q];
       if (a.pid == b.pid && a.device == b.device) c->grm_host_sync = true;
     }
-  return peer_bury(c);       // barrier: everybody has re-mapped, superseded allocations can go
+  return 0;
 }
 
 // wait until every rank has signalled `phase` of `epoch`: a spinning warp on the stream, or (grm_host_sync) through the host
@@ -299,7 +309,7 @@ static int grm_wait(eb_ctx* c, int phase, unsigned long long epoch) {
     EB_CUDA(cudaStreamSynchronize(c->stream));
     return comm_barrier(c);
   }
-  grm_wait_kernel<<<1, 32, 0, c->stream>>>(c->grm_flags.p, c->comm.world, phase, epoch);
+  grm_wait_kernel<<<1, 32, 0, c->stream>>>(c->grm_flags.p, c->comm.world, phase * 16, epoch);
   EB_CHECK_LAUNCH(c);
   return 0;
 }
@@ -330,7 +340,7 @@ int peer_grm_finalize(eb_ctx* c, int nsplit) {
   for (int r = 0; r < W; r++) ra.recv[r] = (const double*)c->peer[PEER_SLOT_PARTIAL].mapped[r];
   const unsigned long long ep = ++c->grm_epoch;
   const int T = c->npad / TILE, ntri = T * (T + 1) / 2, nslots = W * nsplit;
-  grm_signal_kernel<<<1, 32, 0, c->stream>>>(fa, 0, ep, reinterpret_cast<const unsigned long long*>(c->nused_d.p));   // payload: my used-SNP count
+  grm_signal_kernel<<<1, 32, 0, c->stream>>>(fa, 0 * 16, ep, reinterpret_cast<const unsigned long long*>(c->nused_d.p));   // payload: my used-SNP count
   EB_CHECK_LAUNCH(c);
   EB_CUDA(cudaEventRecord(c->ev[5], c->stream));
   if ((rc = grm_wait(c, 0, ep))) return rc;
@@ -340,7 +350,7 @@ int peer_grm_finalize(eb_ctx* c, int nsplit) {
     grm_push_reduce_kernel<<<mine, 256, 0, c->stream>>>(c->grm_recv.p, W, me, nslots, ntri, c->npad, c->xtx.p);
     EB_CHECK_LAUNCH(c);
   }
-  grm_signal_kernel<<<1, 32, 0, c->stream>>>(fa, 1, ep, nullptr);
+  grm_signal_kernel<<<1, 32, 0, c->stream>>>(fa, 1 * 16, ep, nullptr);
   EB_CHECK_LAUNCH(c);
   if ((rc = grm_wait(c, 1, ep))) return rc;
   const int groups = (ntri + W - 1) / W;
@@ -348,7 +358,7 @@ int peer_grm_finalize(eb_ctx* c, int nsplit) {
     grm_push_gather_kernel<<<groups * (W - 1), 256, 0, c->stream>>>(ra, nslots, ntri, c->npad, c->xtx.p);
     EB_CHECK_LAUNCH(c);
   }
-  grm_signal_kernel<<<1, 32, 0, c->stream>>>(fa, 2, ep, nullptr);
+  grm_signal_kernel<<<1, 32, 0, c->stream>>>(fa, 2 * 16, ep, nullptr);
   EB_CHECK_LAUNCH(c);
   EB_CUDA(cudaEventRecord(c->ev[4], c->stream));
   if (c->grm_host_sync) return grm_wait(c, 2, ep);      // nothing left outstanding between passes in this mode
@@ -415,6 +425,48 @@ int peer_allreduce(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64
   return 0;
 }
 
+// The same all-reduce without the host in the loop: "my input is complete" / "my slice is reduced and pushed" travel as device
+// flags (rows 8 and 9 of the flag buffer, epoch ar_epoch), so a chain of kernels, all-reduces and more kernels stays on the stream --
+// what the collective subspace iteration needs for its hundreds of 64 x n products.  exchange: publish / map `buf` first (host
+// collective; pass true whenever the buffer may have been reallocated, all ranks alike).
+int peer_allreduce_stream(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64_t count, bool exchange) {
+  const int W = c->comm.world;
+  int rc;
+  if (count & 1) { set_error("peer_allreduce_stream: odd element count"); return EB_ERR_ARG; }
+  if (exchange) {
+    if ((rc = peer_exchange(c, slot, buf, alloc_doubles * sizeof(double), (int)(count & 0x7fffffff)))) return rc;
+    if ((rc = peer_flags_setup(c))) return rc;
+    if ((rc = peer_bury(c))) return rc;
+  }
+  AllreduceArgs a;
+  memset(&a, 0, sizeof(a));
+  a.world = W; a.rank = c->comm.rank;
+  for (int r = 0; r < W; r++) {
+    a.buf[r] = (double*)c->peer[slot].mapped[r];
+    if (!a.buf[r]) { set_error("peer_allreduce_stream: buffer of rank %d is not mapped", r); return EB_ERR_STATE; }
+  }
+  GrmFlagArgs fa;
+  if ((rc = flag_args(c, &fa))) return rc;
+  const unsigned long long ep = ++c->ar_epoch;
+  auto sync_step = [&](int row) -> int {
+    if (c->grm_host_sync) { EB_CUDA(cudaStreamSynchronize(c->stream)); return comm_barrier(c); }
+    grm_signal_kernel<<<1, 32, 0, c->stream>>>(fa, row * 16, ep, nullptr);
+    EB_CHECK_LAUNCH(c);
+    grm_wait_kernel<<<1, 32, 0, c->stream>>>(c->grm_flags.p, W, row * 16, ep);
+    EB_CHECK_LAUNCH(c);
+    return 0;
+  };
+  if ((rc = sync_step(8))) return rc;
+  const int64_t nvec = count / 2, per = (nvec + W - 1) / W;
+  const int64_t v0 = std::min<int64_t>(nvec, per * a.rank), v1 = std::min<int64_t>(nvec, v0 + per);
+  if (v1 > v0) {
+    const int grid = (int)std::min<int64_t>((v1 - v0 + 255) / 256, (int64_t)c->num_sms * 8);
+    peer_allreduce_kernel<<<grid, 256, 0, c->stream>>>(a, v0, v1);
+    EB_CHECK_LAUNCH(c);
+  }
+  return sync_step(9);
+}
+
 // Sum over ranks of an arbitrary device buffer (any address, any owner): staged through the exported scratch allocation.
 // For the small per-individual / per-sample sums of the projection, lsqproj and shrinkmode passes.  Collective.
 int peer_allreduce_any(eb_ctx* c, double* buf, int64_t count) {
@@ -452,9 +504,9 @@ extern "C" int eb_set_comm(eb_ctx* c, const eb_comm* comm) {
   // leaving a communicator: the peers may still be pulling the last pass out of my receive buffer
   if (c->has_comm && c->grm_epoch > 0 && c->grm_flags.p) { eb::peer_grm_wait_idle(c); cudaStreamSynchronize(c->stream); }
   eb::peer_release(c);
-  c->grm_recv.defer = c->fpG.defer = c->fpB.defer = c->fpS.defer = c->peer_scratch.defer = nullptr;
+  c->grm_recv.defer = c->fpG.defer = c->fpB.defer = c->fpS.defer = c->peer_scratch.defer = c->chfsi_sum.defer = nullptr;
   for (auto& reg : c->peer) { for (void* p : reg.graveyard) cudaFree(p); reg.graveyard.clear(); }
-  c->grm_epoch = 0; c->grm_recv.release(); c->grm_flags.release();
+  c->grm_epoch = 0; c->ar_epoch = 0; c->grm_recv.release(); c->grm_flags.release(); c->chfsi_sum.release();
   if (!comm || comm->world <= 1) { c->has_comm = false; memset(&c->comm, 0, sizeof(c->comm)); c->comm.world = 1; return 0; }
   if (comm->world > eb::EB_MAX_WORLD || comm->rank < 0 || comm->rank >= comm->world || !comm->allgather_host || !comm->barrier) {
     eb::set_error("eb_set_comm: need 0 <= rank < world <= %d and both callbacks", eb::EB_MAX_WORLD);
@@ -466,6 +518,7 @@ extern "C" int eb_set_comm(eb_ctx* c, const eb_comm* comm) {
   c->fpB.defer = &c->peer[eb::PEER_SLOT_B].graveyard;
   c->fpS.defer = &c->peer[eb::PEER_SLOT_C].graveyard;
   c->peer_scratch.defer = &c->peer[eb::PEER_SLOT_T].graveyard;
+  c->chfsi_sum.defer = &c->peer[eb::PEER_SLOT_W].graveyard;
   return 0;
 }
 

@@ -16,8 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     txt = open(os.path.join(ROOT, "include", "eigb200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    # eb_* entry points plus the two drop-in symbols that keep the reference's own names (include/eigsubs.h:6-7)
-    return sorted(set(re.findall(r"\b(eb_[a-z0-9_]+|eigvecs|eigvals)\s*\(", txt)))
+    # eb_* entry points plus the drop-in symbols that keep the reference's own names (include/eigsubs.h:6-7, include/kjg_fpca.h:22)
+    return sorted(set(re.findall(r"\b(eb_[a-z0-9_]+|eigvecs|eigvals|kjg_fpca)\s*\(", txt)))
 
 
 def test_library_exports_every_declared_symbol():
