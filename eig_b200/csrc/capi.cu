@@ -510,6 +510,7 @@ int eb_set_option(eb_ctx* c, const char* key, int value) {
   if (!c || !key) return EB_ERR_ARG;
   if (!strcmp(key, "eig_method")) { c->opt_eig_method = value; return 0; }
   if (!strcmp(key, "two_stage_min")) { c->opt_two_stage_min = value; return 0; }
+  if (!strcmp(key, "dist_min")) { c->opt_dist_min = value; return 0; }
   set_error("eb_set_option: unknown key '%s'", key);
   return EB_ERR_ARG;
 }

@@ -139,6 +139,7 @@ struct eb_ctx {
   double* dbg_band_h = nullptr;    // eb_debug_tridiag only
   int opt_eig_method = 0;          // 0 auto, 1 one-stage (dsytrd-style), 2 two-stage + subspace iteration
   int opt_two_stage_min = 1536;    // auto: n at which the two-stage path takes over
+  int opt_dist_min = 8192;         // collective solves: n from which the band reduction / subspace iteration are split over the ranks
 
   // multi-GPU (peer.cu)
   eb_comm comm = {0, 1, nullptr, nullptr, nullptr};
@@ -183,7 +184,7 @@ int launch_gemm(eb_ctx* c, bool a_km, bool b_kn, const double* A, int64_t lda, c
 // grm_kernel.cu (dense path)
 int grm_dense_finalize(eb_ctx* c);
 // eig2_kernels.cu
-int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, double* e);
+int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, double* e, bool collective = false);
 int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* theta_h, double* vec_d, int* iters_out, int* matvecs_out,
               double lo0 = 0.0, bool collective = false);
 // fpca_kernels.cu
@@ -201,7 +202,7 @@ int peer_grm_wait_idle(eb_ctx* c);              // stream-ordered: peers finishe
 int peer_grm_finalize(eb_ctx* c, int nsplit);   // stream-ordered: signal, wait, reduce, signal, wait, gather, signal
 int peer_grm_collect(eb_ctx* c, long long* nused_total);   // after a stream sync: mailbox + error word
 int peer_allreduce(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64_t count);
-int peer_allreduce_stream(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64_t count, bool exchange);   // stream-ordered (device flags)
+int peer_allreduce_stream(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64_t count, bool exchange, int64_t offset = 0);   // stream-ordered (device flags)
 int peer_flags_setup(eb_ctx* c);
 int peer_allreduce_any(eb_ctx* c, double* buf, int64_t count);
 int peer_sum_host(eb_ctx* c, double* v, int count);

@@ -70,7 +70,7 @@ __device__ __forceinline__ DtSmem dt_setup(uint8_t* raw) {
 __global__ void __launch_bounds__(DT_THREADS, 2)
 sym_skinny_kernel(const __grid_constant__ CUtensorMap mapA_mk, const __grid_constant__ CUtensorMap mapA_km,
                   const __grid_constant__ CUtensorMap mapB, double* __restrict__ Wpart, int64_t ldw, int n, int t0, int ntile, int ksplit,
-                  int tile_first, int tile_stride) {
+                  int tile_first, int tile_stride, int full_rows) {
   extern __shared__ __align__(128) uint8_t dt_raw[];
   const DtSmem sm = dt_setup(dt_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,7 +86,7 @@ sym_skinny_kernel(const __grid_constant__ CUtensorMap mapA_mk, const __grid_cons
         for (int kc = c0; kc < c1; kc++) {
           const int k0 = t0 * DT_M + kc * DT_KC;
           dt_mbar_wait(sm.empty + stage, phase ^ 1);
-          const bool mk = k0 < (T + 1) * DT_M;
+          const bool mk = full_rows || k0 < (T + 1) * DT_M;      // full_rows: the square is stored, no transposed blocks
           dt_mbar_expect_tx(sm.full + stage, (mk ? DT_A_BYTES : DT_A_KM_BYTES) + DT_B_BYTES);
           if (mk) dt_tma_2d(sm.A(stage), &mapA_mk, k0, T * DT_M, sm.full + stage);
           else dt_tma_2d(sm.A(stage), &mapA_km, T * DT_M, k0, sm.full + stage);
@@ -111,7 +111,7 @@ sym_skinny_kernel(const __grid_constant__ CUtensorMap mapA_mk, const __grid_cons
     for (int kc = c0; kc < c1; kc++) {
       const int k0 = t0 * DT_M + kc * DT_KC;
       dt_mbar_wait(sm.full + stage, phase);
-      if (k0 < (T + 1) * DT_M) dt_stage_mma<false, false>(sm.a32(stage), sm.b32(stage), acc, wm, wn, g, q);
+      if (full_rows || k0 < (T + 1) * DT_M) dt_stage_mma<false, false>(sm.a32(stage), sm.b32(stage), acc, wm, wn, g, q);
       else dt_stage_mma<true, false>(sm.a32(stage), sm.b32(stage), acc, wm, wn, g, q);
       dt_release_stage(sm.empty + stage, lane);
       if (++stage == DT_STAGES) { stage = 0; phase ^= 1; }
@@ -144,9 +144,17 @@ __device__ __forceinline__ void syr2k_item(int item, int t0, int& I, int& J64) {
   J64 = 2 * t0 + (item - r * (r + 1));
 }
 
+// rect_stride > 0: the row-distributed reduction (every rank stores the full square and owns every rect_stride-th 128-row tile):
+// item -> (I = t0 + rect_first + (item / rect_cols) * rect_stride, J64 = 2 * t0 + item % rect_cols), all 64-column tiles of the row.
+__device__ __forceinline__ void syr2k_item_any(int item, int t0, int rect_first, int rect_stride, int rect_cols, int& I, int& J64) {
+  if (rect_stride > 0) { I = t0 + rect_first + (item / rect_cols) * rect_stride; J64 = 2 * t0 + item % rect_cols; }
+  else syr2k_item(item, t0, I, J64);
+}
+
 __global__ void __launch_bounds__(DT_THREADS, 2)
 syr2k_lower_kernel(const __grid_constant__ CUtensorMap mapVZ_km, const __grid_constant__ CUtensorMap mapVZ_kn,
-                   double* __restrict__ A, int64_t lda, int n, int t0, int nitems, int nkc, int boff, int krows, double sgn) {
+                   double* __restrict__ A, int64_t lda, int n, int t0, int nitems, int nkc, int boff, int krows, double sgn,
+                   int rect_first, int rect_stride, int rect_cols) {
   extern __shared__ __align__(128) uint8_t dt_raw[];
   const DtSmem sm = dt_setup(dt_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -155,7 +163,7 @@ syr2k_lower_kernel(const __grid_constant__ CUtensorMap mapVZ_km, const __grid_co
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        int I, J64; syr2k_item(item, t0, I, J64);
+        int I, J64; syr2k_item_any(item, t0, rect_first, rect_stride, rect_cols, I, J64);
         for (int kc = 0; kc < nkc; kc++) {
           dt_mbar_wait(sm.empty + stage, phase ^ 1);
           dt_mbar_expect_tx(sm.full + stage, DT_A_KM_BYTES + DT_B_KN_BYTES);
@@ -178,7 +186,7 @@ syr2k_lower_kernel(const __grid_constant__ CUtensorMap mapVZ_km, const __grid_co
     for (int u = 0; u < 4; u++) acc[t][u][0] = acc[t][u][1] = 0.0;
   uint32_t stage = 0, phase = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    int I, J64; syr2k_item(item, t0, I, J64);
+    int I, J64; syr2k_item_any(item, t0, rect_first, rect_stride, rect_cols, I, J64);
     for (int kc = 0; kc < nkc; kc++) {
       dt_mbar_wait(sm.full + stage, phase);
       dt_stage_mma<true, true>(sm.a32(stage), sm.b32(stage), acc, wm, wn, g, q);
@@ -345,7 +353,7 @@ int dt_resident_ctas(eb_ctx* c) {
 
 // Wpart[ks][64][ldw] (ks < ksplit_out) = A[:, t0*128:] * Bt^T restricted to row tiles >= t0.  A: n x n (lda), Bt: 64 x n (ldb).
 int launch_sym_skinny(eb_ctx* c, const double* A, int64_t lda, int n, int t0, const double* Bt, int64_t ldb, double* Wpart, int64_t ldw,
-                      int max_ksplit, int* ksplit_out, int tile_first, int tile_stride) {
+                      int max_ksplit, int* ksplit_out, int tile_first, int tile_stride, bool full_rows) {
   CUtensorMap mk, km, mb;
   int rc;
   if ((rc = make_f64_tensormap(&mk, A, n, n, lda, DT_LD_K, DT_M))) return rc;
@@ -367,22 +375,33 @@ int launch_sym_skinny(eb_ctx* c, const double* A, int64_t lda, int n, int t0, co
   if (const char* e = getenv("EB_DBG_KSPLIT")) best = std::max(1, std::min(atoi(e), max_ksplit));
   *ksplit_out = best;
   const int grid = std::min(ntile * best, slots);
-  sym_skinny_kernel<<<grid, DT_THREADS, DT_SMEM, c->stream>>>(mk, km, mb, Wpart, ldw, n, t0, ntile, best, tile_first, tile_stride);
+  sym_skinny_kernel<<<grid, DT_THREADS, DT_SMEM, c->stream>>>(mk, km, mb, Wpart, ldw, n, t0, ntile, best, tile_first, tile_stride, full_rows ? 1 : 0);
   EB_CHECK_LAUNCH(c);
   return 0;
 }
 
 // A[t0*128:, t0*128:] (lower 128x64 tiles) -= V Z^T + Z V^T with VZ = [Vt(64 rows); Zt(64 rows)] x n (ldv)
-int launch_syr2k_lower(eb_ctx* c, double* A, int64_t lda, int n, int t0, const double* VZ, int64_t ldv) {
+int launch_syr2k_lower(eb_ctx* c, double* A, int64_t lda, int n, int t0, const double* VZ, int64_t ldv, int tile_first, int tile_stride) {
   CUtensorMap km, kn;
   int rc;
   if ((rc = make_f64_tensormap(&km, VZ, 128, n, ldv, DT_LD_M, DT_KC))) return rc;
   if ((rc = make_f64_tensormap(&kn, VZ, 128, n, ldv, DT_LD_N, DT_KC))) return rc;
   const int nt = (n + DT_M - 1) / DT_M - t0;
   if (nt <= 0) return 0;
+  if (tile_stride > 0) {
+    // row-distributed: this rank's row tiles x every 64-column tile of the trailing square (full storage)
+    const int rows = nt > tile_first ? (nt - tile_first + tile_stride - 1) / tile_stride : 0;
+    const int cols = (n + DT_N - 1) / DT_N - 2 * t0;
+    if (rows <= 0 || cols <= 0) return 0;
+    const int nitems = rows * cols;
+    const int grid = std::min(nitems, dt_resident_ctas(c));
+    syr2k_lower_kernel<<<grid, DT_THREADS, DT_SMEM, c->stream>>>(km, kn, A, lda, n, t0, nitems, 4, 64, 128, -1.0, tile_first, tile_stride, cols);
+    EB_CHECK_LAUNCH(c);
+    return 0;
+  }
   const int nitems = nt * (nt + 1);
   const int grid = std::min(nitems, dt_resident_ctas(c));
-  syr2k_lower_kernel<<<grid, DT_THREADS, DT_SMEM, c->stream>>>(km, kn, A, lda, n, t0, nitems, 4, 64, 128, -1.0);
+  syr2k_lower_kernel<<<grid, DT_THREADS, DT_SMEM, c->stream>>>(km, kn, A, lda, n, t0, nitems, 4, 64, 128, -1.0, 0, 0, 0);
   EB_CHECK_LAUNCH(c);
   return 0;
 }
@@ -397,7 +416,7 @@ int launch_syrk_lower_add(eb_ctx* c, double* A, int64_t lda, int n, const double
   const int nt = (n + DT_M - 1) / DT_M;
   const int nitems = nt * (nt + 1);
   const int grid = std::min(nitems, dt_resident_ctas(c));
-  syr2k_lower_kernel<<<grid, DT_THREADS, DT_SMEM, c->stream>>>(km, kn, A, lda, n, 0, nitems, krows / DT_KC, 0, krows, 1.0);
+  syr2k_lower_kernel<<<grid, DT_THREADS, DT_SMEM, c->stream>>>(km, kn, A, lda, n, 0, nitems, krows / DT_KC, 0, krows, 1.0, 0, 0, 0);
   EB_CHECK_LAUNCH(c);
   return 0;
 }

@@ -25,8 +25,8 @@ namespace cg = cooperative_groups;
 namespace eb {
 
 int launch_sym_skinny(eb_ctx* c, const double* A, int64_t lda, int n, int t0, const double* Bt, int64_t ldb, double* Wpart, int64_t ldw,
-                      int max_ksplit, int* ksplit_out, int tile_first = 0, int tile_stride = 1);
-int launch_syr2k_lower(eb_ctx* c, double* A, int64_t lda, int n, int t0, const double* VZ, int64_t ldv);
+                      int max_ksplit, int* ksplit_out, int tile_first = 0, int tile_stride = 1, bool full_rows = false);
+int launch_syr2k_lower(eb_ctx* c, double* A, int64_t lda, int n, int t0, const double* VZ, int64_t ldv, int tile_first = 0, int tile_stride = 0);
 
 constexpr int BW = 64;             // band width after stage 1 == panel width
 constexpr int MAX_KSPLIT = 4;
@@ -802,10 +802,76 @@ __global__ void __launch_bounds__(256) dbg_ref_syr2k_kernel(double* __restrict__
   A[(size_t)row * lda + col] -= s;
 }
 
-// Stage 1 + stage 2: A (n x n, lda, lower triangle + complete diagonal tiles valid; destroyed) -> d, e (unscaled)
-int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, double* e) {
+// ---- row-distributed stage 1 (collective): every rank holds the FULL square and keeps its own 128-row tiles (tile % world == rank)
+// current; W = A22 V and the rank-128 update run on the owned rows only, the 64 x n panel (before its QR) and the 64 x n product
+// block (after it) are summed over the ranks -- the other ranks' rows are zero, so the sum is a gather and every rank ends up with
+// bit-identical V, W, Z and band.  The panel QR and the O(n 64^2) glue run replicated.
+// stage[cc][i] = A[i][col0 + cc] for owned rows i in [row0, n), zero elsewhere (cc < ncols; rows of the other 64 - ncols stay zero)
+__global__ void __launch_bounds__(256) dist_pack_kernel(const double* __restrict__ A, int64_t lda, int n, int row0, int col0, int ncols,
+                                                        int rank, int world, double* __restrict__ stage, int64_t lds) {
+  __shared__ double t[64][65];
+  const int i0 = row0 + blockIdx.x * 64;
+  const bool own = ((i0 >> 7) % world) == rank;           // row0 and the 64-row blocks are 64-aligned: a block lies in one 128-row tile
+  for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
+    const int r = idx >> 6, cc = idx & 63, i = i0 + r;
+    t[r][cc] = (own && i < n && cc < ncols) ? A[(size_t)i * lda + col0 + cc] : 0.0;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
+    const int cc = idx >> 6, r = idx & 63, i = i0 + r;
+    if (i < n) stage[(size_t)cc * lds + i] = t[r][cc];
+  }
+}
+__global__ void __launch_bounds__(256) dist_unpack_kernel(double* __restrict__ A, int64_t lda, int n, int row0, int col0, int ncols,
+                                                          const double* __restrict__ stage, int64_t lds) {
+  __shared__ double t[64][65];
+  const int i0 = row0 + blockIdx.x * 64;
+  for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
+    const int cc = idx >> 6, r = idx & 63, i = i0 + r;
+    t[r][cc] = i < n ? stage[(size_t)cc * lds + i] : 0.0;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
+    const int r = idx >> 6, cc = idx & 63, i = i0 + r;
+    if (i < n && cc < ncols) A[(size_t)i * lda + col0 + cc] = t[r][cc];
+  }
+}
+// Out[c][i] = sum_ks Wpart[ks][c][i] for owned rows i >= i_lo, zero for every other row of [i_zero0, n)
+__global__ void __launch_bounds__(256) dist_combine_kernel(const double* __restrict__ Wpart, int ksplit, int64_t ldw, double* __restrict__ Out,
+                                                           int64_t ldo, int n, int i_zero0, int i_lo, int rank, int world) {
+  const int i = i_zero0 + blockIdx.x * 256 + threadIdx.x, c = blockIdx.y;
+  if (i >= n) return;
+  double v = 0.0;
+  if (i >= i_lo && ((i >> 7) % world) == rank)
+    for (int ks = 0; ks < ksplit; ks++) v += Wpart[((size_t)ks * 64 + c) * ldw + i];
+  Out[(size_t)c * ldo + i] = v;
+}
+
+// all ranks: columns [col0, col0 + ncols) of rows [row0, n) become current everywhere (row0 a multiple of 64)
+static int dist_gather_cols(eb_ctx* c, double* A, int64_t lda, int n, int row0, int col0, int ncols, double* xbuf, int64_t ldx, bool& first) {
   cudaStream_t st = c->stream;
   int rc;
+  double* stage = xbuf + (size_t)64 * ldx;
+  const int nb = (n - row0 + 63) / 64;
+  if (nb <= 0) return 0;
+  if (row0 > 0) EB_CUDA(cudaMemsetAsync(stage, 0, sizeof(double) * 64 * ldx, st));     // rows above row0 must not carry old sums
+  dist_pack_kernel<<<nb, 256, 0, st>>>(A, lda, n, row0, col0, ncols, c->comm.rank, c->comm.world, stage, ldx);
+  EB_CHECK_LAUNCH(c);
+  if ((rc = peer_allreduce_stream(c, PEER_SLOT_W, xbuf, c->chfsi_sum.n, (int64_t)64 * ldx, first, (int64_t)64 * ldx))) return rc;
+  first = false;
+  dist_unpack_kernel<<<nb, 256, 0, st>>>(A, lda, n, row0, col0, ncols, stage, ldx);
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
+// Stage 1 + stage 2: A (n x n, lda, lower triangle + complete diagonal tiles valid; destroyed) -> d, e (unscaled).
+// collective: all ranks of the communicator call with the SAME full symmetric matrix (both triangles valid); see above.
+int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, double* e, bool collective) {
+  cudaStream_t st = c->stream;
+  int rc;
+  const bool dist = collective && c->has_comm && c->comm.world > 1;
+  const int NW = dist ? c->comm.world : 1, me = dist ? c->comm.rank : 0;
+  bool first_exchange = true;
   const int64_t ldv = ((int64_t)n + 7) & ~7ll;
   const int G_max = c->num_sms;
   const int nchunk_max = (n + 255) / 256 + 1;
@@ -830,6 +896,12 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
   w.prog = reinterpret_cast<int*>(W + oInt); w.err = w.prog + n + 8;
   EB_CUDA(cudaMemsetAsync(w.VZ, 0, sizeof(double) * 128 * ldv, st));
   EB_CUDA(cudaMemsetAsync(w.prog, 0, sizeof(int) * ((size_t)n + 16), st));
+  double* xbuf = nullptr;                              // exported: [0, 64 ldv) product block, [64 ldv, 128 ldv) panel stage
+  if (dist) {
+    if ((rc = c->chfsi_sum.ensure((size_t)128 * ldv))) return rc;
+    xbuf = c->chfsi_sum.p;
+    EB_CUDA(cudaMemsetAsync(xbuf, 0, sizeof(double) * 128 * ldv, st));
+  }
 
   // per device, not per process: set on every call (several contexts on different GPUs may live in one process)
   EB_CUDA(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -838,8 +910,11 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
 
   const bool dbg_sync = getenv("EB_DBG_SYNC") != nullptr, dbg_ref_w = getenv("EB_DBG_REF_W") != nullptr,
              dbg_ref_syr2k = getenv("EB_DBG_REF_SYR2K") != nullptr;
+  int j_done = 0;
   for (int j = 0; n - j - BW >= 2; j += BW) {
     const int r0 = j + BW, np = n - r0, t0 = r0 / DT_M;
+    // ---- distributed: the panel (diagonal block included) is current only on the owners of its rows: gather it
+    if (dist && (rc = dist_gather_cols(c, A, lda, n, j, j, BW, xbuf, ldv, first_exchange))) return rc;
     // ---- panel QR
     PanelParams pp;
     pp.A = A; pp.lda = lda; pp.n = n; pp.j = j; pp.VZ = w.VZ; pp.ldv = ldv; pp.T = w.T; pp.gpart = w.gpart; pp.rowk = w.rowk;
@@ -859,6 +934,15 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
     if (dbg_ref_w) {
       dbg_ref_w_kernel<<<dim3((n + 255) / 256, 64), 256, 0, st>>>(A, lda, n, r0, w.VZ, ldv, w.Wt);
       EB_CHECK_LAUNCH(c);
+    } else if (dist) {
+      // owned row tiles only (full rows of the stored square), then the sum over ranks = gather of the 64 x n block
+      if ((rc = launch_sym_skinny(c, A, lda, n, t0, w.VZ, ldv, w.Wpart, ldv, MAX_KSPLIT, &ksplit, (me - t0 % NW + NW) % NW, NW, true))) return rc;
+      dim3 grid((n + 255) / 256, 64);                 // every row: the block is summed over the ranks as a whole, stale rows must be zero
+      dist_combine_kernel<<<grid, 256, 0, st>>>(w.Wpart, ksplit, ldv, xbuf, ldv, n, 0, r0, me, NW);
+      EB_CHECK_LAUNCH(c);
+      if ((rc = peer_allreduce_stream(c, PEER_SLOT_W, xbuf, c->chfsi_sum.n, (int64_t)64 * ldv, first_exchange, 0))) return rc;
+      first_exchange = false;
+      EB_CUDA(cudaMemcpyAsync(w.Wt, xbuf, sizeof(double) * 64 * ldv, cudaMemcpyDeviceToDevice, st));
     } else {
       if ((rc = launch_sym_skinny(c, A, lda, n, t0, w.VZ, ldv, w.Wpart, ldv, MAX_KSPLIT, &ksplit))) return rc;
       dim3 grid((n - i_z0 + 255) / 256, 64);
@@ -878,8 +962,17 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
     if (dbg_ref_syr2k) {
       dbg_ref_syr2k_kernel<<<dim3((n - i_z0 + 255) / 256, n - i_z0), 256, 0, st>>>(A, lda, n, i_z0, w.VZ, ldv);
       EB_CHECK_LAUNCH(c);
+    } else if (dist) {
+      if ((rc = launch_syr2k_lower(c, A, lda, n, t0, w.VZ, ldv, (me - t0 % NW + NW) % NW, NW))) return rc;
     } else if ((rc = launch_syr2k_lower(c, A, lda, n, t0, w.VZ, ldv))) return rc;
     if (dbg_sync) EB_CUDA(cudaStreamSynchronize(st));
+    j_done = j + BW;
+  }
+  if (dist) {
+    // the trailing block that got no panel of its own (2 .. 65 columns): its band entries live with the owners of its rows
+    const int row0 = j_done & ~63;
+    for (int col0 = row0; col0 < n; col0 += 64)
+      if ((rc = dist_gather_cols(c, A, lda, n, row0, col0, std::min(64, n - col0), xbuf, ldv, first_exchange))) return rc;
   }
 
   // ---- stage 2

@@ -823,7 +823,7 @@ static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, do
     dim3 grid((n + 255) / 256, n);
     copy_matrix_kernel<<<grid, 256, 0, st>>>(A_d, lda_in, c->eigA.p, lda, n);
     EB_CHECK_LAUNCH(c);
-    if ((rc = two_stage_tridiag(c, c->eigA.p, lda, n, d, e))) return rc;
+    if ((rc = two_stage_tridiag(c, c->eigA.p, lda, n, d, e, collective && n >= c->opt_dist_min))) return rc;
     EB_CUDA(cudaEventRecord(c->ev[6], st));
     if ((rc = tridiag_spectrum(c, n, d, e, e2, bounds, scale))) return rc;
     EB_CUDA(cudaEventRecord(c->ev[7], st));
@@ -838,7 +838,7 @@ static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, do
     c->zvec_ld = n;
     std::vector<double> th(nvec);
     EB_CUDA(cudaEventRecord(c->ev[8], st));
-    if ((rc = chfsi_top(c, A_d, lda_in, n, nvec, th.data(), c->zvec_d.p, &c->tm.chfsi_iters, &c->tm.chfsi_matvecs, lo0, collective && n >= 4096))) {
+    if ((rc = chfsi_top(c, A_d, lda_in, n, nvec, th.data(), c->zvec_d.p, &c->tm.chfsi_iters, &c->tm.chfsi_matvecs, lo0, collective && n >= c->opt_dist_min))) {
       if (rc != EB_ERR_NUMERIC) return rc;
       // the subspace iteration gave up: take the vectors from the one-stage path (slower, direct)
       const int keep = c->opt_eig_method;

@@ -135,7 +135,10 @@ __device__ __forceinline__ void count_word(uint32_t x, int& n1, int& n2, int& n3
   n3 += __popc(hi & lo);
 }
 
-// One warp per SNP row of the working matrix; warp-shuffle reduction of the three code counts.
+// LPR lanes per SNP row of the working matrix (32 / LPR rows per warp: short rows -- 1.25 KB at 5,000 individuals -- would leave a
+// whole warp with two or three loads in flight); four independent 16-byte loads per lane and trip; shuffle reduction of the three
+// code counts inside the lane group.
+template <int LPR>
 __global__ void __launch_bounds__(256) snp_stats_kernel(const uint8_t* __restrict__ work, int64_t wpitch, int64_t nsnp, int64_t mpad,
                                                         int nrows, int npad, int fancynorm, int altnormstyle, int minallelecnt,
                                                         int maxmissing, const uint8_t* __restrict__ ignore,
@@ -143,26 +146,39 @@ __global__ void __launch_bounds__(256) snp_stats_kernel(const uint8_t* __restric
                                                         int* __restrict__ c1o, int* __restrict__ nmisso, uint8_t* __restrict__ usedo,
                                                         double* __restrict__ xmeano, double* __restrict__ xfancyo,
                                                         double* __restrict__ table, unsigned long long* __restrict__ nused) {
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;                      // rows per warp
+  const int lane = threadIdx.x & (LPR - 1);         // lane inside the row's group
+  const int grp = (threadIdx.x & 31) / LPR;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int vecs = (int)(wpitch >> 4);
   const int padcount = npad - nrows;
-  for (int64_t s = warp; s < mpad; s += nwarps) {
+  // every lane of a warp runs the same number of trips (mpad is a multiple of 128, hence of RPW)
+  for (int64_t s = warp * RPW + grp; s < mpad; s += nwarps * RPW) {
     double t0 = 0, t1 = 0, t2 = 0;
     if (s < nsnp) {
       const uint4* row = reinterpret_cast<const uint4*>(work + s * wpitch);
       int n1 = 0, n2 = 0, n3 = 0;
-      for (int v = lane; v < vecs; v += 32) {
+      int v = lane;
+      for (; v + 3 * LPR < vecs; v += 4 * LPR) {
+        const uint4 q0 = __ldg(row + v), q1 = __ldg(row + v + LPR), q2 = __ldg(row + v + 2 * LPR), q3 = __ldg(row + v + 3 * LPR);
+        count_word(q0.x, n1, n2, n3); count_word(q0.y, n1, n2, n3); count_word(q0.z, n1, n2, n3); count_word(q0.w, n1, n2, n3);
+        count_word(q1.x, n1, n2, n3); count_word(q1.y, n1, n2, n3); count_word(q1.z, n1, n2, n3); count_word(q1.w, n1, n2, n3);
+        count_word(q2.x, n1, n2, n3); count_word(q2.y, n1, n2, n3); count_word(q2.z, n1, n2, n3); count_word(q2.w, n1, n2, n3);
+        count_word(q3.x, n1, n2, n3); count_word(q3.y, n1, n2, n3); count_word(q3.z, n1, n2, n3); count_word(q3.w, n1, n2, n3);
+      }
+      for (; v < vecs; v += LPR) {
         const uint4 q = __ldg(row + v);
         count_word(q.x, n1, n2, n3); count_word(q.y, n1, n2, n3);
         count_word(q.z, n1, n2, n3); count_word(q.w, n1, n2, n3);
       }
+      // groups of one warp may disagree on s < nsnp in the pad tail: synchronise the group's lanes only
+      const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        n1 += __shfl_xor_sync(0xffffffffu, n1, o);
-        n2 += __shfl_xor_sync(0xffffffffu, n2, o);
-        n3 += __shfl_xor_sync(0xffffffffu, n3, o);
+      for (int o = LPR / 2; o > 0; o >>= 1) {
+        n1 += __shfl_xor_sync(gmask, n1, o);
+        n2 += __shfl_xor_sync(gmask, n2, o);
+        n3 += __shfl_xor_sync(gmask, n3, o);
       }
       if (lane == 0) {
         int nmiss = n3 - padcount;
@@ -242,14 +258,21 @@ int launch_pop_counts(eb_ctx* c, const uint8_t* work3, int64_t wp3, int npops, c
 }
 
 int launch_stats(eb_ctx* c, const eb_grm_opts* o) {
-  const int warpsPerBlock = 8;
-  int64_t blocks = (c->mpad + warpsPerBlock - 1) / warpsPerBlock;
+  const int vecs = (int)(c->wpitch >> 4);
+  const int lpr = vecs <= 128 ? 8 : (vecs <= 512 ? 16 : 32);       // lanes per row: ~16 loads per lane for the short rows
+  const int rowsPerBlock = 8 * (32 / lpr);
+  int64_t blocks = (c->mpad + rowsPerBlock - 1) / rowsPerBlock;
   blocks = std::min<int64_t>(blocks, (int64_t)c->num_sms * 16);
   EB_CUDA(cudaMemsetAsync(c->nused_d.p, 0, sizeof(long long), c->stream));
-  snp_stats_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(
-      c->work.p, c->wpitch, c->nsnp, c->mpad, c->nrows, c->npad, o->fancynorm, o->altnormstyle, o->minallelecnt, o->maxmissing,
-      o->snp_ignore ? c->ignore_d.p : nullptr, o->snp_weight ? c->weight_d.p : nullptr, c->c0_d.p, c->c1_d.p, c->nmiss_d.p,
-      c->used_d.p, c->xmean_d.p, c->xfancy_d.p, c->table_d.p, reinterpret_cast<unsigned long long*>(c->nused_d.p));
+#define EB_STATS_LAUNCH(LPR_)                                                                                                      \
+  snp_stats_kernel<LPR_><<<(unsigned)blocks, 256, 0, c->stream>>>(                                                                  \
+      c->work.p, c->wpitch, c->nsnp, c->mpad, c->nrows, c->npad, o->fancynorm, o->altnormstyle, o->minallelecnt, o->maxmissing,      \
+      o->snp_ignore ? c->ignore_d.p : nullptr, o->snp_weight ? c->weight_d.p : nullptr, c->c0_d.p, c->c1_d.p, c->nmiss_d.p,           \
+      c->used_d.p, c->xmean_d.p, c->xfancy_d.p, c->table_d.p, reinterpret_cast<unsigned long long*>(c->nused_d.p))
+  if (lpr == 8) EB_STATS_LAUNCH(8);
+  else if (lpr == 16) EB_STATS_LAUNCH(16);
+  else EB_STATS_LAUNCH(32);
+#undef EB_STATS_LAUNCH
   EB_CHECK_LAUNCH(c);
   return 0;
 }

@@ -429,10 +429,10 @@ int peer_allreduce(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64
 // flags (rows 8 and 9 of the flag buffer, epoch ar_epoch), so a chain of kernels, all-reduces and more kernels stays on the stream --
 // what the collective subspace iteration needs for its hundreds of 64 x n products.  exchange: publish / map `buf` first (host
 // collective; pass true whenever the buffer may have been reallocated, all ranks alike).
-int peer_allreduce_stream(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64_t count, bool exchange) {
+int peer_allreduce_stream(eb_ctx* c, int slot, double* buf, size_t alloc_doubles, int64_t count, bool exchange, int64_t offset) {
   const int W = c->comm.world;
   int rc;
-  if (count & 1) { set_error("peer_allreduce_stream: odd element count"); return EB_ERR_ARG; }
+  if ((count & 1) || (offset & 1)) { set_error("peer_allreduce_stream: odd element count / offset"); return EB_ERR_ARG; }
   if (exchange) {
     if ((rc = peer_exchange(c, slot, buf, alloc_doubles * sizeof(double), (int)(count & 0x7fffffff)))) return rc;
     if ((rc = peer_flags_setup(c))) return rc;
@@ -444,6 +444,7 @@ int peer_allreduce_stream(eb_ctx* c, int slot, double* buf, size_t alloc_doubles
   for (int r = 0; r < W; r++) {
     a.buf[r] = (double*)c->peer[slot].mapped[r];
     if (!a.buf[r]) { set_error("peer_allreduce_stream: buffer of rank %d is not mapped", r); return EB_ERR_STATE; }
+    a.buf[r] += offset;                      // `count` doubles starting `offset` doubles into every rank's exported allocation
   }
   GrmFlagArgs fa;
   if ((rc = flag_args(c, &fa))) return rc;

@@ -163,7 +163,11 @@ int64_t eb_snp_used_count (eb_ctx *);
 /* -------- symmetric eigensolver on the resident GRM: eigvecs(), eigsubs.c:39-55 / dspev_, eigx.c:107 --------
  * lambda[nrows] descending (all eigenvalues of XTX/y); evecs[nvec*nrows], row i = unit eigenvector i.
  * lambda may be NULL (leading vectors only: what the outlier iterations need, smartpca.c:1250) and nvec may be 0
- * (spectrum only). */
+ * (spectrum only).  Sign: every returned vector has its entry of largest magnitude positive (LAPACK's sign is arbitrary; this
+ * convention is deterministic across solver paths and GPUs and is the one POPGEN/example.evec happens to carry).
+ * With a communicator set and the GRM of a sharded eb_grm resident the call is COLLECTIVE: from n = "dist_min" the dense -> band
+ * reduction runs row-distributed (owned 128-row tiles of the products, panel / product block summed over peer memory) and the
+ * subspace iteration splits its block mat-vecs by row tiles; results are bit-identical on every rank. */
 int eb_eig (eb_ctx *, int nvec, double *lambda, double *evecs);
 /* standalone drop-in with the reference's contract (mat row-major n*n, preserved): include/eigsubs.h:6-7 */
 int eb_eigvecs (eb_ctx *, const double *mat, double *evals, double *evecs, int n, int nvec);
@@ -175,7 +179,9 @@ void eigvecs (double *mat, double *evals, double *evecs, int n);
 void eigvals (double *mat, double *evals, int n);
 
 /* eigensolver selection: key "eig_method" = 0 auto | 1 one-stage | 2 two-stage + subspace iteration;
- * "two_stage_min" = n at which auto switches to 2.  Returns EB_ERR_ARG for an unknown key. */
+ * "two_stage_min" = n at which auto switches to 2; "dist_min" = n from which a COLLECTIVE eb_eig (communicator set, GRM from a
+ * sharded eb_grm) splits the band reduction and the subspace iteration over the ranks (default 8192).  Returns EB_ERR_ARG for an
+ * unknown key. */
 int eb_set_option (eb_ctx *, const char *key, int value);
 
 /* testing aid: two-stage tridiagonalisation alone.  d[n], e[n] of the similar tridiagonal (unscaled); band (may be

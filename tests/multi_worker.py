@@ -124,6 +124,7 @@ def main():
     single.upload_packed(Pb, nb); single.set_rows(None); single.grm(want_snp=False)
     ctx.upload_packed(Pb[u0:u1], nb); ctx.set_rows(None); ctx.grm(want_snp=False)
     la, va = single.eig(5)
+    ctx.set_option("dist_min", 2048)          # default 8192: force the row-distributed band reduction / subspace iteration at this n
     lb, vb = ctx.eig(5)
     tm = ctx.timings()
     assert tm["eig_method"] == 2 and tm["chfsi_matvecs"] > 0
