@@ -329,7 +329,8 @@ def run_b200(args):
                        "nused": int(res["nused"]), "lambda_top": [float(x) for x in lam[:3]], "lambda_sum": float(lam.sum()), "tw_top": float(tw[0]),
                        "tw_pvalue_top": float(pv[0]), "coords_ok": bool(ok.all()), "eval_bytes": os.path.getsize(os.path.join(outdir, "bench.eval")),
                        "evec_bytes": os.path.getsize(os.path.join(outdir, "bench.evec")),
-                       "eig_ms": {k: tm[k] for k in ("tridiag_ms", "bisect_ms", "vectors_ms")}, "chfsi_converged": int(tm["chfsi_converged"]),
+                       "eig_ms": {k: tm[k] for k in ("tridiag_ms", "band_ms", "chase_ms", "bisect_ms")},
+                       "tridiag_tflops": 4.0 / 3.0 * float(nind) ** 3 / (tm["tridiag_ms"] * 1e-3) / 1e12 if tm["tridiag_ms"] > 0 else None, "chfsi_converged": int(tm["chfsi_converged"]),
                        "chfsi_resid": float(tm["chfsi_resid"]),
                        "what": "host matrix (pinned) -> eb_upload_packed -> eb_pca_full(numoutevec 10, numoutlieriter 5, all eigenvalues) -> eb_evec_coords -> "
                                "Tracy-Widom -> .eval/.evec files; wall clock, max over ranks"}

@@ -976,6 +976,7 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
   }
 
   // ---- stage 2
+  EB_CUDA(cudaEventRecord(c->ev[10], st));            // end of dense -> band (eb_timings.band_ms / chase_ms)
   band_extract_kernel<<<n, 128, 0, st>>>(A, lda, n, w.AB);
   EB_CHECK_LAUNCH(c);
   if (c->dbg_band_h) {   // testing aid: the band matrix before bulge chasing ([n][128], AB[col][d] = A[col+d][col])

@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(256) sign_fix_kernel(double* __restrict__ Z, i
 static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, double scale, int nvec, double* lambda_h, double* evecs_h, bool collective) {
   cudaStream_t st = c->stream;
   int rc;
-  c->tm.tridiag_ms = c->tm.bisect_ms = c->tm.vectors_ms = 0.f;
+  c->tm.tridiag_ms = c->tm.bisect_ms = c->tm.vectors_ms = c->tm.band_ms = c->tm.chase_ms = 0.f;
   c->tm.chfsi_iters = c->tm.chfsi_matvecs = 0;
   c->tm.chfsi_converged = 1; c->tm.chfsi_resid = 0.f;
   double lo0 = 0.0;                 // smallest eigenvalue (unscaled) when the spectrum was computed: the filter's lower end
@@ -831,6 +831,8 @@ static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, do
     EB_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&c->tm.tridiag_ms, c->ev[5], c->ev[6]);
     cudaEventElapsedTime(&c->tm.bisect_ms, c->ev[6], c->ev[7]);
+    cudaEventElapsedTime(&c->tm.band_ms, c->ev[5], c->ev[10]);
+    cudaEventElapsedTime(&c->tm.chase_ms, c->ev[10], c->ev[6]);
     if (scale > 0.0) lo0 = lambda_h[n - 1] / scale;
   }
   if (nvec > 0) {

@@ -288,7 +288,8 @@ typedef struct {
   int grm_sms;
   int chfsi_converged;          /* 1: every requested pair reached the strict residual tolerance; 0: accepted at the relaxed one */
   float chfsi_resid;            /* largest relative residual |A v - theta v| / |A| among the returned pairs */
-  float exchange_wait_ms;       /* multi-GPU: host time spent waiting for the other ranks before the exchange kernels */
+  float exchange_wait_ms;       /* multi-GPU: time the stream spent waiting for the slowest rank's tiles before the reduce */
+  float band_ms, chase_ms;      /* two-stage tridiagonalisation: dense -> band (DMMA products + panel QR), band -> tridiagonal */
 } eb_timings;
 int eb_get_timings (eb_ctx *, eb_timings * t);
 /* FP64 DMMA / DFMA issue-rate microbenchmarks (TFLOP/s) used as roofline cross-checks */
