@@ -154,6 +154,7 @@ struct eb_ctx {
   size_t grm_recv_need = 0;                 // doubles the current geometry needs in grm_recv
   int grm_geom_npad = 0, grm_geom_nsplit = 0;   // geometry the peers have agreed on
   bool grm_host_sync = false;               // two ranks are contexts of ONE process on ONE device: waits go through the host (see peer.cu)
+  eb::DevBuf<double> pg_part;         // split-K planes of the packed products (fpca_kernels.cu)
   eb::DevBuf<double> fpG, fpB, fpS;   // fastmode buffers that take part in an exchange (persistent: peers map them)
 
   eb_timings tm = {};

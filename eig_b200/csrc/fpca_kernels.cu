@@ -14,48 +14,113 @@
 #include <algorithm>
 #include <cmath>
 #include <vector>
-#include "common.cuh"
+#include "dmma_tile.cuh"
 
 namespace eb {
 
 constexpr int PG_ROWS = 256;      // output rows per CTA (8 warps x 32)
 constexpr int PG_KT = 64;         // K elements per stage
 constexpr int PG_LD = PG_KT + 4;  // dense tile row stride in doubles (== 4 mod 16 -> conflict-free B fragments)
+// TMA ring depth: a stage of the narrow shapes (fastmode: 24 columns) is only ~1.5 us of DMMA work, so the ring runs four stages ahead
+__host__ __device__ constexpr int pg_stages(int nblk) { return nblk <= 4 ? 6 : 4; }
 enum { MODE_XA = 0, MODE_XTB = 1 };
 
 __device__ __forceinline__ void dmma884f(double& c0, double& c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ uint32_t pg_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pg_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pg_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pg_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pg_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pg_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pg_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pg_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "PG_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra PG_DONE_%=;\n"
+      "bra PG_WAIT_%=;\n"
+      "PG_DONE_%=:\n"
+      "}\n" ::"r"(pg_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void pg_tma_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(pg_u32(dst)),
+               "l"(map), "r"(x), "r"(y), "r"(pg_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void pg_bulk_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pg_u32(dst)), "l"(src),
+               "r"(bytes), "r"(pg_u32(bar))
+               : "memory");
+}
+// explicit, volatile shared loads: they keep their program order with respect to the mbarrier waits / arrives (see dmma_tile.cuh)
+__device__ __forceinline__ double pg_lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t pg_lds_u8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 pg_lds_v2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
 }
 
-__device__ __forceinline__ void pg_cp_async16(void* dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void pg_cp_async8(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void pg_cp_async4(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-
-// XTB: work tile [PG_KT snps][64 bytes = 256 individuals], table tile [PG_KT][4]
-// XA : work tile [256 snps][16 bytes = 64 individuals] (row stride 20 B to spread banks), table [256][4] fixed per CTA
+// Stage layout (bytes): dense tile In[NC][PG_LD] doubles | packed tile (XTB: [PG_KT snps][64 B = 256 individuals];
+// XA: [256 snps][16 B = 64 individuals]) | XTB only: decode table [PG_KT][4] doubles.  XA keeps its table (256 rows, fixed per CTA)
+// outside the ring.  Everything arrives by TMA (cp.async.bulk.tensor.2d for the two tiles, cp.async.bulk for the table) into a
+// pg_stages()-deep mbarrier full / empty ring driven by thread 0, which stays two stages short of the ring depth ahead of the consumers -- the same
+// structure as grm_syrk_kernel.  (Round 1 staged with per-thread cp.async into a 2-stage ring with two __syncthreads per stage:
+// DMMA pipe 83 % / 69 % active for X A / X^T B.)
+// The dense box is 4 doubles wider than the 64-element K window, which pads the shared-memory rows to 68 doubles (== 4 mod 16):
+// conflict-free B fragments without a swizzle (the trick of dmma_tile.cuh).
+// grid = (row tiles, k splits): split ks covers K stages [nk ks / nsplit, nk (ks + 1) / nsplit) and writes its own output plane
+// (summed in a fixed order by pg_sum_planes_kernel), so that a few hundred row tiles still give tens of waves over the SMs.
 template <int MODE, int NBLK>
 __global__ void __launch_bounds__(256, 1)
-packed_gemm_kernel(const uint8_t* __restrict__ work, int64_t wpitch, const double* __restrict__ table, int64_t mpad, int npad,
-                   const double* __restrict__ In_t, int64_t ld_in, double* __restrict__ Out_t, int64_t ld_out, int ncols, double oscale) {
+packed_gemm_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapIn, const double* __restrict__ table,
+                   int64_t mpad, int npad, double* __restrict__ Out_t, int64_t ld_out, int64_t plane_stride, int ncols, double oscale,
+                   int nk, int nsplit) {
   constexpr int NC = NBLK * 8;
-  constexpr int XA_STRIDE = 20;
-  constexpr int WBYTES = MODE == MODE_XTB ? PG_KT * 64 : PG_ROWS * XA_STRIDE;
-  extern __shared__ __align__(16) uint8_t pg_smem[];
-  double (*In_s)[NC][PG_LD] = reinterpret_cast<double (*)[NC][PG_LD]>(pg_smem);
-  uint8_t (*W_s)[WBYTES] = reinterpret_cast<uint8_t (*)[WBYTES]>(pg_smem + sizeof(double) * 2 * NC * PG_LD);
-  double* T_s = reinterpret_cast<double*>(pg_smem + sizeof(double) * 2 * NC * PG_LD + 2 * WBYTES);
+  constexpr int PG_STAGES = pg_stages(NBLK);
+  constexpr int IN_BYTES = NC * PG_LD * 8;
+  constexpr int W_BYTES = MODE == MODE_XTB ? PG_KT * 64 : PG_ROWS * 16;
+  constexpr int T_BYTES = MODE == MODE_XTB ? PG_KT * 4 * 8 : 0;
+  constexpr int STAGE_BYTES = IN_BYTES + W_BYTES + T_BYTES;
+  extern __shared__ __align__(128) uint8_t pg_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pg_raw) + 127) & ~uintptr_t(127));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + PG_STAGES * STAGE_BYTES);
+  uint64_t* empty = full + PG_STAGES;
+  double* T_fix = reinterpret_cast<double*>(smem + PG_STAGES * STAGE_BYTES + 2 * PG_STAGES * 8);      // XA: [PG_ROWS][4]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, h = lane >> 4;
   const int64_t r0 = (int64_t)blockIdx.x * PG_ROWS;          // first output row (SNP or individual)
-  const int l0 = blockIdx.y * NC;                             // first output column
-  const int64_t Klen = MODE == MODE_XTB ? mpad : npad;
-  const int nk = (int)(Klen / PG_KT);
+  const int ks = blockIdx.y;
+  const int kb0 = (int)(((long long)nk * ks) / nsplit), kb1 = (int)(((long long)nk * (ks + 1)) / nsplit);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PG_STAGES; s++) { pg_mbar_init(full + s, 1); pg_mbar_init(empty + s, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (MODE == MODE_XA) {
+    for (int idx = threadIdx.x; idx < PG_ROWS * 4; idx += 256) {
+      const int64_t s = r0 + (idx >> 2);
+      T_fix[idx] = s < mpad ? table[s * 4 + (idx & 3)] : 0.0;
+    }
+  }
+  __syncthreads();
 
   double acc[4][NBLK][2];
 #pragma unroll
@@ -63,103 +128,110 @@ packed_gemm_kernel(const uint8_t* __restrict__ work, int64_t wpitch, const doubl
 #pragma unroll
     for (int u = 0; u < NBLK; u++) acc[t][u][0] = acc[t][u][1] = 0.0;
 
-  if (MODE == MODE_XA) {
-    for (int idx = threadIdx.x; idx < PG_ROWS * 4; idx += 256) {
-      const int64_t s = r0 + (idx >> 2);
-      T_s[idx] = s < mpad ? table[s * 4 + (idx & 3)] : 0.0;
-    }
-  }
-
-  // Stage loads are asynchronous copies (cp.async -> SASS LDGSTS): the global-memory latency of stage kb+1 is hidden behind
-  // the DMMAs of stage kb instead of being paid by every thread before it may start computing (the first version staged
-  // through registers: DMMA pipe 69 % / 83 % active for X^T B / X A; see profiles/r1_kernels_ncu.md).
-  auto load_stage = [&](int st, int kb) {
-    const int64_t k0 = (int64_t)kb * PG_KT;
-    // dense tile: NC rows x PG_KT doubles (rows beyond ncols are zero-filled by a zero-length source)
-    for (int idx = threadIdx.x; idx < NC * (PG_KT / 2); idx += 256) {
-      const int l = idx / (PG_KT / 2), kk = (idx % (PG_KT / 2)) * 2;
-      const bool ok = l0 + l < ncols;
-      const double* src = ok ? In_t + (size_t)(l0 + l) * ld_in + k0 + kk : In_t;
-      pg_cp_async16(&In_s[st][l][kk], src, ok ? 16 : 0);
-    }
-    if (MODE == MODE_XTB) {
-      // packed: PG_KT snp rows x 64 bytes (256 individuals starting at r0); beyond the row pitch: all-missing codes
-      for (int idx = threadIdx.x; idx < PG_KT * 4; idx += 256) {
-        const int kk = idx >> 2, part = idx & 3;
-        const int64_t byte0 = r0 / 4 + part * 16;
-        if (byte0 + 16 <= wpitch) pg_cp_async16(&W_s[st][kk * 64 + part * 16], work + (k0 + kk) * wpitch + byte0, 16);
-        else *reinterpret_cast<uint4*>(&W_s[st][kk * 64 + part * 16]) = make_uint4(~0u, ~0u, ~0u, ~0u);
+  // producer cursor (thread 0)
+  int p_kb = kb0, ahead = 0;
+  uint32_t p_stage = 0, p_phase = 0;
+  auto produce = [&]() {
+    while (ahead < PG_STAGES - 2 && p_kb < kb1) {
+      pg_mbar_wait(empty + p_stage, p_phase ^ 1);
+      uint8_t* sb = smem + p_stage * STAGE_BYTES;
+      pg_mbar_expect_tx(full + p_stage, STAGE_BYTES);
+      const int k0 = p_kb * PG_KT;
+      pg_tma_2d(sb, &mapIn, k0, 0, full + p_stage);
+      if (MODE == MODE_XTB) {
+        pg_tma_2d(sb + IN_BYTES, &mapW, (int)(r0 / 4), k0, full + p_stage);
+        pg_bulk_1d(sb + IN_BYTES + W_BYTES, table + (size_t)k0 * 4, T_BYTES, full + p_stage);
+      } else {
+        pg_tma_2d(sb + IN_BYTES, &mapW, k0 / 4, (int)r0, full + p_stage);
       }
-      for (int idx = threadIdx.x; idx < PG_KT * 4; idx += 256) pg_cp_async8(&T_s[st * PG_KT * 4 + idx], table + k0 * 4 + idx);
-    } else {
-      // packed: 256 snp rows x 16 bytes (64 individuals starting at k0); rows are 20 bytes apart in shared memory
-      for (int idx = threadIdx.x; idx < PG_ROWS; idx += 256) {
-        const int64_t s = r0 + idx;
-        uint8_t* dst = &W_s[st][idx * XA_STRIDE];
-        if (s < mpad) {
-          const uint8_t* src = work + s * wpitch + k0 / 4;
-#pragma unroll
-          for (int j = 0; j < 4; j++) pg_cp_async4(dst + 4 * j, src + 4 * j);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; j++) reinterpret_cast<uint32_t*>(dst)[j] = ~0u;
-        }
-      }
+      if (++p_stage == PG_STAGES) { p_stage = 0; p_phase ^= 1; }
+      ahead++; p_kb++;
     }
   };
 
-  load_stage(0, 0);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  for (int kb = 0; kb < nk; kb++) {
-    const int st = kb & 1;
-    if (kb + 1 < nk) load_stage(st ^ 1, kb + 1);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");      // everything but the newest group (stage kb + 1) has landed
-    __syncthreads();
-#pragma unroll 2
+  uint32_t stage = 0, phase = 0;
+  const uint32_t sh = ((3 - (g & 3)) << 1) + (h << 3);
+  for (int kb = kb0; kb < kb1; kb++) {
+    if (threadIdx.x == 0) produce();
+    __syncwarp();
+    pg_mbar_wait(full + stage, phase);
+    const uint32_t sb = pg_u32(smem + stage * STAGE_BYTES);
+    const uint32_t in_s = sb, w_s = sb + IN_BYTES, t_s = sb + IN_BYTES + W_BYTES, tfix = pg_u32(T_fix);
+#pragma unroll(NBLK <= 4 ? 4 : 2)
     for (int kk = 0; kk < PG_KT; kk += 4) {
       double a[4], b[NBLK];
       if (MODE == MODE_XTB) {
-        const uint32_t sh = ((3 - (g & 3)) << 1) + (h << 3);
-        const uint2 w = *reinterpret_cast<const uint2*>(&W_s[st][(kk + q) * 64 + warp * 8]);
-        const double* tk = &T_s[st * PG_KT * 4 + (kk + q) * 4];
+        const uint2 w = pg_lds_v2(w_s + (kk + q) * 64 + warp * 8);
+        const uint32_t tk = t_s + (kk + q) * 32;
         const uint32_t v0 = w.x >> sh, v1 = w.y >> sh;
-        a[0] = tk[v0 & 3]; a[1] = tk[(v0 >> 16) & 3]; a[2] = tk[v1 & 3]; a[3] = tk[(v1 >> 16) & 3];
+        a[0] = pg_lds_f64(tk + ((v0 & 3) << 3)); a[1] = pg_lds_f64(tk + (((v0 >> 16) & 3) << 3));
+        a[2] = pg_lds_f64(tk + ((v1 & 3) << 3)); a[3] = pg_lds_f64(tk + (((v1 >> 16) & 3) << 3));
       } else {
         // individuals k0+kk .. +3 live in byte kk/4 of the 16-byte row segment; this thread's code is q (MSB first)
         const int byte = kk >> 2;
 #pragma unroll
         for (int t = 0; t < 4; t++) {
           const int row = warp * 32 + t * 8 + g;
-          const uint32_t bv = W_s[st][row * XA_STRIDE + byte];
-          a[t] = T_s[row * 4 + ((bv >> ((3 - q) << 1)) & 3)];
+          const uint32_t bv = pg_lds_u8(w_s + row * 16 + byte);
+          a[t] = pg_lds_f64(tfix + row * 32 + (((bv >> ((3 - q) << 1)) & 3) << 3));
         }
       }
 #pragma unroll
-      for (int u = 0; u < NBLK; u++) b[u] = In_s[st][u * 8 + g][kk + q];
+      for (int u = 0; u < NBLK; u++) b[u] = pg_lds_f64(in_s + ((u * 8 + g) * PG_LD + kk + q) * 8);
 #pragma unroll
       for (int t = 0; t < 4; t++)
 #pragma unroll
         for (int u = 0; u < NBLK; u++) dmma884f(acc[t][u][0], acc[t][u][1], a[t], b[u]);
     }
-    __syncthreads();
+    // release the stage (fence + converge + one arrive per warp, see dt_release_stage)
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) pg_mbar_arrive(empty + stage);
+    if (threadIdx.x == 0) ahead--;
+    if (++stage == PG_STAGES) { stage = 0; phase ^= 1; }
   }
   const int64_t rlimit = MODE == MODE_XTB ? npad : mpad;
+  double* out = Out_t + (size_t)ks * plane_stride;
 #pragma unroll
   for (int t = 0; t < 4; t++) {
     const int64_t r = r0 + warp * 32 + t * 8 + g;
     if (r >= rlimit) continue;
 #pragma unroll
     for (int u = 0; u < NBLK; u++) {
-      const int l = l0 + u * 8 + q * 2;
-      if (l < ncols) Out_t[(size_t)l * ld_out + r] = acc[t][u][0] * oscale;
-      if (l + 1 < ncols) Out_t[(size_t)(l + 1) * ld_out + r] = acc[t][u][1] * oscale;
+      const int l = u * 8 + q * 2;
+      if (l < ncols) out[(size_t)l * ld_out + r] = acc[t][u][0] * oscale;
+      if (l + 1 < ncols) out[(size_t)(l + 1) * ld_out + r] = acc[t][u][1] * oscale;
     }
   }
 }
 
+// Out[l][r] = sum over planes (fixed order) of Part[ks][l][r]
+__global__ void __launch_bounds__(256) pg_sum_planes_kernel(const double* __restrict__ Part, int64_t plane_stride, int nsplit, int64_t ld, int64_t rows,
+                                                            double* __restrict__ Out, int64_t ld_out) {
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int l = blockIdx.y;
+  if (r >= rows) return;
+  double v = 0.0;
+  for (int ks = 0; ks < nsplit; ks++) v += Part[(size_t)ks * plane_stride + (size_t)l * ld + r];
+  Out[(size_t)l * ld_out + r] = v;
+}
+
 // view of a 2-bit working matrix [mpad][npad/4] (the PCA rows by default; lsqproj builds one over all listed individuals)
 struct PackedView { const uint8_t* work; int64_t wpitch; int npad; };
+
+PFN_encodeTiled_t get_tensormap_encoder();
+static int make_u8_tensormap(CUtensorMap* map, const uint8_t* base, int64_t rows, int64_t pitch, int boxc, int boxr) {
+  PFN_encodeTiled_t enc = get_tensormap_encoder();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return EB_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)pitch, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch};
+  cuuint32_t box[2] = {(cuuint32_t)boxc, (cuuint32_t)boxr};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(u8 %lld x %lld box %d x %d) failed: %d", (long long)rows, (long long)pitch, boxc, boxr, (int)r); return EB_ERR_CUDA; }
+  return 0;
+}
 
 template <int MODE>
 static int launch_packed_gemm(eb_ctx* c, const double* table, const double* In_t, int64_t ld_in, double* Out_t, int64_t ld_out,
@@ -167,28 +239,51 @@ static int launch_packed_gemm(eb_ctx* c, const double* table, const double* In_t
   const PackedView dflt = {c->work.p, c->wpitch, c->npad};
   const PackedView pv = view ? *view : dflt;
   const int64_t rows = MODE == MODE_XTB ? pv.npad : c->mpad;
+  const int64_t Klen = MODE == MODE_XTB ? c->mpad : pv.npad;
+  const int nk = (int)(Klen / PG_KT);
   const unsigned gx = (unsigned)((rows + PG_ROWS - 1) / PG_ROWS);
+  // k splits: ~24 waves of CTAs over the SMs, at least 16 stages per split
+  int nsplit = (int)std::min<int64_t>(std::min<int64_t>(16, std::max(1, nk / 16)), (24LL * c->num_sms + gx - 1) / gx);
+  nsplit = std::max(1, nsplit);
+  if ((ld_in & 1)) { set_error("packed_gemm: leading dimension of the dense operand must be even"); return EB_ERR_ARG; }
+  CUtensorMap mapW;
+  int rc;
+  if (MODE == MODE_XTB) { if ((rc = make_u8_tensormap(&mapW, pv.work, c->mpad, pv.wpitch, 64, PG_KT))) return rc; }
+  else { if ((rc = make_u8_tensormap(&mapW, pv.work, c->mpad, pv.wpitch, 16, PG_ROWS))) return rc; }
   int done = 0;
   while (done < ncols) {
     const int rem = ncols - done;
     const int nblk = std::min(8, (rem + 7) / 8);
     const int take = std::min(rem, nblk * 8);
-    dim3 grid(gx, 1);
     const double* in = In_t + (size_t)done * ld_in;
     double* out = Out_t + (size_t)done * ld_out;
+    double* dst = out; int64_t plane = 0;
+    if (nsplit > 1) {
+      plane = (int64_t)take * ld_out;
+      if ((rc = c->pg_part.ensure((size_t)nsplit * plane))) return rc;
+      dst = c->pg_part.p;
+    }
+    CUtensorMap mapIn;
+    if ((rc = make_f64_tensormap(&mapIn, in, take, Klen, ld_in, PG_LD, nblk * 8))) return rc;
+    dim3 grid(gx, nsplit);
 #define PG_CASE(NB_)                                                                                                              \
   case NB_: {                                                                                                                     \
-    const size_t smem = sizeof(double) * 2 * (NB_ * 8) * PG_LD + 2 * (MODE == MODE_XTB ? PG_KT * 64 : PG_ROWS * 20) +              \
-                        sizeof(double) * (MODE == MODE_XTB ? 2 * PG_KT * 4 : PG_ROWS * 4);                                        \
+    const size_t smem = (size_t)pg_stages(NB_) * ((NB_ * 8) * PG_LD * 8 + (MODE == MODE_XTB ? PG_KT * 64 + PG_KT * 32 : PG_ROWS * 16)) + \
+                        2 * pg_stages(NB_) * 8 + (MODE == MODE_XA ? PG_ROWS * 32 : 0) + 128;                                         \
     EB_CUDA(cudaFuncSetAttribute(packed_gemm_kernel<MODE, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-    packed_gemm_kernel<MODE, NB_><<<grid, 256, smem, c->stream>>>(pv.work, pv.wpitch, table, c->mpad, pv.npad, in, ld_in, out,    \
-                                                                 ld_out, take, oscale);                                           \
+    packed_gemm_kernel<MODE, NB_><<<grid, 256, smem, c->stream>>>(mapW, mapIn, table, c->mpad, pv.npad, dst, ld_out, plane, take,  \
+                                                                 oscale, nk, nsplit);                                             \
   } break;
     switch (nblk) {
       PG_CASE(1) PG_CASE(2) PG_CASE(3) PG_CASE(4) PG_CASE(5) PG_CASE(6) PG_CASE(7) PG_CASE(8)
     }
 #undef PG_CASE
     EB_CHECK_LAUNCH(c);
+    if (nsplit > 1) {
+      dim3 g2((unsigned)((rows + 255) / 256), take);
+      pg_sum_planes_kernel<<<g2, 256, 0, c->stream>>>(c->pg_part.p, plane, nsplit, ld_out, rows, out, ld_out);
+      EB_CHECK_LAUNCH(c);
+    }
     done += take;
   }
   return 0;
