@@ -910,11 +910,19 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
 
   const bool dbg_sync = getenv("EB_DBG_SYNC") != nullptr, dbg_ref_w = getenv("EB_DBG_REF_W") != nullptr,
              dbg_ref_syr2k = getenv("EB_DBG_REF_SYR2K") != nullptr;
+  // EB_EIG_PROFILE=1: per-phase device time of stage 1 (events around every phase, one sync per panel) on stderr
+  const bool prof = getenv("EB_EIG_PROFILE") != nullptr;
+  cudaEvent_t pe[6] = {};
+  double pacc[5] = {0, 0, 0, 0, 0};
+  if (prof) for (auto& e_ : pe) cudaEventCreate(&e_);
+  auto mark = [&](int i) { if (prof) cudaEventRecord(pe[i], st); };
   int j_done = 0;
   for (int j = 0; n - j - BW >= 2; j += BW) {
     const int r0 = j + BW, np = n - r0, t0 = r0 / DT_M;
     // ---- distributed: the panel (diagonal block included) is current only on the owners of its rows: gather it
+    mark(0);
     if (dist && (rc = dist_gather_cols(c, A, lda, n, j, j, BW, xbuf, ldv, first_exchange))) return rc;
+    mark(1);
     // ---- panel QR
     PanelParams pp;
     pp.A = A; pp.lda = lda; pp.n = n; pp.j = j; pp.VZ = w.VZ; pp.ldv = ldv; pp.T = w.T; pp.gpart = w.gpart; pp.rowk = w.rowk;
@@ -928,6 +936,7 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
     const size_t smem = use_global ? (size_t)(8192 + 512) * 8 : (size_t)rows_per * 512 + SH_EXTRA;
     void* args[] = {&pp};
     if ((rc = coop_launch(c, (const void*)panel_qr_kernel, dim3(G), dim3(256), args, smem))) return rc;
+    mark(2);
     // ---- W = A22 V
     int ksplit = 1;
     const int i_z0 = t0 * DT_M;
@@ -949,6 +958,7 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
       combine_kernel<<<grid, 256, 0, st>>>(w.Wpart, ksplit, ldv, w.Wt, ldv, n, i_z0, r0, 1.0, nullptr, 0.0, nullptr, 0.0, ldv);
       EB_CHECK_LAUNCH(c);
     }
+    mark(3);
     // ---- S = V^T W ; C1 = T ; C2 = -T^T S T / 2 ; Z = W C1 + V C2
     const int gch = gram_chunk(c, n - r0);
     const int nchunk = (n - r0 + gch - 1) / gch;
@@ -958,6 +968,7 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
     EB_CHECK_LAUNCH(c);
     left_mult_kernel<<<(n - i_z0 + 63) / 64, 256, 16384 * 8, st>>>(w.C1, w.Wt, w.C2, w.VZ, ldv, w.VZ + (size_t)64 * ldv, ldv, i_z0, n);
     EB_CHECK_LAUNCH(c);
+    mark(4);
     // ---- A22 -= V Z^T + Z V^T
     if (dbg_ref_syr2k) {
       dbg_ref_syr2k_kernel<<<dim3((n - i_z0 + 255) / 256, n - i_z0), 256, 0, st>>>(A, lda, n, i_z0, w.VZ, ldv);
@@ -966,7 +977,17 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
       if ((rc = launch_syr2k_lower(c, A, lda, n, t0, w.VZ, ldv, (me - t0 % NW + NW) % NW, NW))) return rc;
     } else if ((rc = launch_syr2k_lower(c, A, lda, n, t0, w.VZ, ldv))) return rc;
     if (dbg_sync) EB_CUDA(cudaStreamSynchronize(st));
+    if (prof) {
+      mark(5);
+      EB_CUDA(cudaStreamSynchronize(st));
+      for (int i = 0; i < 5; i++) { float ms = 0; cudaEventElapsedTime(&ms, pe[i], pe[i + 1]); pacc[i] += ms; }
+    }
     j_done = j + BW;
+  }
+  if (prof) {
+    fprintf(stderr, "[eig profile] n %d stage 1: panel gather %.1f ms, panel QR %.1f ms, W = A V (+ sum over ranks) %.1f ms, 64x64 glue %.1f ms, rank-128 update %.1f ms\n", n,
+            pacc[0], pacc[1], pacc[2], pacc[3], pacc[4]);
+    for (auto& e_ : pe) cudaEventDestroy(e_);
   }
   if (dist) {
     // the trailing block that got no panel of its own (2 .. 65 columns): its band entries live with the owners of its rows
