@@ -6,7 +6,8 @@
 // Design (sm_100a):
 //   * FP64 tensor path = mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4); tcgen05 has no f64 kind.
 //   * CTA = 128x128 output tile, 8 warps (2x4, 64x32 each, 64 FP64 accumulators/thread); lane 0 of warp 0 doubles
-//     as the TMA producer.  Lower-triangle tiles only; optional split over SNP chunks into separate partial
+//     as the TMA producer.  Lower-triangle tiles only, walked in bands of 12 tile rows, column by column (tile_order.cuh), so that
+//     the 148 concurrent tiles share ~12 row operands and ~12 column operands in L2; optional split over SNP chunks into separate partial
 //     buffers (deterministic, no atomics) so that small N still fills 148 SMs for many waves.
 //   * Per stage the producer TMA-loads KT=128 SNPs x 32 bytes for the row tile and the column tile
 //     (cp.async.bulk.tensor.2d) and the 128x4 FP64 decode table (cp.async.bulk), mbarrier full/empty ring.
@@ -18,6 +19,7 @@
 #include <string.h>
 #include <algorithm>
 #include "common.cuh"
+#include "tile_order.cuh"
 
 namespace eb {
 
@@ -135,7 +137,7 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restri
       if (!p_open) {
         if (p_item >= nitems) return;
         const int chunk = p_item / ntiles_tri, t = p_item - chunk * ntiles_tri;
-        tri_decode(t, p_ti, p_tj);
+        tile_decode_banded(t, npad / TILE, p_ti, p_tj);
         p_kb = (int)(((long long)nkblocks * chunk) / nsplit);
         p_kb1 = (int)(((long long)nkblocks * (chunk + 1)) / nsplit);
         if (p_kb >= p_kb1) { p_item += gridDim.x; continue; }      // empty chunk (fewer SNP blocks than chunks): nothing to load
@@ -166,7 +168,7 @@ grm_syrk_kernel(const __grid_constant__ CUtensorMap tmap, const double* __restri
   uint32_t stage = 0, phase = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     const int chunk = item / ntiles_tri, t_ = item - chunk * ntiles_tri;
-    int ti, tj; tri_decode(t_, ti, tj);
+    int ti, tj; tile_decode_banded(t_, npad / TILE, ti, tj);      // L2-friendly walk of the triangle (tile_order.cuh)
     const int kb0 = (int)(((long long)nkblocks * chunk) / nsplit), kb1 = (int)(((long long)nkblocks * (chunk + 1)) / nsplit);
     // valid m8 row blocks of this warp (rows beyond nrows are padding and decode to zero anyway)
     int tvalid = (nrows - (ti * TILE + wm * TB * 8) + 7) >> 3;
@@ -431,18 +433,32 @@ int grm_dense_finalize(eb_ctx* c) {
 }
 
 // ---------------------------------------------------------------------------------------------- FP64 microbenchmarks
-__global__ void __launch_bounds__(256) dmma_bench_kernel(double* out, int iters) {
-  double acc[16][2];
+// DMMA issue-rate probe with the instruction stream of the real kernel minus the decode: 8 warps per SM, 8 x 4 m8n8 blocks per warp
+// (64 accumulators per thread, 32 DMMAs per k-step, 8 distinct A and 4 distinct B operands).  (Round 1's probe issued 16 DMMAs with ONE
+// A and ONE B register from 32 warps per SM and read 29.7 TFLOP/s on most leases -- below what grm_syrk_kernel sustains -- so it
+// measured that artificial stream, not the pipe.)
+__global__ void __launch_bounds__(256, 1) dmma_bench_kernel(double* out, int iters) {
+  double acc[8][4][2];
 #pragma unroll
-  for (int i = 0; i < 16; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
-  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int t = 0; t < 8; t++)
+#pragma unroll
+    for (int u = 0; u < 4; u++) { acc[t][u][0] = 0.0; acc[t][u][1] = 0.0; }
+  double a[8], b[4];
+#pragma unroll
+  for (int t = 0; t < 8; t++) a[t] = 1.0 + (threadIdx.x + t) * 1e-9;
+#pragma unroll
+  for (int u = 0; u < 4; u++) b[u] = 1.0 - (threadIdx.x + u) * 1e-9;
   for (int it = 0; it < iters; it++) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) dmma884(acc[i][0], acc[i][1], a, b);
+    for (int t = 0; t < 8; t++)
+#pragma unroll
+      for (int u = 0; u < 4; u++) dmma884(acc[t][u][0], acc[t][u][1], a[t], b[u]);
   }
   double s = 0;
 #pragma unroll
-  for (int i = 0; i < 16; i++) s += acc[i][0] + acc[i][1];
+  for (int t = 0; t < 8; t++)
+#pragma unroll
+    for (int u = 0; u < 4; u++) s += acc[t][u][0] + acc[t][u][1];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 __global__ void __launch_bounds__(256) dfma_bench_kernel(double* out, int iters) {
@@ -463,6 +479,7 @@ __global__ void __launch_bounds__(256) dfma_bench_kernel(double* out, int iters)
 int microbench_fp64(eb_ctx* c, double* dmma, double* dfma) {
   DevBuf<double> out;
   const int blocks = c->num_sms * 4, threads = 256, iters = 20000;
+  const int dblocks = c->num_sms, diters = 40000;      // DMMA probe: one CTA of 8 warps per SM, like grm_syrk_kernel
   int rc;
   if ((rc = out.ensure((size_t)blocks * threads))) return rc;
   cudaEvent_t e0, e1;
@@ -470,14 +487,14 @@ int microbench_fp64(eb_ctx* c, double* dmma, double* dfma) {
   float ms = 0;
   for (int rep = 0; rep < 2; rep++) {
     EB_CUDA(cudaEventRecord(e0, c->stream));
-    dmma_bench_kernel<<<blocks, threads, 0, c->stream>>>(out.p, iters);
+    dmma_bench_kernel<<<dblocks, threads, 0, c->stream>>>(out.p, diters);
     EB_CHECK_LAUNCH(c);
     EB_CUDA(cudaEventRecord(e1, c->stream));
     EB_CUDA(cudaEventSynchronize(e1));
     EB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
   }
-  // per warp per iteration: 16 DMMA x (8*8*4 FMA) x 2 flops
-  *dmma = (double)blocks * (threads / 32) * (double)iters * 16.0 * 512.0 / (ms * 1e-3) / 1e12;
+  // per warp per iteration: 32 DMMA x (8*8*4 FMA) x 2 flops
+  *dmma = (double)dblocks * (threads / 32) * (double)diters * 32.0 * 512.0 / (ms * 1e-3) / 1e12;
   for (int rep = 0; rep < 2; rep++) {
     EB_CUDA(cudaEventRecord(e0, c->stream));
     dfma_bench_kernel<<<blocks, threads, 0, c->stream>>>(out.p, iters);

@@ -23,6 +23,7 @@
 #include <unistd.h>
 #include <algorithm>
 #include "common.cuh"
+#include "tile_order.cuh"
 
 namespace eb {
 
@@ -123,13 +124,6 @@ int peer_exchange(eb_ctx* c, int slot, void* local, size_t bytes, int aux) {
 // set-up of eb_local_comm).  There a lagging rank's cudaFree synchronises the whole device and would wait for the leading
 // rank's spinning kernel, which waits for the lagging rank: the waits then go through the host (stream sync + eb_comm.barrier).
 
-__device__ __forceinline__ void tri_decode32(int t, int& ti, int& tj) {
-  int r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-  while ((r + 1) * (r + 2) / 2 <= t) r++;
-  while (r * (r + 1) / 2 > t) r--;
-  ti = r; tj = t - r * (r + 1) / 2;
-}
-
 constexpr unsigned long long GRM_WAIT_TIMEOUT_NS = 60ull * 1000000000ull;
 constexpr int FLAG_ERR = 3 * 16 + 2 * 16 * 2;     // word index of the error flag
 
@@ -203,7 +197,7 @@ __global__ void __launch_bounds__(256) grm_push_reduce_kernel(double* __restrict
   __shared__ double tile[32][33];
   const int t = rank + blockIdx.x * world;
   if (t >= ntri) return;
-  int ti, tj; tri_decode32(t, ti, tj);
+  int ti, tj; tile_decode_banded(t, npad / TILE, ti, tj);      // same walk as grm_syrk_kernel: tile index t -> position
   const bool diag = ti == tj;
   double* slot0 = recv + (size_t)blockIdx.x * nslots * (TILE * TILE);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -230,7 +224,7 @@ __global__ void __launch_bounds__(256) grm_push_gather_kernel(const GrmReduceArg
   const int t = grp * a.world + (k < a.rank ? k : k + 1);
   if (t >= ntri) return;
   const int owner = t % a.world;
-  int ti, tj; tri_decode32(t, ti, tj);
+  int ti, tj; tile_decode_banded(t, npad / TILE, ti, tj);      // same walk as grm_syrk_kernel: tile index t -> position
   const bool diag = ti == tj;
   const double* src = a.recv[owner] + (size_t)(t / a.world) * nslots * (TILE * TILE);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
