@@ -627,7 +627,7 @@ __global__ void lsq_pairs_kernel(const double* __restrict__ Et, int64_t ld, int6
   Pt[(size_t)pr * ld + s] = s < nsnp ? 1.0 : 0.0;
 }
 // one thread per individual: normal equations -> choldc / cholsl in the reference's operation order (linsubs.c:331-393)
-constexpr int LSQ_KMAX = 16;
+constexpr int LSQ_KMAX = 32;       // numeigs of eb_lsqproj / eb_evec_coords (documented in eigb200.h); the k x k system lives in local memory
 __global__ void __launch_bounds__(128) lsq_solve_kernel(const double* __restrict__ Nt, const double* __restrict__ Rt, int64_t ld, int nlist, int k,
                                                         double* __restrict__ At, int* __restrict__ nvalid, uint8_t* __restrict__ ok) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -716,7 +716,7 @@ int lsqproj_run(eb_ctx* c, const int* indiv, int nlist, const double* ffvecs, co
 //   F_i[s][a]  = sum_t x_ts Enew_i[a][t]                            DMMA GEMM per SNP block against the decoded block
 //   per-sample sums over s (all / observed only) of F_i^2, F_i x_a, F_i F_l or F_i ff_l       reduction kernel
 // and a k x k Cholesky per sample.  mmat is never materialised beyond one SNP block.
-constexpr int SHR_KMAX = 16;
+constexpr int SHR_KMAX = 32;
 
 // (g - ymean) * yfancy of getcolxf (smartpca.c:3564-3597 via fvadjust 2236-2279): no SNP weight; zero rows for unused SNPs
 __global__ void mm_table_kernel(int64_t nsnp, int64_t mpad, int nrows, const int* __restrict__ c0, const int* __restrict__ nmiss,

@@ -91,8 +91,3 @@ class ShardedGrm:
         torch.cuda.synchronize(self.device)
         r["y"], _ = self.ctx.grm_finish()
         return r
-
-
-def _world(group=None):
-    import torch.distributed as dist
-    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1

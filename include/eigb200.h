@@ -211,7 +211,9 @@ typedef struct {
 } eb_pca_result;
 /* xindex_io: in = initial rows, out = surviving rows (nrows_final).  removed_*: per removal (capacity nrows):
  * original individual index, iteration (1-based), eigenvector number, z-score.
- * lambda[nrows_final], evecs[numeigs*nrows_final]; snp_used/xmean/xfancy as in eb_grm for the last pass. */
+ * lambda and evecs are written on EVERY pass with the row count of that pass, so they must hold nrows (the INITIAL count) and
+ * numeigs * nrows doubles; on return the first nrows_final / numeigs * nrows_final entries are the result, packed
+ * [numeigs][nrows_final].  snp_used/xmean/xfancy as in eb_grm for the last pass. */
 int eb_pca_full (eb_ctx *, const eb_pca_opts * opts, int *xindex_io, int nrows,
                  double *lambda, double *evecs, uint8_t * snp_used, double *xmean, double *xfancy,
                  int *removed_index, int *removed_iter, int *removed_vecno, double *removed_score,
@@ -243,7 +245,8 @@ int eb_project (eb_ctx *, const double *evecs, int numeigs, double *ffvecs /* [n
  * indiv[nindiv] ascending indices into 0..numindivs-1 (NULL = 0..nindiv-1): the reference walks all non-ignored
  * individuals, PCA rows or not (projected populations).  acoeffs/bcoeffs [numeigs][nindiv] (smartpca.c:4713,4745);
  * nvalid = rows of the individual's regression; ok = 0 where the reference ignores the individual
- * ("insufficient data", nvalid <= numeigs) -- its coefficients are 0.  Uses xmean/xfancy/used of the last eb_grm. */
+ * ("insufficient data", nvalid <= numeigs) -- its coefficients are 0.  Uses xmean/xfancy/used of the last eb_grm.
+ * Limit: numeigs <= 32 for eb_lsqproj, eb_evec_coords and eb_shrink_coords (EB_ERR_ARG beyond; the reference has no limit). */
 int eb_lsqproj (eb_ctx *, const int *indiv, int nindiv, const double *ffvecs /* [numeigs][nsnp] */ , const double *fxscal,
                 int numeigs, double *acoeffs, double *bcoeffs, int *nvalid, uint8_t * ok);
 /* the .evec values: the whole sequence smartpca.c:1440-1564 (setfvecs, loadings, projections, lsqproj, seteigscale,

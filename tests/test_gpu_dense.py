@@ -68,6 +68,28 @@ def test_dropin_eigvecs_symbols():
             assert np.abs(ev - rl).max() <= 1e-12 * max(1.0, np.abs(w).max())
 
 
+def test_dropin_eigvecs_fills_all_vectors_beyond_8192():
+    """the reference's eigvecs() fills all n vectors at any n (eigsubs.c:39-55); round 1 returned 40 + zeros above n = 8192"""
+    L = capi.lib()
+    n = 8320
+    rs = np.random.RandomState(1)
+    B = rs.randn(n, 300)
+    A = B @ B.T / 300 + np.diag(np.linspace(0.0, 1.0, n))
+    mat = A.copy(); ev = np.empty(n); vec = np.empty((n, n))
+    L.eigvecs(mat.ctypes.data_as(C.c_void_p), ev.ctypes.data_as(C.c_void_p), vec.ctypes.data_as(C.c_void_p), C.c_int(n))
+    assert np.array_equal(mat, A)
+    assert np.all(np.diff(ev) <= 1e-12)
+    nrm = np.linalg.norm(vec, axis=1)
+    assert np.abs(nrm - 1).max() < 1e-10                             # every one of the n rows is a unit vector (none left zero)
+    idx = np.r_[0:4, n // 2:n // 2 + 4, n - 4:n]
+    V = vec[idx]
+    assert np.abs(V @ V.T - np.eye(len(idx))).max() < 1e-9
+    R = A @ V.T - V.T * ev[idx]
+    assert np.abs(R).max() <= 1e-9 * np.abs(ev).max()
+    # sign convention: the entry of largest magnitude of every vector is positive
+    assert np.all(vec[np.arange(n), np.abs(vec).argmax(axis=1)] > 0)
+
+
 def test_dense_syrk_many_tiles_per_cta(ctx):
     """4608 rows: the tensor-core SYRK runs 4-5 output tiles per persistent CTA (see test_two_stage_tridiagonal_many_tiles_per_cta)"""
     n = 4608
