@@ -187,6 +187,18 @@ syr2k_lower_kernel(const __grid_constant__ CUtensorMap mapVZ_km, const __grid_co
   uint32_t stage = 0, phase = 0;
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
     int I, J64; syr2k_item_any(item, t0, rect_first, rect_stride, rect_cols, I, J64);
+    // the tile this item will read-modify-write: pull its 512 lines (128 rows x 512 B) into L2 now, under the DMMA main loop, so
+    // that the epilogue's dependent loads pay L2 latency instead of HBM latency (the main loop is only 4 k-chunks long)
+    {
+      const int tid = threadIdx.x;                 // 128 consumer threads: one row each, 4 lines per row
+      const int row = I * DT_M + tid;
+      if (row < n) {
+        const double* p = A + (size_t)row * lda + (size_t)J64 * DT_N;
+#pragma unroll
+        for (int l = 0; l < 4; l++)
+          if (J64 * DT_N + l * 16 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + l * 16));
+      }
+    }
     for (int kc = 0; kc < nkc; kc++) {
       dt_mbar_wait(sm.full + stage, phase);
       dt_stage_mma<true, true>(sm.a32(stage), sm.b32(stage), acc, wm, wn, g, q);

@@ -280,9 +280,9 @@ __global__ void __launch_bounds__(128) e2_kernel(int n, const double* __restrict
 
 // thread k finds the k-th smallest eigenvalue; output descending: lam[n-1-k]
 __global__ void __launch_bounds__(128) tri_bisect_kernel(int n, const double* __restrict__ d, const double* __restrict__ e2,
-                                                         const double* __restrict__ bounds, double* __restrict__ lam) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
+                                                         const double* __restrict__ bounds, double* __restrict__ lam, int k0, int k1) {
+  const int k = k0 + blockIdx.x * blockDim.x + threadIdx.x;      // eigenvalue indices [k0, k1): a rank's share in a collective solve
+  if (k >= k1) return;
   double lo = bounds[0], hi = bounds[1];
   const double tn = bounds[2];
   const double pivmin = fmax(2.3e-308 * fmax(1.0, tn * tn), 1e-300);
@@ -767,7 +767,9 @@ __global__ void copy_matrix_kernel(const double* __restrict__ src, int64_t lds, 
 
 // ------------------------------------------------------------------------------------------ host driver
 // all eigenvalues of the tridiagonal (d, e; scaled in place by `scale`) -> c->lambda_d descending
-static int tridiag_spectrum(eb_ctx* c, int n, double* d, double* e, double* e2, double* bounds, double scale) {
+// dist (collective solves, after the row-distributed reduction has mapped the exchange block): every rank bisects n / world of the
+// eigenvalues and the vector is summed over the ranks (the other entries are zero) -- bit-identical everywhere
+static int tridiag_spectrum(eb_ctx* c, int n, double* d, double* e, double* e2, double* bounds, double scale, bool dist = false) {
   cudaStream_t st = c->stream;
   scale_de_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, d, e, scale);
   EB_CHECK_LAUNCH(c);
@@ -775,7 +777,21 @@ static int tridiag_spectrum(eb_ctx* c, int n, double* d, double* e, double* e2, 
   EB_CHECK_LAUNCH(c);
   tri_bounds_kernel<<<1, 1024, 0, st>>>(n, d, e, bounds);
   EB_CHECK_LAUNCH(c);
-  tri_bisect_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, c->lambda_d.p);
+  if (dist && c->has_comm && c->comm.world > 1 && c->chfsi_sum.p && c->chfsi_sum.n >= (size_t)n + 2) {
+    const int W = c->comm.world, me = c->comm.rank;
+    const int k0 = (int)((long long)n * me / W), k1 = (int)((long long)n * (me + 1) / W);
+    const int64_t cnt = ((int64_t)n + 1) & ~1ll;
+    int rc;
+    EB_CUDA(cudaMemsetAsync(c->chfsi_sum.p, 0, sizeof(double) * cnt, st));
+    if (k1 > k0) {
+      tri_bisect_kernel<<<(k1 - k0 + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, c->chfsi_sum.p, k0, k1);
+      EB_CHECK_LAUNCH(c);
+    }
+    if ((rc = peer_allreduce_stream(c, PEER_SLOT_W, c->chfsi_sum.p, c->chfsi_sum.n, cnt, false, 0))) return rc;
+    EB_CUDA(cudaMemcpyAsync(c->lambda_d.p, c->chfsi_sum.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  tri_bisect_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, c->lambda_d.p, 0, n);
   EB_CHECK_LAUNCH(c);
   return 0;
 }
@@ -825,7 +841,7 @@ static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, do
     EB_CHECK_LAUNCH(c);
     if ((rc = two_stage_tridiag(c, c->eigA.p, lda, n, d, e, collective && n >= c->opt_dist_min))) return rc;
     EB_CUDA(cudaEventRecord(c->ev[6], st));
-    if ((rc = tridiag_spectrum(c, n, d, e, e2, bounds, scale))) return rc;
+    if ((rc = tridiag_spectrum(c, n, d, e, e2, bounds, scale, collective && n >= c->opt_dist_min))) return rc;
     EB_CUDA(cudaEventRecord(c->ev[7], st));
     EB_CUDA(cudaMemcpyAsync(lambda_h, c->lambda_d.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     EB_CUDA(cudaStreamSynchronize(st));
