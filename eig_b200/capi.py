@@ -59,7 +59,7 @@ EXPORTS = [
     "eb_microbench_fp64", "eb_set_option", "eb_debug_tridiag", "eb_lsqproj", "eb_evec_coords", "eb_pop_counts", "eb_hash_ids", "eb_packed_file_header", "eb_upload_packed_file",
     "eb_download_packed", "eb_write_eval", "eb_write_evec", "eb_write_grm", "eb_grm_dense_begin", "eb_grm_dense_add", "eb_grm_dense_end", "eigvecs", "eigvals",
     "eb_set_comm", "eb_peer_allreduce_test", "eb_snp_used_count", "eb_shrink_coords", "eb_debug_gemm", "eb_local_comm_create", "eb_local_comm_get", "eb_local_comm_destroy", "eb_numgtz", "eb_tw_stats", "eb_tw_tail",
-    "eb_setgval_packed", "eb_unsetgval", "kjg_fpca", "eb_write_grm_bin",
+    "eb_setgval_packed", "eb_unsetgval", "kjg_fpca", "eb_write_grm_bin", "eb_grm_popfill",
 ]
 
 _lib = None
@@ -322,6 +322,24 @@ class Context:
             if want_xtx:
                 r["XTX"] = xtx
         r["nused"] = nused.value
+        return r
+
+    def grm_popfill(self, xtypes, npops, fancynorm=1, altnormstyle=1, minallelecnt=1, maxmissing=9999999, snp_ignore=None, snp_weight=None,
+                    want_xtx=False):
+        """usepopsformissing: YES -- eb_grm_popfill (getcolxz with the population fill, dense path, all on the device)"""
+        o = self._opts(fancynorm, altnormstyle, minallelecnt, maxmissing, snp_ignore, snp_weight)
+        xt = np.ascontiguousarray(xtypes, np.int32)
+        assert len(xt) == self.nrows
+        m = self.nsnp
+        r = dict(c0=np.empty(m, np.int32), c1=np.empty(m, np.int32), nmiss=np.empty(m, np.int32), used=np.empty(m, np.uint8),
+                 xmean=np.empty(m), xfancy=np.empty(m))
+        y = C.c_double(0); nused = C.c_int64(0)
+        xtx = np.empty((self.nrows, self.nrows)) if want_xtx else None
+        _chk(lib().eb_grm_popfill(self.h, C.byref(o), _p(xt), C.c_int(npops), *[_p(r[k]) for k in ("c0", "c1", "nmiss", "used", "xmean", "xfancy")],
+                                  C.byref(y), C.byref(nused), _p(xtx)))
+        r["y"] = y.value; r["nused"] = nused.value
+        if want_xtx:
+            r["XTX"] = xtx
         return r
 
     def snp_used_count(self):

@@ -315,6 +315,7 @@ static int grm_pass(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* n
   cudaEventElapsedTime(&c->tm.finalize_ms, c->ev[3], c->ev[4]);
   c->grm_valid = true;
   c->grm_collective = peer;
+  c->grm_popfill = false;
   return 0;
 }
 
@@ -361,6 +362,54 @@ int eb_grm(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* nmiss, uin
            double* y_out, int64_t* nused_out, double* XTX_host) {
   int rc;
   if ((rc = grm_pass(c, opts, c0, c1, nmiss, used, xmean, xfancy, nused_out, c && c->has_comm))) return rc;
+  return eb_grm_finish(c, y_out, XTX_host);
+}
+
+// ---- usepopsformissing: YES.  getcolxz (smartpca.c:3129-3216) fills a missing genotype with the mean of the individual's population
+// before fvadjust, which makes the columns arbitrary FP64 values: the reference then takes its dense path (smartpca.c:995-1014,
+// domult_increment_normal).  Here the per-population sums, the fill, the normalisation and the drop rule run on the device
+// (popfill_stats_kernel), the FP64 columns are materialised 1024 SNPs at a time in device memory (popfill_cols_kernel) and go
+// through the dense tensor-core SYRK -- nothing but the per-SNP outputs crosses PCIe.
+int eb_grm_popfill(eb_ctx* c, const eb_grm_opts* opts, const int* xtypes, int npops, int* c0, int* c1, int* nmiss, uint8_t* used,
+                   double* xmean, double* xfancy, double* y_out, int64_t* nused_out, double* XTX_host) {
+  int rc;
+  if ((rc = need_rows(c, "eb_grm_popfill"))) return rc;
+  if (!opts || !xtypes || npops < 1) { set_error("eb_grm_popfill: bad argument"); return EB_ERR_ARG; }
+  if (c->has_comm) { set_error("eb_grm_popfill: not available on a sharded context (the dense path is not collective)"); return EB_ERR_STATE; }
+  if (c->nrows < 2) { set_error("eb_grm_popfill: need at least 2 rows"); return EB_ERR_ARG; }
+  if ((rc = stage_opts(c, opts))) return rc;
+  DevBuf<int> xt_d, nmiss_after;
+  DevBuf<double> fill;
+  const size_t plane = (size_t)c->npad * c->npad;
+  if ((rc = xt_d.ensure(c->npad)) || (rc = nmiss_after.ensure(c->mpad)) || (rc = fill.ensure((size_t)c->mpad * npops)) ||
+      (rc = c->partial.ensure(plane)) || (rc = c->xtx.ensure(plane)) || (rc = c->trace_d.ensure(1)) ||
+      (rc = c->dense_blk.ensure((size_t)1024 * c->npad)))
+    return rc;
+  std::vector<int> xt(c->npad, -1);
+  for (int i = 0; i < c->nrows; i++) xt[i] = xtypes[i];
+  EB_CUDA(cudaMemcpyAsync(xt_d.p, xt.data(), sizeof(int) * c->npad, cudaMemcpyHostToDevice, c->stream));
+  EB_CUDA(cudaMemsetAsync(c->partial.p, 0, sizeof(double) * plane, c->stream));
+  EB_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  if ((rc = launch_popfill_stats(c, opts, xt_d.p, npops, nmiss_after.p, fill.p))) return rc;
+  EB_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  EB_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  for (int64_t s0 = 0; s0 < c->mpad; s0 += 1024) {
+    const int nb = (int)std::min<int64_t>(1024, c->mpad - s0);       // mpad is a multiple of 128: whole k-chunks of 32
+    if ((rc = launch_popfill_cols(c, s0, nb, xt_d.p, npops, fill.p, c->dense_blk.p))) return rc;
+    if ((rc = launch_syrk_lower_add(c, c->partial.p, c->npad, c->npad, c->dense_blk.p, c->npad, nb))) return rc;
+  }
+  EB_CUDA(cudaEventRecord(c->ev[3], c->stream));
+  c->nsplit = 1; c->grm_grid = 0;
+  if ((rc = grm_dense_finalize(c))) return rc;
+  EB_CUDA(cudaEventRecord(c->ev[4], c->stream));
+  // per-SNP outputs: nmiss is the count AFTER the fill (what getcolxz returns); the device keeps the raw count for later passes
+  if (nmiss) EB_CUDA(cudaMemcpyAsync(nmiss, nmiss_after.p, sizeof(int) * (size_t)c->nsnp, cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = fetch_snp_outputs(c, c0, c1, nullptr, used, xmean, xfancy, nused_out))) return rc;
+  cudaEventElapsedTime(&c->tm.stats_ms, c->ev[0], c->ev[1]);
+  cudaEventElapsedTime(&c->tm.grm_ms, c->ev[2], c->ev[3]);
+  cudaEventElapsedTime(&c->tm.finalize_ms, c->ev[3], c->ev[4]);
+  c->nused_total = c->nused;
+  c->grm_valid = true; c->grm_collective = false; c->grm_popfill = true;
   return eb_grm_finish(c, y_out, XTX_host);
 }
 
@@ -650,6 +699,7 @@ int eb_project(eb_ctx* c, const double* evecs, int numeigs, double* ffvecs, doub
   int rc;
   if ((rc = need_rows(c, "eb_project"))) return rc;
   if (!c->grm_valid) { set_error("eb_project: run eb_grm first (needs the per-SNP normalisation)"); return EB_ERR_STATE; }
+  if (c->grm_popfill) { set_error("eb_project: the resident GRM was built with usepopsformissing (eb_grm_popfill); its projection passes stay on the host"); return EB_ERR_STATE; }
   return project_run(c, evecs, numeigs, ffvecs, fxvecs, fxscal);
 }
 
@@ -658,6 +708,7 @@ int eb_lsqproj(eb_ctx* c, const int* indiv, int nindiv, const double* ffvecs, co
   int rc;
   if ((rc = need_rows(c, "eb_lsqproj"))) return rc;
   if (!c->grm_valid) { set_error("eb_lsqproj: run eb_grm first (needs the per-SNP normalisation)"); return EB_ERR_STATE; }
+  if (c->grm_popfill) { set_error("eb_lsqproj: the resident GRM was built with usepopsformissing (eb_grm_popfill); its projection passes stay on the host"); return EB_ERR_STATE; }
   if (!ffvecs || !fxscal || nindiv <= 0) { set_error("eb_lsqproj: bad argument"); return EB_ERR_ARG; }
   std::vector<int> all;
   if (!indiv) { all.resize(nindiv); for (int i = 0; i < nindiv; i++) all[i] = i; indiv = all.data(); }
@@ -704,6 +755,7 @@ int eb_shrink_coords(eb_ctx* c, int numeigs, int newshrink, double* coords, doub
   if ((rc = need_rows(c, "eb_shrink_coords"))) return rc;
   if (!c->grm_valid || c->y <= 0.0) { set_error("eb_shrink_coords: run eb_grm first (needs the resident GRM and the per-SNP normalisation)"); return EB_ERR_STATE; }
   if (!coords || !lambda_out) { set_error("eb_shrink_coords: null argument"); return EB_ERR_ARG; }
+  if (c->grm_popfill) { set_error("eb_shrink_coords: not available after eb_grm_popfill"); return EB_ERR_STATE; }
   return shrink_run(c, numeigs, newshrink, coords, lambda_out, ok);
 }
 

@@ -123,6 +123,7 @@ struct eb_ctx {
   bool dense_open = false;
   int nsplit = 1;
   bool grm_valid = false;
+  bool grm_popfill = false;       // the resident GRM came from eb_grm_popfill: the packed-table projection passes do not apply
   bool grm_collective = false;    // the resident GRM is the reduced matrix of a sharded pass: identical on every rank of the communicator
   double y = 0.0;                 // trace/(nrows-1)
   int64_t nused = 0;              // SNPs of THIS shard that entered XTX
@@ -168,6 +169,8 @@ int launch_gather_into(eb_ctx* c, const int* list_d, int nlist, uint8_t* dst, in
 int launch_stats(eb_ctx* c, const eb_grm_opts* o);
 int launch_pop_counts(eb_ctx* c, const uint8_t* work3, int64_t wp3, int npops, const int* seg_word0_d, int* out_d);
 int launch_indiv_counts(eb_ctx* c, const uint8_t* keep_d, int* out_d);
+int launch_popfill_stats(eb_ctx* c, const eb_grm_opts* o, const int* xt_d, int npops, int* nmiss_after_d, double* fill_d);
+int launch_popfill_cols(eb_ctx* c, int64_t s0, int nb, const int* xt_d, int npops, const double* fill_d, double* blk);
 int launch_synth(eb_ctx* c, uint8_t* dst, int64_t nsnp, int64_t pitch, int numindivs, uint64_t seed, int64_t s0,
                  double missing, int npops, double delta);
 // grm_kernel.cu

@@ -277,6 +277,148 @@ int launch_stats(eb_ctx* c, const eb_grm_opts* o) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------- usepopsformissing
+// getcolxz with usepopsformissing (smartpca.c:3129-3216) + fvadjust (2236-2279) for every SNP: a missing genotype of an individual
+// whose population has data at the SNP takes that population's mean; mean / scale are then taken over observed AND filled values.
+// One warp per SNP of the working matrix; per-population sums live in the warp's slice of shared memory (integer atomics).
+// Outputs per SNP: c0, c1 (observed genotypes only), nmiss AFTER the fill (-1: no value at all), used, xmean, xfancy, the 3-entry
+// table of the observed genotypes {(g - ymean) yfancy w, .., 0} and the fill values fill[s][k] = (mean_k - ymean) yfancy w (0 when
+// population k has no data at s).  The filled sum is accumulated population by population (the reference adds row by row): the
+// results agree to rounding, not bit for bit -- the dense path's bar is 1e-11 relative on the GRM.
+__global__ void __launch_bounds__(256) popfill_stats_kernel(const uint8_t* __restrict__ work, int64_t wpitch, int64_t nsnp, int64_t mpad, int nrows,
+                                                            const int* __restrict__ xt, int npops, int fancynorm, int altnormstyle, int minallelecnt,
+                                                            int maxmissing, const uint8_t* __restrict__ ignore, const double* __restrict__ weight,
+                                                            int* __restrict__ c0o, int* __restrict__ c1o, int* __restrict__ nmisso, int* __restrict__ nmiss0o,
+                                                            uint8_t* __restrict__ usedo, double* __restrict__ xmeano, double* __restrict__ xfancyo,
+                                                            double* __restrict__ table, double* __restrict__ fill, unsigned long long* __restrict__ nused) {
+  extern __shared__ int pf_sm[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int* psum = pf_sm + (size_t)wib * 3 * npops;
+  int* pnum = psum + npops;
+  int* pmis = pnum + npops;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int words = (int)(wpitch >> 2);
+  for (int64_t s = warp; s < mpad; s += nwarps) {
+    for (int k = lane; k < 3 * npops; k += 32) psum[k] = 0;
+    __syncwarp();
+    int c0 = 0, nobs = 0, nmiss0 = 0, lost = 0;          // lost: missing genotypes of individuals outside every population
+    if (s < nsnp) {
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(work + s * wpitch);
+      for (int w = lane; w < words; w += 32) {
+        const uint32_t x = __ldg(row + w);
+        const int j0 = w * 16;
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+          const int j = j0 + t;
+          if (j >= nrows) break;
+          const int code = (x >> (((t >> 2) << 3) + ((3 - (t & 3)) << 1))) & 3;
+          const int k = xt[j];
+          if (code < 3) {
+            c0 += code; nobs++;
+            if (k >= 0 && k < npops) { atomicAdd(psum + k, code); atomicAdd(pnum + k, 1); }
+          } else {
+            nmiss0++;
+            if (k >= 0 && k < npops) atomicAdd(pmis + k, 1); else lost++;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o); nobs += __shfl_xor_sync(0xffffffffu, nobs, o);
+      nmiss0 += __shfl_xor_sync(0xffffffffu, nmiss0, o); lost += __shfl_xor_sync(0xffffffffu, lost, o);
+    }
+    __syncwarp();
+    double fsum = 0.0; int filled = 0, remain = 0;
+    for (int k = lane; k < npops; k += 32) {
+      if (pnum[k] > 0) { fsum += (double)pmis[k] * __ddiv_rn((double)psum[k], (double)pnum[k]); filled += pmis[k]; }
+      else remain += pmis[k];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      fsum += __shfl_xor_sync(0xffffffffu, fsum, o); filled += __shfl_xor_sync(0xffffffffu, filled, o);
+      remain += __shfl_xor_sync(0xffffffffu, remain, o);
+    }
+    remain += lost;
+    // every lane holds the same totals: the normalisation is computed redundantly, lane 0 writes the per-SNP scalars
+    int a = c0, b = 2 * nobs - c0, tt = remain;
+    double ym = 0.0, yf = 0.0, xm = 0.0;
+    const double ynum = (double)(nobs + filled), ysum = (double)c0 + fsum;
+    bool drop;
+    if (!(ynum > 0.0) || s >= nsnp) { a = -1; b = -1; tt = -1; drop = true; }
+    else {
+      ym = __ddiv_rn(ysum, ynum);
+      yf = 1.0;
+      if (fancynorm) {
+        double p = __dmul_rn(0.5, ym);
+        if (!altnormstyle) p = __ddiv_rn(__dadd_rn(ysum, 1.0), __dadd_rn(__dmul_rn(2.0, ynum), 2.0));
+        const double y = __dmul_rn(p, __dadd_rn(1.0, -p));
+        if (y > 0.0) yf = __ddiv_rn(1.0, __dsqrt_rn(y));
+      }
+      xm = __dmul_rn(ym, yf);
+      const int t = a < b ? a : b;
+      drop = (t < minallelecnt) || (tt > maxmissing) || (t == 0);
+    }
+    if (s < nsnp && ignore && ignore[s]) { drop = true; xm = 0.0; yf = 0.0; }
+    const double w = (!drop && weight) ? weight[s] : 1.0;
+    for (int k = lane; k < npops; k += 32)
+      fill[(size_t)s * npops + k] = (!drop && pnum[k] > 0) ? __dmul_rn(__dmul_rn(__dadd_rn(__ddiv_rn((double)psum[k], (double)pnum[k]), -ym), yf), w) : 0.0;
+    if (lane == 0) {
+      double t0 = 0, t1 = 0, t2 = 0;
+      if (!drop) {
+        t0 = __dmul_rn(__dmul_rn(-ym, yf), w); t1 = __dmul_rn(__dmul_rn(__dadd_rn(1.0, -ym), yf), w); t2 = __dmul_rn(__dmul_rn(__dadd_rn(2.0, -ym), yf), w);
+      }
+      reinterpret_cast<double4*>(table)[s] = make_double4(t0, t1, t2, 0.0);
+      if (s < nsnp) {
+        c0o[s] = a; c1o[s] = b; nmisso[s] = tt; nmiss0o[s] = nmiss0; usedo[s] = drop ? 0 : 1;
+        xmeano[s] = xm; xfancyo[s] = (tt < 0) ? 0.0 : yf;
+        if (!drop) atomicAdd(nused, 1ull);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// FP64 columns of SNPs [s0, s0 + nb) -> blk[b][i] (row pitch npad): table value of an observed genotype, the population's fill value
+// for a missing one, zero in the pad
+__global__ void __launch_bounds__(256) popfill_cols_kernel(const uint8_t* __restrict__ work, int64_t wpitch, int64_t s0, int nb, int nrows, int npad,
+                                                           const int* __restrict__ xt, int npops, const double* __restrict__ table,
+                                                           const double* __restrict__ fill, double* __restrict__ blk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= npad || b >= nb) return;
+  const int64_t s = s0 + b;
+  double v = 0.0;
+  if (i < nrows) {
+    const int code = (work[s * wpitch + (i >> 2)] >> ((3 - (i & 3)) << 1)) & 3;
+    if (code < 3) v = table[s * 4 + code];
+    else { const int k = xt[i]; if (k >= 0 && k < npops) v = fill[(size_t)s * npops + k]; }
+  }
+  blk[(size_t)b * npad + i] = v;
+}
+
+int launch_popfill_stats(eb_ctx* c, const eb_grm_opts* o, const int* xt_d, int npops, int* nmiss_after_d, double* fill_d) {
+  const int warps = 8;
+  const size_t smem = sizeof(int) * warps * 3 * (size_t)npops;
+  if (smem > 200 * 1024) { set_error("usepopsformissing: too many populations (%d)", npops); return EB_ERR_ARG; }
+  EB_CUDA(cudaFuncSetAttribute(popfill_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+  int64_t blocks = std::min<int64_t>((c->mpad + warps - 1) / warps, (int64_t)c->num_sms * 8);
+  EB_CUDA(cudaMemsetAsync(c->nused_d.p, 0, sizeof(long long), c->stream));
+  popfill_stats_kernel<<<(unsigned)blocks, 256, smem, c->stream>>>(
+      c->work.p, c->wpitch, c->nsnp, c->mpad, c->nrows, xt_d, npops, o->fancynorm, o->altnormstyle, o->minallelecnt, o->maxmissing,
+      o->snp_ignore ? c->ignore_d.p : nullptr, o->snp_weight ? c->weight_d.p : nullptr, c->c0_d.p, c->c1_d.p, nmiss_after_d, c->nmiss_d.p,
+      c->used_d.p, c->xmean_d.p, c->xfancy_d.p, c->table_d.p, fill_d, reinterpret_cast<unsigned long long*>(c->nused_d.p));
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
+int launch_popfill_cols(eb_ctx* c, int64_t s0, int nb, const int* xt_d, int npops, const double* fill_d, double* blk) {
+  dim3 grid((c->npad + 255) / 256, nb);
+  popfill_cols_kernel<<<grid, 256, 0, c->stream>>>(c->work.p, c->wpitch, s0, nb, c->nrows, c->npad, xt_d, npops, c->table_d.p, fill_d, blk);
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- per-individual counts
 // thread = one raw byte column (4 individuals); blockIdx.y strides over SNPs; integer atomics (order-independent).
 __global__ void __launch_bounds__(256) indiv_counts_kernel(const uint8_t* __restrict__ raw, int64_t raw_pitch, int64_t nsnp,

@@ -114,6 +114,17 @@ typedef struct {
 int eb_grm (eb_ctx *, const eb_grm_opts * opts, int *c0, int *c1, int *nmiss, uint8_t * used,
             double *xmean, double *xfancy, double *y_out, int64_t * nused_out, double *XTX_host);
 
+/* usepopsformissing: YES (smartpca.c:2150): getcolxz (smartpca.c:3129-3216) replaces a missing genotype by the mean of the
+ * individual's population at that SNP (when the population has data) before fvadjust (2236-2279), so mean and scale are taken over
+ * observed and filled values and the columns are arbitrary FP64 numbers -- the reference's dense path (smartpca.c:995-1014).  All of
+ * it runs on the device; the columns never exist on the host.  xtypes[nrows]: population of every current row, 0..npops-1 (other
+ * values: no population, stays missing).  Outputs as eb_grm, except nmiss = genotypes still missing AFTER the fill (getcolxz's
+ * return value) and that xmean / xfancy agree with the reference to rounding, not bit for bit (the reference adds the filled
+ * values row by row, the kernel population by population).  The GRM stays resident for eb_eig; the packed-table passes
+ * (eb_project, eb_lsqproj, eb_evec_coords, eb_shrink_coords) refuse to run on it.  Not collective. */
+int eb_grm_popfill (eb_ctx *, const eb_grm_opts * opts, const int *xtypes, int npops, int *c0, int *c1, int *nmiss, uint8_t * used,
+                    double *xmean, double *xfancy, double *y_out, int64_t * nused_out, double *XTX_host);
+
 /* dense path: getcolxz + domult_increment_normal + block_increment_normal (smartpca.c:3129-3216, 3531-3561, 3498-3528),
  * which the reference takes when usepopsformissing / ldregress make the normalised columns arbitrary FP64 values
  * (smartpca.c:995-1014).  The host keeps producing tblock (nblock rows of nrows doubles, smartpca.c:1198-1218); each call

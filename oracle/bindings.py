@@ -298,6 +298,19 @@ def ref_dense_grm(tblock, blocksize=1024, nthreads=4):
     return out
 
 
+def ref_popfill_cols(packed, numindivs, xtypes, npops, xindex=None, fancynorm=1, altnormstyle=1):
+    """usepopsformissing: the reference's getcolxz for every SNP -> columns [nsnp][nrows], c0, c1, nmiss (after the fill), xmean, xfancy"""
+    nsnp, rlen = packed.shape; xi = _xi(xindex, numindivs); n = len(xi)
+    xt = np.ascontiguousarray(xtypes, np.int32)
+    r = dict(c0=np.empty(nsnp, np.int32), c1=np.empty(nsnp, np.int32), nmiss=np.empty(nsnp, np.int32), xmean=np.zeros(nsnp), xfancy=np.zeros(nsnp),
+             cols=np.zeros((nsnp, n)))
+    rc = ref().refh_popfill_cols(packed.ctypes.data_as(C.c_void_p), C.c_long(nsnp), C.c_long(rlen), C.c_int(numindivs), xi.ctypes.data_as(C.c_void_p),
+                                 xt.ctypes.data_as(C.c_void_p), C.c_int(n), C.c_int(npops), C.c_int(fancynorm), C.c_int(altnormstyle),
+                                 *[r[k].ctypes.data_as(C.c_void_p) for k in ("c0", "c1", "nmiss", "xmean", "xfancy", "cols")])
+    assert rc == 0
+    return r
+
+
 def port_pop_counts(packed, numindivs, xtypes, npops, xindex=None):
     nsnp, rlen = packed.shape; xi = _xi(xindex, numindivs); xt = np.ascontiguousarray(xtypes, np.int32)
     out = np.empty((nsnp, npops, 3), np.int32)

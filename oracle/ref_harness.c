@@ -279,6 +279,25 @@ int refh_dense_grm (const double *tblock_all, long ncols, int nrows, int blocksi
   return 0;
 }
 
+/* usepopsformissing: the reference's getcolxz (smartpca.c:3129-3216) for every SNP with the global switched on: normalised FP64
+ * columns cols[nsnp][nrows] (population means filled in for missing genotypes), n0 / n1, the missing count after the fill, xmean, xfancy */
+int refh_popfill_cols (const unsigned char *packed, long nsnp, long rl, int nind, const int *xindex_in, const int *xtypes_in, int nrows, int npops,
+                       int fancy, int altnorm, int *c0, int *c1, int *nmiss, double *xmean_o, double *xfancy_o, double *cols)
+{
+  long s; int *xidx, *xt, n0, n1, keep_usepops = usepopsformissing, keep_maxpops = maxpops;
+  hbuild (packed, nsnp, rl, nind);
+  fancynorm = fancy; altnormstyle = altnorm; usepopsformissing = YES; maxpops = npops;
+  ZALLOC (xidx, nrows, int); ZALLOC (xt, nrows, int);
+  memcpy (xidx, xindex_in, sizeof (int) * nrows); memcpy (xt, xtypes_in, sizeof (int) * nrows);
+  for (s = 0; s < nsnp; s++) {
+    nmiss[s] = getcolxz (cols + s * nrows, hsnpp[s], xidx, xt, nrows, (int) s, xmean_o, xfancy_o, &n0, &n1);
+    c0[s] = n0; c1[s] = n1;
+  }
+  usepopsformissing = keep_usepops; maxpops = keep_maxpops;
+  free (xidx); free (xt); hfree ();
+  return 0;
+}
+
 /* the reference's fstcolyy (qpsubs.c:1205-1346) for every SNP: estn/estd [nsnp][numeg*numeg] */
 int refh_fstcol (const unsigned char *packed, long nsnp, long rl, int nind, const int *xindex_in, const int *xtypes_in, int nrows, int numeg,
                  double *estn, double *estd)
