@@ -278,21 +278,36 @@ __global__ void __launch_bounds__(128) e2_kernel(int n, const double* __restrict
   if (i < n) e2[i] = e[i] * e[i];
 }
 
-// thread k finds the k-th smallest eigenvalue; output descending: lam[n-1-k]
+// SEC lanes find the k-th smallest eigenvalue together by (SEC + 1)-section: every round lane i counts the eigenvalues below
+// lo + (i + 1)(hi - lo) / (SEC + 1) and the bracket shrinks to the sub-interval that holds eigenvalue k -- log2(SEC + 1) bits per Sturm
+// sweep instead of one.  A sweep is a chain of n dependent divisions, so the kernel is latency bound with one thread per eigenvalue
+// (50,000 threads on 148 SMs); the extra lanes are free until the SMs fill up.  Output descending: lam[n-1-k].  Indices [k0, k1).
+template <int SEC>
 __global__ void __launch_bounds__(128) tri_bisect_kernel(int n, const double* __restrict__ d, const double* __restrict__ e2,
                                                          const double* __restrict__ bounds, double* __restrict__ lam, int k0, int k1) {
-  const int k = k0 + blockIdx.x * blockDim.x + threadIdx.x;      // eigenvalue indices [k0, k1): a rank's share in a collective solve
-  if (k >= k1) return;
+  const int gid = (blockIdx.x * blockDim.x + threadIdx.x) / SEC, sub = threadIdx.x % SEC;
+  const int k = k0 + gid;
+  const bool live = k < k1;                         // whole groups are live or not; dead groups still take part in the shuffles
   double lo = bounds[0], hi = bounds[1];
   const double tn = bounds[2];
   const double pivmin = fmax(2.3e-308 * fmax(1.0, tn * tn), 1e-300);
   const double atol = 2.0 * 2.220446049250313e-16 * tn * 0.25 + 2.0 * pivmin;
+  const unsigned gmask = SEC == 32 ? 0xffffffffu : (((1u << SEC) - 1u) << ((threadIdx.x & 31) / SEC * SEC));
   for (int it = 0; it < 200; it++) {
+    const double w = hi - lo;
     const double mid = 0.5 * (lo + hi);
-    if (hi - lo <= atol + 2.220446049250313e-16 * fmax(fabs(lo), fabs(hi)) || mid <= lo || mid >= hi) break;
-    if (sturm_count(n, d, e2, mid, pivmin) > k) hi = mid; else lo = mid;
+    if (w <= atol + 2.220446049250313e-16 * fmax(fabs(lo), fabs(hi)) || mid <= lo || mid >= hi) break;     // uniform over the group
+    const double x = SEC == 1 ? mid : lo + w * ((double)(sub + 1) / (double)(SEC + 1));
+    const bool above = live ? sturm_count(n, d, e2, x, pivmin) > k : true;       // eigenvalue k lies below x
+    if (SEC == 1) { if (above) hi = x; else lo = x; continue; }
+    // lanes are ordered by x: the first lane whose point lies above eigenvalue k closes the bracket from the right
+    const unsigned m = (__ballot_sync(gmask, above) & gmask) >> ((threadIdx.x & 31) / SEC * SEC);
+    const int first = m ? __ffs(m) - 1 : SEC;        // points 0 .. first-1 are at or below eigenvalue k
+    const double nlo = first > 0 ? lo + w * ((double)first / (double)(SEC + 1)) : lo;
+    const double nhi = first < SEC ? lo + w * ((double)(first + 1) / (double)(SEC + 1)) : hi;
+    lo = nlo; hi = nhi;
   }
-  lam[n - 1 - k] = 0.5 * (lo + hi);
+  if (live && sub == 0) lam[n - 1 - k] = 0.5 * (lo + hi);
 }
 
 // ------------------------------------------------------------------------------------------ inverse iteration
@@ -784,14 +799,20 @@ static int tridiag_spectrum(eb_ctx* c, int n, double* d, double* e, double* e2, 
     int rc;
     EB_CUDA(cudaMemsetAsync(c->chfsi_sum.p, 0, sizeof(double) * cnt, st));
     if (k1 > k0) {
-      tri_bisect_kernel<<<(k1 - k0 + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, c->chfsi_sum.p, k0, k1);
+      // a rank bisects n / world eigenvalues: the lanes the other eigenvalues would have used go into the section width
+      const int cnt_k = k1 - k0;
+      if (W >= 8) tri_bisect_kernel<8><<<(cnt_k * 8 + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, c->chfsi_sum.p, k0, k1);
+      else tri_bisect_kernel<4><<<(cnt_k * 4 + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, c->chfsi_sum.p, k0, k1);
       EB_CHECK_LAUNCH(c);
     }
     if ((rc = peer_allreduce_stream(c, PEER_SLOT_W, c->chfsi_sum.p, c->chfsi_sum.n, cnt, false, 0))) return rc;
     EB_CUDA(cudaMemcpyAsync(c->lambda_d.p, c->chfsi_sum.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     return 0;
   }
-  tri_bisect_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, c->lambda_d.p, 0, n);
+  // section width by size: the chain length is n, the thread count n * SEC should stay within what the SMs hold at once
+  if ((int64_t)n * 4 <= (int64_t)c->num_sms * 2048) tri_bisect_kernel<4><<<(unsigned)(((int64_t)n * 4 + 127) / 128), 128, 0, st>>>(n, d, e2, bounds, c->lambda_d.p, 0, n);
+  else if ((int64_t)n * 2 <= (int64_t)c->num_sms * 2048) tri_bisect_kernel<2><<<(unsigned)(((int64_t)n * 2 + 127) / 128), 128, 0, st>>>(n, d, e2, bounds, c->lambda_d.p, 0, n);
+  else tri_bisect_kernel<1><<<(n + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, c->lambda_d.p, 0, n);
   EB_CHECK_LAUNCH(c);
   return 0;
 }

@@ -27,6 +27,9 @@ SRC = os.path.join(REF, "src", "eigensrc", "smartpca.c")
 HELPERS = r'''
 /* ---- libeigb200: the GRM / eigen / projection hot path on the GPU (INTEGRATION.md) ---- */
 static eb_ctx *ebctx = NULL;
+/* the passes that decode the packed matrix with the GRM's own tables (loadings, projections, lsqproj, shrinkmode) run on the GPU
+   unless usepopsformissing made the columns population-dependent: those stay with the reference's host code */
+#define EB_PACKED (ebctx != NULL && !usepopsformissing)
 static SNP **eb_snps0 = NULL;   /* the SNP list as uploaded (the initial xsnplist) */
 static int eb_ncols0 = 0;
 static double *eb_ffvecs0 = NULL;       /* SNP loadings indexed like the uploaded list (for eb_lsqproj) */
@@ -134,9 +137,9 @@ eb_doshrink (double *xcoeffs)
 '''
 
 UPLOAD = r'''
-  if ((!usepopsformissing) && (ldregress == 0) && (!fastmode || numeigs == 0) && (!fstonly) && packmode
-      && (getenv ("EIGB200_OFF") == NULL)) {
-    /* the lookup path (smartpca.c:995-1014) runs on the GPU: upload the packed genotypes of the used SNPs once */
+  if ((ldregress == 0) && (!fastmode || numeigs == 0) && (!fstonly) && packmode && (getenv ("EIGB200_OFF") == NULL)) {
+    /* the GRM (lookup path, or the dense path of usepopsformissing, smartpca.c:995-1014) runs on the GPU: upload the packed
+       genotypes of the used SNPs once */
     const uint8_t **eb_rows;
     ebctx = eb_create (-1);
     if (ebctx == NULL)
@@ -189,7 +192,11 @@ PASS = r'''
       eo.snp_weight = ewt;
       if (eb_set_rows (ebctx, xindex, nrows) != 0)
         eb_fail ("eb_set_rows");
-      if (eb_grm (ebctx, &eo, ec0, ec1, enm, eused, exm, exf, &y, &enused, NULL) != 0)
+      if (usepopsformissing) {
+        if (eb_grm_popfill (ebctx, &eo, xtypes, numeg, ec0, ec1, enm, eused, exm, exf, &y, &enused, NULL) != 0)
+          eb_fail ("eb_grm_popfill");
+      }
+      else if (eb_grm (ebctx, &eo, ec0, ec1, enm, eused, exm, exf, &y, &enused, NULL) != 0)
         eb_fail ("eb_grm");
       for (i = 0; i < ncols; i++) {
         cupt = xsnplist[i];
@@ -243,7 +250,7 @@ FETCH_XTX = r'''
 '''
 
 PROJECT = r'''
-    if (ebctx) {
+    if (EB_PACKED) {
       /* SNP loadings, sample projections and fxscal (smartpca.c:1485-1525) in one call */
       int *emap;
       ZALLOC (eb_ffvecs0, numeigs * eb_ncols0 + 1, double);
@@ -273,7 +280,7 @@ def edit(src):
              "void estedgar(double *edgarw, double *lambdav, int lentop, int lenspec, double gamm, double yjfac) ;\n" + HELPERS)
     # upload + no dense mmat on the GPU path
     s = once(s, "  if (shrinkmode) {\n    ZALLOC (mmat, nrows * ncols, double);\n    regmode = YES;\n  }\n",
-             UPLOAD + "  if (shrinkmode) {\n    if (!ebctx)\n      ZALLOC (mmat, nrows * ncols, double);\n    regmode = YES;\n  }\n")
+             UPLOAD + "  if (shrinkmode) {\n    if (!EB_PACKED)\n      ZALLOC (mmat, nrows * ncols, double);\n    regmode = YES;\n  }\n")
     # the pass
     s = once(s, "    for (i = 0; i < ncols; i++) {\n      cupt = xsnplist[i];\n      chrom = cupt->chrom;\n",
              PASS + "    for (i = 0; i < ncols; i++) {\n      cupt = xsnplist[i];\n      chrom = cupt->chrom;\n")
@@ -284,21 +291,21 @@ def edit(src):
     s = once(s, "    for (i = 0; i < ncols; i++) {\n      cupt = xsnplist[i];\n      getcolxf (cc, cupt, xindex, nrows, i, NULL, NULL);\n\n      for (j = 0; j < numeigs; j++) {\n",
              PROJECT + "    for (i = 0; i < ncols; i++) {\n      cupt = xsnplist[i];\n      getcolxf (cc, cupt, xindex, nrows, i, NULL, NULL);\n\n      for (j = 0; j < numeigs; j++) {\n")
     s = once(s, "      xtypes[i] = k;\n\n      loadxdataind (xrow, xsnplist, xindex[i], ncols);\n      fixxrow (xrow, xmean, xfancy, ncols);\n",
-             "      xtypes[i] = k;\n      if (ebctx)\n        continue;\n\n      loadxdataind (xrow, xsnplist, xindex[i], ncols);\n      fixxrow (xrow, xmean, xfancy, ncols);\n")
+             "      xtypes[i] = k;\n      if (EB_PACKED)\n        continue;\n\n      loadxdataind (xrow, xsnplist, xindex[i], ncols);\n      fixxrow (xrow, xmean, xfancy, ncols);\n")
     s = once(s, "      y = fxscal[j];\n      fxscal[j] = 1.0 / sqrt (y);       // standard\n",
-             "      if (ebctx)\n        break;\n      y = fxscal[j];\n      fxscal[j] = 1.0 / sqrt (y);       // standard\n")
+             "      if (EB_PACKED)\n        break;\n      y = fxscal[j];\n      fxscal[j] = 1.0 / sqrt (y);       // standard\n")
     # lsqproj
     s = once(s, "      lsqproj(-99, xsnplist, ncols, indivmarkers, numindivs, fxscal, ffvecs, acoeffs, bcoeffs, xtypes, numeg) ; \n",
-             "      if (ebctx) eb_lsqproj_all (indivmarkers, numindivs, numeigs, fxscal, acoeffs, bcoeffs) ;\n      else\n"
+             "      if (EB_PACKED) eb_lsqproj_all (indivmarkers, numindivs, numeigs, fxscal, acoeffs, bcoeffs) ;\n      else\n"
              "      lsqproj(-99, xsnplist, ncols, indivmarkers, numindivs, fxscal, ffvecs, acoeffs, bcoeffs, xtypes, numeg) ; \n")
     # shrinkmode (two call sites)
     old_fill = "  for (i = 0; i < ncols; ++i) {\n    cupt = xsnplist[i];\n    getcolxf (cc, cupt, xindex, nrows, i, NULL, NULL);\n    for (j = 0; j < nrows; ++j) {\n      mmat[j * ncols + i] = cc[j];\n"
     assert s.count(old_fill) == 2
-    s = s.replace(old_fill, "  if (!ebctx)\n" + old_fill)
+    s = s.replace(old_fill, "  if (!EB_PACKED)\n" + old_fill)
     s = once(s, "  doshrinkp (mmat, nrows, ncols, xindex, xsnplist, xcoeffs) ;\n",
-             "  if (ebctx) eb_doshrink (xcoeffs) ;\n  else\n  doshrinkp (mmat, nrows, ncols, xindex, xsnplist, xcoeffs) ;\n")
+             "  if (EB_PACKED) eb_doshrink (xcoeffs) ;\n  else\n  doshrinkp (mmat, nrows, ncols, xindex, xsnplist, xcoeffs) ;\n")
     s = once(s, "  doshrinkp (mmat, nrows, ncols, xindex, xsnplist, xcoeffs);\n",
-             "  if (ebctx) eb_doshrink (xcoeffs);\n  else\n  doshrinkp (mmat, nrows, ncols, xindex, xsnplist, xcoeffs);\n")
+             "  if (EB_PACKED) eb_doshrink (xcoeffs);\n  else\n  doshrinkp (mmat, nrows, ncols, xindex, xsnplist, xcoeffs);\n")
     return s
 
 

@@ -34,7 +34,9 @@ def test_popfill_grm_vs_reference(ctx, nsnp, nind, npops, missing, alt, rows):
     t = np.minimum(ref["c0"], ref["c1"])
     used = ~((t < 1) | (ref["nmiss"] < 0) | (t == 0))
     assert np.array_equal(r["used"].astype(bool), used) and r["nused"] == used.sum()
-    assert not used[5] and ref["nmiss"][6] > 0
+    assert not used[5]
+    if npops > 1:
+        assert ref["nmiss"][6] > 0                      # the population without data keeps its missing genotypes
     # normalisation: to rounding (the filled sum is accumulated in a different order)
     assert np.abs(r["xmean"] - ref["xmean"]).max() <= 1e-12 * np.abs(ref["xmean"]).max()
     assert np.abs(r["xfancy"] - ref["xfancy"]).max() <= 1e-12 * np.abs(ref["xfancy"]).max()

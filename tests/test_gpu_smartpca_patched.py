@@ -158,3 +158,13 @@ def test_fastmode_vs_reference_binary(tmp_path):
     outs = _both(tmp_path, "fastmode: YES\nseed: 77\n", k=4, empty_indiv=False, outliers=False)      # printevecs needs nrows == numindivs
     assert "end of smartpca(fastmode)" in outs["gpu"]
     _hiprec_compare(tmp_path, 4)
+
+
+def test_usepopsformissing_vs_reference_binary(tmp_path):
+    """usepopsformissing: YES -> the dense path: eb_grm_popfill on the GPU (population fill, normalisation, GRM) + eb_eig; the
+    projection passes stay with the reference's host code (their columns are population dependent)"""
+    outs = _both(tmp_path, "numoutlieriter: 2\nusepopsformissing: YES\n", k=3, missing=0.2)
+    assert "libeigb200:" in outs["gpu"]
+    ev_g = np.loadtxt(tmp_path / "gpu.eval"); ev_r = np.loadtxt(tmp_path / "ref.eval")
+    assert ev_g.shape == ev_r.shape and np.abs(ev_g - ev_r).max() <= 1.0001e-6
+    _hiprec_compare(tmp_path, 3)
