@@ -261,14 +261,29 @@ __global__ void __launch_bounds__(1024) tri_bounds_kernel(int n, const double* _
   }
 }
 
+// Number of eigenvalues of the tridiagonal (d, e) below x.  LAPACK's dstebz runs the ratio recurrence q_i = d_i - x - e_{i-1}^2 / q_{i-1}
+// and counts negative q_i; a chain of n dependent FP64 DIVISIONS (~280 cycles each on this part, measured: 0.38 s for n = 50,000).
+// The same count comes out of the three-term recurrence of the leading principal minors p_i = (d_i - x) p_{i-1} - e_{i-1}^2 p_{i-2}
+// (q_i = p_i / p_{i-1}: q_i < 0 iff p_i and p_{i-1} differ in sign) -- two dependent DFMAs per step -- with the pair rescaled by a power
+// of two every 8 steps (exact, so no sign changes) and dstebz's pivot floor kept: |q_i| < pivmin counts as a negative pivot.
 __device__ __forceinline__ int sturm_count(int n, const double* __restrict__ d, const double* __restrict__ e2, double x, double pivmin) {
-  double qv = d[0] - x;
-  if (fabs(qv) < pivmin) qv = -pivmin;
-  int cnt = qv < 0.0;
+  double pm = 1.0, p = d[0] - x;
+  if (fabs(p) < pivmin) p = -pivmin;
+  int cnt = p < 0.0;
   for (int i = 1; i < n; i++) {
-    qv = d[i] - x - e2[i - 1] / qv;
-    if (fabs(qv) < pivmin) qv = -pivmin;
-    cnt += qv < 0.0;
+    double pn = fma(d[i] - x, p, -e2[i - 1] * pm);
+    if (fabs(pn) < pivmin * fabs(p)) pn = -pivmin * p;             // q_i = -pivmin
+    cnt += (pn < 0.0) != (p < 0.0);
+    pm = p; p = pn;
+    if ((i & 7) == 0) {
+      // bring the larger of the pair to [1, 2): multiply both by 2^-(exponent)
+      const int ea = (__double2hiint(p) >> 20) & 0x7ff, eb = (__double2hiint(pm) >> 20) & 0x7ff;
+      const int em = ea > eb ? ea : eb;
+      if (em > 0 && em < 0x7fe) {
+        const double sc = __hiloint2double((2046 - em) << 20, 0);
+        p *= sc; pm *= sc;
+      }
+    }
   }
   return cnt;
 }
