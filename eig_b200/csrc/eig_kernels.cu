@@ -797,6 +797,22 @@ __global__ void copy_matrix_kernel(const double* __restrict__ src, int64_t lds, 
 
 // ------------------------------------------------------------------------------------------ host driver
 // all eigenvalues of the tridiagonal (d, e; scaled in place by `scale`) -> c->lambda_d descending
+// Section width for `cnt` eigenvalues: with the division-free Sturm sweep the kernel is issue bound once ~64k threads are in flight
+// and latency bound below, and a (SEC + 1)-section spends SEC / log2(SEC + 1) times the work of a bisection -- so widen only while
+// the threads are free.
+static int launch_bisect(eb_ctx* c, int n, const double* d, const double* e2, const double* bounds, double* lam, int k0, int k1) {
+  const int cnt = k1 - k0;
+  if (cnt <= 0) return 0;
+  cudaStream_t st = c->stream;
+  const int want = 65536 / cnt;
+  if (want >= 8) tri_bisect_kernel<8><<<(unsigned)(((int64_t)cnt * 8 + 127) / 128), 128, 0, st>>>(n, d, e2, bounds, lam, k0, k1);
+  else if (want >= 4) tri_bisect_kernel<4><<<(unsigned)(((int64_t)cnt * 4 + 127) / 128), 128, 0, st>>>(n, d, e2, bounds, lam, k0, k1);
+  else if (want >= 2) tri_bisect_kernel<2><<<(unsigned)(((int64_t)cnt * 2 + 127) / 128), 128, 0, st>>>(n, d, e2, bounds, lam, k0, k1);
+  else tri_bisect_kernel<1><<<(cnt + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, lam, k0, k1);
+  EB_CHECK_LAUNCH(c);
+  return 0;
+}
+
 // dist (collective solves, after the row-distributed reduction has mapped the exchange block): every rank bisects n / world of the
 // eigenvalues and the vector is summed over the ranks (the other entries are zero) -- bit-identical everywhere
 static int tridiag_spectrum(eb_ctx* c, int n, double* d, double* e, double* e2, double* bounds, double scale, bool dist = false) {
@@ -813,23 +829,13 @@ static int tridiag_spectrum(eb_ctx* c, int n, double* d, double* e, double* e2, 
     const int64_t cnt = ((int64_t)n + 1) & ~1ll;
     int rc;
     EB_CUDA(cudaMemsetAsync(c->chfsi_sum.p, 0, sizeof(double) * cnt, st));
-    if (k1 > k0) {
-      // a rank bisects n / world eigenvalues: the lanes the other eigenvalues would have used go into the section width
-      const int cnt_k = k1 - k0;
-      if (W >= 8) tri_bisect_kernel<8><<<(cnt_k * 8 + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, c->chfsi_sum.p, k0, k1);
-      else tri_bisect_kernel<4><<<(cnt_k * 4 + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, c->chfsi_sum.p, k0, k1);
-      EB_CHECK_LAUNCH(c);
-    }
+    // a rank bisects n / world eigenvalues: the lanes the other eigenvalues would have used go into the section width
+    if ((rc = launch_bisect(c, n, d, e2, bounds, c->chfsi_sum.p, k0, k1))) return rc;
     if ((rc = peer_allreduce_stream(c, PEER_SLOT_W, c->chfsi_sum.p, c->chfsi_sum.n, cnt, false, 0))) return rc;
     EB_CUDA(cudaMemcpyAsync(c->lambda_d.p, c->chfsi_sum.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     return 0;
   }
-  // section width by size: the chain length is n, the thread count n * SEC should stay within what the SMs hold at once
-  if ((int64_t)n * 4 <= (int64_t)c->num_sms * 2048) tri_bisect_kernel<4><<<(unsigned)(((int64_t)n * 4 + 127) / 128), 128, 0, st>>>(n, d, e2, bounds, c->lambda_d.p, 0, n);
-  else if ((int64_t)n * 2 <= (int64_t)c->num_sms * 2048) tri_bisect_kernel<2><<<(unsigned)(((int64_t)n * 2 + 127) / 128), 128, 0, st>>>(n, d, e2, bounds, c->lambda_d.p, 0, n);
-  else tri_bisect_kernel<1><<<(n + 127) / 128, 128, 0, st>>>(n, d, e2, bounds, c->lambda_d.p, 0, n);
-  EB_CHECK_LAUNCH(c);
-  return 0;
+  return launch_bisect(c, n, d, e2, bounds, c->lambda_d.p, 0, n);
 }
 
 // large-n path: spectrum by two-stage tridiagonalisation (only if lambda_h), leading vectors by subspace iteration
