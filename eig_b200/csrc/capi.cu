@@ -560,6 +560,11 @@ int eb_set_option(eb_ctx* c, const char* key, int value) {
   if (!strcmp(key, "eig_method")) { c->opt_eig_method = value; return 0; }
   if (!strcmp(key, "two_stage_min")) { c->opt_two_stage_min = value; return 0; }
   if (!strcmp(key, "dist_min")) { c->opt_dist_min = value; return 0; }
+  if (!strcmp(key, "grm_method")) { c->opt_grm_method = value; return 0; }
+  if (!strcmp(key, "i8_min")) { c->opt_i8_min = value; return 0; }
+  if (!strcmp(key, "i8_slices")) { c->opt_i8_slices = value; return 0; }
+  if (!strcmp(key, "i8_slab")) { c->opt_i8_slab = value; return 0; }
+  if (!strcmp(key, "i8_splitv")) { c->opt_i8_splitv = value; return 0; }
   set_error("eb_set_option: unknown key '%s'", key);
   return EB_ERR_ARG;
 }

@@ -158,6 +158,19 @@ struct eb_ctx {
   eb::DevBuf<double> pg_part;         // split-K planes of the packed products (fpca_kernels.cu)
   eb::DevBuf<double> fpG, fpB, fpS;   // fastmode buffers that take part in an exchange (persistent: peers map them)
 
+  // exact integer tensor-core GRM (grm_i8.cu)
+  eb::DevBuf<uint8_t> i8_ops;       // byte operands of one SNP slab: A[nseg][rows][npad], B[nseg * nsl][rows][npad]
+  eb::DevBuf<uint8_t> i8_flag;      // per 128-SNP block: a used SNP with a missing genotype
+  eb::DevBuf<double> i8_coef;       // [2][mpad]: a b and a^2 of the SNPs without missing genotypes (rank-one terms)
+  eb::DevBuf<double> i8_r;          // rank-one partial sums per SNP chunk, r[npad], sum a^2
+  eb::DevBuf<long long> i8_prep;    // largest weight exponent, flagged blocks, used SNPs, exponent sum
+  eb::DevBuf<int> i8_tiles;         // (nb, mb) tile order
+  int opt_grm_method = 0;           // 0 auto (integer path from opt_i8_min rows), 1 FP64 DMMA, 2 integer tensor cores
+  int opt_i8_min = 4096;
+  int opt_i8_slices = 0;            // 0 auto (52 bits below the typical weight), else the digit count (1..9)
+  int opt_i8_slab = 0;              // 0 = as many SNPs per slab as memory allows, else the cap (tests: several slabs)
+  int opt_i8_splitv = 0;            // 1 = validity basis in its own accumulator with a negative scale instead of a signed operand
+
   eb_timings tm = {};
   cudaEvent_t ev[12] = {};
 };
@@ -177,6 +190,9 @@ int launch_synth(eb_ctx* c, uint8_t* dst, int64_t nsnp, int64_t pitch, int numin
 int grm_accumulate(eb_ctx* c, bool finalize_local = true, bool push = false);   // work+table -> split-K planes [-> xtx] | -> owners' receive buffers
 int grm_nsplit_for(const eb_ctx* c, bool sharded);
 int grm_trace(eb_ctx* c);        // recompute trace_d / y from xtx
+// grm_i8.cu
+bool grm_use_i8(const eb_ctx* c);
+int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push);
 int microbench_fp64(eb_ctx* c, double* dmma, double* dfma);
 // eig_kernels.cu
 int eig_resident(eb_ctx* c, const double* A_d, int64_t lda, int n, double scale, int nvec, double* lambda_h, double* evecs_h, bool collective = false);

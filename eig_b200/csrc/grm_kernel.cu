@@ -371,7 +371,7 @@ int grm_nsplit_for(const eb_ctx* c, bool sharded) {
   const int T = c->npad / TILE;
   const int ntri = T * (T + 1) / 2;
   int nsplit = (40 * c->num_sms + ntri - 1) / ntri;
-  if (sharded) return std::max(1, std::min(nsplit, 16));
+  if (sharded) return grm_use_i8(c) ? 1 : std::max(1, std::min(nsplit, 16));
   const int nkb = (int)(c->mpad / KT);
   nsplit = std::max(1, std::min(nsplit, std::min(nkb, 32)));
   size_t freeb = 0, totalb = 0;
@@ -383,6 +383,8 @@ int grm_nsplit_for(const eb_ctx* c, bool sharded) {
 }
 
 int grm_accumulate(eb_ctx* c, bool finalize_local, bool push_mode) {
+  if (grm_use_i8(c)) { c->tm.grm_method = 2; return grm_accumulate_i8(c, finalize_local, push_mode); }
+  c->tm.grm_method = 1;
   const int T = c->npad / TILE;
   const int ntri = T * (T + 1) / 2;
   const int nkb = (int)(c->mpad / KT);

@@ -304,6 +304,10 @@ typedef struct {
   float chfsi_resid;            /* largest relative residual |A v - theta v| / |A| among the returned pairs */
   float exchange_wait_ms;       /* multi-GPU: time the stream spent waiting for the slowest rank's tiles before the reduce */
   float band_ms, chase_ms;      /* two-stage tridiagonalisation: dense -> band (DMMA products + panel QR), band -> tridiagonal */
+  int grm_method;               /* GRM of the last pass: 1 = FP64 DMMA (grm_syrk_kernel), 2 = exact integer tensor cores (grm_i8_kernel) */
+  int i8_slices, i8_segments;   /* integer path: 7-bit weight digits; 1 = complete data (one basis), 3 = missing genotypes present */
+  int i8_flag_blocks;           /* integer path: 128-SNP blocks that contain a missing genotype (they take the two extra bases) */
+  float i8_tera_ops;            /* integer path: 1e12 8-bit multiply-adds x 2 issued by the last pass (all digits and bases) */
 } eb_timings;
 int eb_get_timings (eb_ctx *, eb_timings * t);
 /* FP64 DMMA / DFMA issue-rate microbenchmarks (TFLOP/s) used as roofline cross-checks */
