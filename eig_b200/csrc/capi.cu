@@ -302,6 +302,10 @@ static int grm_pass(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* n
   if ((rc = fetch_snp_outputs(c, c0, c1, nmiss, used, xmean, xfancy, nused_out))) return rc;
   cudaEventElapsedTime(&c->tm.stats_ms, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->tm.grm_ms, c->ev[2], c->ev[3]);
+  if (c->tm.grm_method == 2 && c->i8_sync_h[2]) {
+    set_error("grm (i8): %u pass synchronisations timed out (clusters not co-resident?)", c->i8_sync_h[2]);
+    return EB_ERR_STATE;
+  }
   c->tm.exchange_wait_ms = 0.f;
   if (peer) {
     long long tot = 0;
@@ -565,6 +569,8 @@ int eb_set_option(eb_ctx* c, const char* key, int value) {
   if (!strcmp(key, "i8_slices")) { c->opt_i8_slices = value; return 0; }
   if (!strcmp(key, "i8_slab")) { c->opt_i8_slab = value; return 0; }
   if (!strcmp(key, "i8_splitv")) { c->opt_i8_splitv = value; return 0; }
+  if (!strcmp(key, "i8_pair")) { c->opt_i8_pair = value; return 0; }
+  if (!strcmp(key, "i8_sync")) { c->opt_i8_sync = value; return 0; }
   set_error("eb_set_option: unknown key '%s'", key);
   return EB_ERR_ARG;
 }

@@ -165,10 +165,13 @@ struct eb_ctx {
   eb::DevBuf<double> i8_r;          // rank-one partial sums per SNP chunk, r[npad], sum a^2
   eb::DevBuf<long long> i8_prep;    // largest weight exponent, flagged blocks, used SNPs, exponent sum
   eb::DevBuf<int> i8_tiles;         // (nb, mb) tile order
+  unsigned int i8_sync_h[4] = {0, 0, 0, 0};   // [2]: pass-synchronisation time-outs of the last pass (0 in a healthy run)
   int opt_grm_method = 0;           // 0 auto (integer path from opt_i8_min rows), 1 FP64 DMMA, 2 integer tensor cores
   int opt_i8_min = 4096;
   int opt_i8_slices = 0;            // 0 auto (52 bits below the typical weight), else the digit count (1..9)
   int opt_i8_slab = 0;              // 0 = as many SNPs per slab as memory allows, else the cap (tests: several slabs)
+  int opt_i8_pair = 1;              // 1 = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles), 0 = one CTA per 128 x 256 tile
+  int opt_i8_sync = 0;              // pair kernel: passes a cluster may run ahead of the slowest one (-1: no synchronisation)
   int opt_i8_splitv = 0;            // 1 = validity basis in its own accumulator with a negative scale instead of a signed operand
 
   eb_timings tm = {};

@@ -47,6 +47,8 @@ constexpr int I8_MAXSL = 10;
 struct I8Args {
   int npad, ntiles, nkb, nsl, nseg, splitv, first;
   double scale[I8_MAXSL];                        // 2^(E - 7 (k + 1))
+  int sync_lag;                                  // pair kernel: -1 = free-running clusters, else passes a cluster may run ahead of the slowest
+  unsigned int* sync_ctr;                        // pair kernel: arrivals at pass boundaries (zeroed before the launch), [2] = time-outs of the whole pass
   const int2* tiles;                             // (nb, mb) in L2-friendly order
   const uint8_t* kbflag;                         // per 128-SNP block of THIS slab: contains a used SNP with a missing genotype
   double* out;                                   // lower-tile accumulator [npad][npad]
@@ -278,6 +280,234 @@ grm_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------ the GEMM, CTA pairs
+// Same work, two SMs per tile (cluster of 2, tcgen05.mma.cta_group::2): the pair computes 256 GRM columns (M side, 128 per CTA) x 256
+// GRM rows (N side); every CTA loads ITS half of both operands (16 KB + 16 KB per 128-SNP stage instead of 16 + 32 for half the work),
+// the leader's thread issues one M 256 x N 256 x K 32 instruction per 32 SNPs, and both CTAs drain their 128 accumulator lanes.
+// L2 -> SM traffic per multiply-add drops by a third and the 6 (not 4) stages fit the same shared memory.
+constexpr int I8P_STAGES = 6;
+constexpr int I8P_STAGE = 2 * I8_STAGE_A;                 // 32 KB per CTA and stage
+constexpr int I8P_SMEM = I8P_STAGES * I8P_STAGE + 1024 + 256;
+
+__device__ __forceinline__ uint32_t i8_ld_acquire_u32(const unsigned int* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t i8_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t i8_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void i8_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void i8_mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of this CTA's operand half; the transaction bytes are counted on the LEADER's barrier (cluster address)
+__device__ __forceinline__ void i8_tma_load_3d_pair(void* dst, const CUtensorMap* map, int x, int y, int z, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          i8_smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar_cluster_addr)
+      : "memory");
+}
+__device__ __forceinline__ constexpr uint32_t i8p_idesc(int a_signed, int b_signed) {
+  return (2u << 4) | ((uint32_t)a_signed << 7) | ((uint32_t)b_signed << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) |
+         ((uint32_t)(256 >> 4) << 24);
+}
+__device__ __forceinline__ void i8p_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void i8p_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(i8_smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
+grm_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ I8Args args) {
+  extern __shared__ uint8_t i8_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(i8_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + I8P_STAGES * I8P_STAGE);     // used in the leader only
+  uint64_t* empty = full + I8P_STAGES;          // per CTA: the pair's MMAs have read this CTA's stage
+  uint64_t* tfull = empty + I8P_STAGES;         // [2] per CTA: accumulator buffer complete
+  uint64_t* tempty = tfull + 2;                 // [2] leader only: both CTAs have drained the buffer (8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = i8_cluster_rank();
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < I8P_STAGES; s++) { i8_mbar_init(full + s, 1); i8_mbar_init(empty + s, 1); }
+    for (int b = 0; b < 2; b++) { i8_mbar_init(tfull + b, 1); i8_mbar_init(tempty + b, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(i8_smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  i8_cluster_sync();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const I8Walk walk(args);
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs, each its own halves)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      int pass = 0;
+      for (int t = cluster_id; t < args.ntiles; t += nclusters) {
+        const int2 tl = args.tiles[t];
+        const int xa = tl.y * 256 + (int)rank * 128, xb = tl.x * 256 + (int)rank * 128;
+        for (int g = 0; g < walk.ngroups; g++, pass++) {
+          int k, seg0, seg1; bool neg;
+          walk.group(args, g, k, seg0, seg1, neg);
+          // Keep the clusters of a wave within sync_lag passes of each other: they stream the same operand columns through L2, and the
+          // lines only survive there while everybody reads them at about the same time (free-running clusters drift apart, every one
+          // then pulls its own copy from DRAM and the kernel becomes DRAM bound: 35 % L2 hit rate instead of ~85 %).
+          if (rank == 0 && args.sync_lag >= 0) {
+            atomicAdd(args.sync_ctr, 1u);
+            const long long target = ((long long)pass + 1 - args.sync_lag) * (long long)nclusters;
+            const long long t0 = clock64();
+            while ((long long)i8_ld_acquire_u32(args.sync_ctr) < target) {
+              __nanosleep(100);
+              if (clock64() - t0 > (1ll << 32)) { atomicAdd(args.sync_ctr + 2, 1u); break; }      // ~2 s: never wedge the GPU
+            }
+          }
+          for (int seg = seg0; seg < seg1; seg++) {
+            for (int kb = 0; kb < args.nkb; kb++) {
+              if (seg > 0 && !args.kbflag[kb]) continue;
+              i8_mbar_wait(empty + stage, phase ^ 1);
+              uint8_t* sb = smem + stage * I8P_STAGE;
+              if (rank == 0) i8_mbar_expect_tx(full + stage, 2 * I8P_STAGE);
+              const uint32_t lead_bar = i8_mapa(i8_smem_u32(full + stage), 0);
+              i8_tma_load_3d_pair(sb, &mapA, xa, kb * I8_BK, seg, lead_bar);
+              i8_tma_load_3d_pair(sb + I8_STAGE_A, &mapB, xb, kb * I8_BK, seg * args.nsl + k, lead_bar);
+              if (++stage == I8P_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+      // a cluster without a tile in the last round still owes that round's arrivals
+      if (rank == 0 && args.sync_lag >= 0) {
+        const int rounds = (args.ntiles + nclusters - 1) / nclusters;
+        const int owed = rounds * walk.ngroups - pass;
+        if (owed > 0) atomicAdd(args.sync_ctr, (unsigned int)owed);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (one thread of the leader CTA)
+    if (lane == 0 && rank == 0) {
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int t = cluster_id; t < args.ntiles; t += nclusters) {
+        for (int g = 0; g < walk.ngroups; g++, it++) {
+          int k, seg0, seg1; bool neg;
+          walk.group(args, g, k, seg0, seg1, neg);
+          const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
+          i8_mbar_wait(tempty + buf, bphase ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tacc = tmem_base + buf * 256;
+          uint32_t acc = 0;
+          for (int seg = seg0; seg < seg1; seg++) {
+            const uint32_t idesc = i8p_idesc((seg == 2 && !args.splitv) ? 1 : 0, 0);
+            for (int kb = 0; kb < args.nkb; kb++) {
+              if (seg > 0 && !args.kbflag[kb]) continue;
+              i8_mbar_wait(full + stage, phase);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t sa = i8_smem_u32(smem + stage * I8P_STAGE);
+              const uint32_t sbb = sa + I8_STAGE_A;
+#pragma unroll
+              for (int j = 0; j < I8_BK / 32; j++) {
+                const uint64_t ad = i8_smem_desc(sa + j * 4096, I8_STAGE_A, 1024);
+                const uint64_t bd = i8_smem_desc(sbb + j * 4096, I8_STAGE_A, 1024);
+                i8p_mma(tacc, ad, bd, idesc, acc);
+                acc = 1;
+              }
+              i8p_commit(empty + stage);
+              if (++stage == I8P_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+          i8p_commit(tfull + buf);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue (both CTAs: 128 accumulator lanes each)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    uint32_t it = 0;
+    for (int t = cluster_id; t < args.ntiles; t += nclusters) {
+      const int2 tl = args.tiles[t];
+      const int nb = tl.x;
+      const int col0 = tl.y * 256 + (int)rank * 128;         // first GRM column of this CTA's half
+      for (int g = 0; g < walk.ngroups; g++, it++) {
+        int k, seg0, seg1; bool neg;
+        walk.group(args, g, k, seg0, seg1, neg);
+        const uint32_t buf = it & 1u, bphase = (it >> 1) & 1u;
+        const double sc = neg ? -args.scale[k] : args.scale[k];
+        const bool store_only = args.first && g == 0;
+        i8_mbar_wait(tfull + buf, bphase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
+        if (col0 < args.npad) {
+#pragma unroll 1
+          for (int cg = 0; cg < 8; cg++) {
+            const int row0 = nb * 256 + cg * 32;
+            if (row0 >= args.npad) break;
+            if (row0 + 31 < col0) continue;
+            uint32_t v[32];
+            i8_tmem_ld32(taddr + cg * 32, v);
+            double* p = args.out + (size_t)row0 * args.npad + (size_t)col0 + m;
+            if (store_only) {
+#pragma unroll
+              for (int c = 0; c < 32; c++) p[(size_t)c * args.npad] = (double)(int)v[c] * sc;
+            } else {
+              double o[32];
+#pragma unroll
+              for (int c = 0; c < 32; c++) o[c] = p[(size_t)c * args.npad];
+#pragma unroll
+              for (int c = 0; c < 32; c++) p[(size_t)c * args.npad] = fma((double)(int)v[c], sc, o[c]);
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) i8_mbar_arrive_remote(i8_mapa(i8_smem_u32(tempty + buf), 0));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  i8_cluster_sync();                                 // the peer's shared memory and barriers stay alive until both are done
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -522,6 +752,17 @@ static void i8_tile_order(int npad, std::vector<int2>& tiles) {
   }
 }
 
+// CTA pairs: 256 x 256 tiles (nb, mb2 <= nb), same banding
+static void i8_pair_tile_order(int npad, std::vector<int2>& tiles) {
+  const int NB = (npad + 255) / 256;
+  tiles.clear();
+  for (int b0 = 0; b0 < NB; b0 += I8_BAND) {
+    const int b1 = std::min(NB, b0 + I8_BAND);
+    for (int mb = 0; mb < b1; mb++)
+      for (int nb = std::max(b0, mb); nb < b1; nb++) tiles.push_back(make_int2(nb, mb));
+  }
+}
+
 bool grm_use_i8(const eb_ctx* c) {
   if (c->opt_grm_method == 1) return false;
   if (c->opt_grm_method == 2) return true;
@@ -600,7 +841,8 @@ int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push_mode) {
   uint8_t* Bop = Aop + (size_t)nseg_all * rows * npad;
 
   std::vector<int2> tiles;
-  i8_tile_order(npad, tiles);
+  const bool pair = c->opt_i8_pair != 0;
+  if (pair) i8_pair_tile_order(npad, tiles); else i8_tile_order(npad, tiles);
   if ((rc = c->i8_tiles.ensure(tiles.size() * 2))) return rc;
   EB_CUDA(cudaMemcpyAsync(c->i8_tiles.p, tiles.data(), sizeof(int2) * tiles.size(), cudaMemcpyHostToDevice, c->stream));
 
@@ -608,6 +850,7 @@ int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push_mode) {
   if ((rc = i8_make_map(&mapA, Aop, npad, (int)rows, nseg_all))) return rc;
   if ((rc = i8_make_map(&mapB, Bop, npad, (int)rows, nseg_all * nsl))) return rc;
   EB_CUDA(cudaFuncSetAttribute(grm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+  EB_CUDA(cudaFuncSetAttribute(grm_i8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8P_SMEM));
 
   I8Args args;
   memset(&args, 0, sizeof(args));
@@ -615,7 +858,21 @@ int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push_mode) {
   for (int k = 0; k < nsl; k++) args.scale[k] = ldexp(1.0, Emax - 7 * (k + 1));
   args.tiles = reinterpret_cast<const int2*>(c->i8_tiles.p);
   args.out = c->partial.p;
-  const int grid = std::min((int)tiles.size(), c->num_sms);
+  int grid = pair ? 2 * std::min((int)tiles.size(), c->num_sms / 2) : std::min((int)tiles.size(), c->num_sms);
+  if (pair) {
+    // the pass-level synchronisation spins on a global counter: every cluster of the grid must be resident
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(I8_THREADS); cfg.dynamicSmemBytes = I8P_SMEM;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int ncl = 0;
+    EB_CUDA(cudaOccupancyMaxActiveClusters(&ncl, grm_i8_pair_kernel, &cfg));
+    if (ncl < 1) { set_error("grm (i8): no CTA pair fits on this device"); return EB_ERR_CUDA; }
+    grid = std::min(grid, 2 * ncl);
+  }
+  const double tile_macs = pair ? 256.0 * 256.0 : (double)I8_TM * I8_TN;
   c->grm_grid = 0;                                       // no per-CTA self-measurement on this path
   bool first = true;
   double ops = 0.0;
@@ -632,13 +889,20 @@ int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push_mode) {
                                                      (int)rows, npad, nsl, Emax, nseg, splitv, Aop, Bop);
       EB_CHECK_LAUNCH(c);
       args.nkb = nkb; args.nseg = nseg; args.first = first ? 1 : 0; args.kbflag = c->i8_flag.p + kb0;
-      grm_i8_kernel<<<grid, I8_THREADS, I8_SMEM, c->stream>>>(mapA, mapB, args);
+      if (pair) {
+        args.sync_lag = c->opt_i8_sync;
+        args.sync_ctr = reinterpret_cast<unsigned int*>(c->i8_prep.p + 4);
+        EB_CUDA(cudaMemsetAsync(c->i8_prep.p + 4, 0, sizeof(int), c->stream));
+        grm_i8_pair_kernel<<<grid, I8_THREADS, I8P_SMEM, c->stream>>>(mapA, mapB, args);
+      }
+      else grm_i8_kernel<<<grid, I8_THREADS, I8_SMEM, c->stream>>>(mapA, mapB, args);
       EB_CHECK_LAUNCH(c);
       first = false;
-      ops += (double)tiles.size() * (double)I8_TM * I8_TN * 2.0 * (double)I8_BK * nsl * ((double)nkb + 2.0 * nfl * (nseg == 3 ? 1 : 0));
+      ops += (double)tiles.size() * tile_macs * 2.0 * (double)I8_BK * nsl * ((double)nkb + 2.0 * nfl * (nseg == 3 ? 1 : 0));
     }
   }
   c->tm.i8_tera_ops = (float)(ops * 1e-12);
+  EB_CUDA(cudaMemcpyAsync(c->i8_sync_h, c->i8_prep.p + 4, sizeof(c->i8_sync_h), cudaMemcpyDeviceToHost, c->stream));
   EB_CUDA(cudaEventRecord(c->ev[3], c->stream));
   c->tm.grm_launches = 2;
   if (push_mode) {

@@ -20,6 +20,14 @@ def _both(ctx, **kw):
     ctx.set_option("grm_method", 2)
     i = ctx.grm(want_xtx=True, **kw)
     t = ctx.timings()
+    # one CTA per 128 x 256 tile instead of CTA pairs on 256 x 256 tiles: the integer sums are exact and the FP64 accumulation order
+    # is the same, so the two kernels must agree bit for bit
+    ctx.set_option("i8_pair", 0)
+    try:
+        j = ctx.grm(want_xtx=True, **kw)
+    finally:
+        ctx.set_option("i8_pair", 1)
+    assert np.array_equal(i["XTX"], j["XTX"])
     ctx.set_option("grm_method", 0)
     return d, i, t
 

@@ -14,7 +14,11 @@ nsnp = int(sys.argv[2]) if len(sys.argv) > 2 else 60000
 missing = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
 slices = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 check = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+slabs = [int(x) for x in sys.argv[6].split(",")] if len(sys.argv) > 6 else [0]
+syncs = [int(x) for x in sys.argv[7].split(",")] if len(sys.argv) > 7 else [0]
+pair = int(sys.argv[8]) if len(sys.argv) > 8 else 1
 ctx = capi.Context(0)
+ctx.set_option("i8_pair", pair)
 rl = synth.rlen_for(nind)
 slab = torch.empty((nsnp, rl), dtype=torch.uint8, device="cuda")
 ctx.synth_packed_device(slab.data_ptr(), nsnp, rl, nind, seed=1, s0=0, missing=missing)
@@ -22,8 +26,12 @@ ctx.adopt_packed_device(slab.data_ptr(), nsnp, rl, nind)
 ctx.set_rows(None)
 ctx.set_option("i8_slices", slices)
 ref = None
-for method in ((1, 2) if check else (2,)):
+for method, slab, sync in ([(1, 0, 0)] if check else []) + [(2, s, y) for s in slabs for y in syncs]:
     ctx.set_option("grm_method", method)
+    ctx.set_option("i8_slab", slab)
+    ctx.set_option("i8_sync", sync)
+    if method == 2:
+        print("slab cap %d SNPs, sync lag %d, pair %d" % (slab, sync, pair))
     for rep in range(2):
         t0 = time.perf_counter()
         r = ctx.grm(want_snp=False)
