@@ -37,6 +37,8 @@ def main():
 
     ctx = capi.Context(dev_index)
     ctx.set_comm(comm)
+    if os.environ.get("EB_TEST_GRM_METHOD"):      # 2: the sharded passes take the integer tensor-core GRM (the single-GPU expectation stays FP64 DMMA)
+        ctx.set_option("grm_method", int(os.environ["EB_TEST_GRM_METHOD"]))
     # 1. the all-reduce kernel alone
     v = np.arange(1000, dtype=np.float64) * (rank + 1)
     out = ctx.peer_allreduce_test(v)

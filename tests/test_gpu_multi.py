@@ -12,13 +12,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _run(world, backend=None, timeout=600):
+def _run(world, backend=None, timeout=600, extra_env=None):
     port = 29600 + (os.getpid() % 2000)
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         if backend:
             env["EB_BACKEND"] = backend
+        env.update(extra_env or {})
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "multi_worker.py")], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []
@@ -36,6 +37,12 @@ def _run(world, backend=None, timeout=600):
 
 def test_two_ranks_sharded_grm_pca_fpca():
     _run(2)
+
+
+def test_two_ranks_sharded_integer_grm():
+    """the same worker with every sharded GRM pass on the exact integer tensor-core path (grm_i8.cu): tiles pushed to their owners after
+    the integer GEMM, compared with the single-GPU FP64 DMMA result"""
+    _run(2, extra_env={"EB_TEST_GRM_METHOD": "2"})
 
 
 def test_three_ranks_shared_gpu_gloo():
