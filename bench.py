@@ -5,16 +5,20 @@ quoted on, 50,000 individuals x 600,000 SNPs (configs[3], "C4"), plus one comple
 Contract: python bench.py --gpus N --steps K --warmup W [--impl reference]   (torchrun launches N>1, one rank per GPU)
 
 Workload: synthetic Hardy-Weinberg genotypes, 50,000 x 600,000, no missing data, fancynorm + altnormstyle YES.
-A "step" = one pass of the region smartpca.c:1088-1236 over one 60,000-SNP slab of that matrix (1/10 of it; step i takes
-slab i mod 10): row selection (loadindx -> working matrix), per-SNP allele counts + normalisation + drop rule, the
-packed -> FP64 symmetric rank-M update of the 50,000 x 50,000 matrix, mirror (symit2) + trace.
-  value : the slab resident in HBM when the timed region starts (eb_adopt_packed_device / eb_set_rows / eb_grm)
+A "step" = one pass of the region smartpca.c:1088-1236 over the WHOLE 600,000-SNP matrix: row selection (loadindx -> working
+matrix), per-SNP allele counts + normalisation + drop rule, the symmetric rank-M update of the 50,000 x 50,000 matrix, mirror
+(symit2) + trace.  (Until the integer tensor-core GRM a step was one 60,000-SNP slab -- 4.1 s on one GPU; the whole matrix now
+takes less than that.)
+  value : the matrix resident in HBM when the timed region starts (eb_adopt_packed_device / eb_set_rows / eb_grm)
   e2e   : the same pass through the C-ABI with HOST buffers (eb_upload_packed from pinned memory, eb_set_rows, eb_grm,
           per-SNP outputs copied back) -- H2D / D2H inside the timed region
-N>1 is STRONG scaling: the slab's SNPs are split over the ranks; every rank accumulates a partial 50,000 x 50,000 GRM whose
-128 x 128 tiles go straight from the SYRK kernel's epilogue into the owning rank's receive buffer over NVLink (peer memory,
-CUDA IPC); a stream-ordered flag barrier, the owner's fixed-order sum and an all-gather of the reduced tiles complete the
-step -- the 20 GB exchange is inside the timed region, with no host collective in it.
+The rank-M update runs on the 5th-generation tensor cores as an EXACT integer computation (grm_i8.cu: tcgen05.mma kind::i8 on CTA
+pairs, s32 accumulators in TMEM, 7-bit digits of the FP64 per-SNP weights, FP64 accumulation of the digit products); the FP64
+DMMA kernel of round 1 (grm_syrk_kernel) is timed beside it on a 16,384-SNP slab (`roofline_fp64`).
+N>1 is STRONG scaling: the matrix's SNPs are split over the ranks; every rank accumulates a partial 50,000 x 50,000 GRM whose
+128 x 128 tiles go into the owning rank's receive buffer over NVLink (peer memory, CUDA IPC); a stream-ordered flag barrier,
+the owner's fixed-order sum and an all-gather of the reduced tiles complete the step -- the 20 GB exchange is inside the
+timed region, with no host collective in it.
 `smartpca_e2e_s`: after the timed steps, ONE complete run of the named configuration on the N GPUs, host buffers to output
 files: upload of the 600,000-SNP matrix -> eb_pca_full (numoutevec 10, numoutlieriter 5, all 50,000 eigenvalues) ->
 eb_evec_coords (loadings, projections, lsqproj) -> Tracy-Widom table -> .eval / .evec files.
@@ -37,7 +41,7 @@ sys.path.insert(0, ROOT)
 
 N_IND = int(os.environ.get("EB_BENCH_NIND", 50000))
 N_SNP = int(os.environ.get("EB_BENCH_NSNP", 600000))
-N_SLABS = 10
+N_SLABS = 1            # a step is the whole matrix
 STEP_SNPS = N_SNP // N_SLABS
 SEED = 1
 METRIC = "grm_snp_indiv2_per_s"
@@ -46,10 +50,10 @@ UNIT = "SNP*indiv^2/s"
 
 def workload_config(extra=None):
     cfg = {"workload": "smartpca full mode %d indiv x %d SNPs (BASELINE configs[3]; the shape the metric is quoted on), synthetic "
-                       "Hardy-Weinberg p~U(0.05,0.95), no missing, fancynorm+altnormstyle YES; step = region smartpca.c:1088-1236 over one "
-                       "%d-SNP slab (1/%d of the matrix, slabs rotate)" % (N_IND, N_SNP, STEP_SNPS, N_SLABS),
+                       "Hardy-Weinberg p~U(0.05,0.95), no missing, fancynorm+altnormstyle YES; step = region smartpca.c:1088-1236 over all "
+                       "%d SNPs" % (N_IND, N_SNP, STEP_SNPS),
            "nindiv": N_IND, "nsnp": N_SNP, "nsnp_per_step": STEP_SNPS, "seed": SEED,
-           "l2": "every step streams a different %.0f MB slab and writes a %.1f GB FP64 accumulator per GPU (>> 126 MB L2): no explicit flush needed"
+           "l2": "every step streams the %.0f MB packed matrix and a %.1f GB FP64 accumulator per GPU (>> 126 MB L2): no explicit flush needed"
                  % (STEP_SNPS * max(48, (N_IND + 3) // 4) / 1e6, 8.0 * N_IND * N_IND / 1e9)}
     if extra:
         cfg.update(extra)
@@ -186,6 +190,25 @@ def run_b200(args):
     s0, s1 = parallel.shard_snps(STEP_SNPS, rank, world)       # this rank's part of every slab (strong scaling)
     per = s1 - s0
 
+    # ---- the FP64 DMMA kernel (grm_syrk_kernel, round 1's GRM) on a 16,384-SNP slab of the same 50,000 rows, rank 0's GPU, before
+    #      anything else: its algorithmic FP64 rate against the FP64 tensor peak stays in the line as `roofline_fp64`
+    fp64 = None
+    if rank == 0 and not args.no_fp64_probe:
+        fs = 16384
+        fslab = torch.empty((fs, rl), dtype=torch.uint8, device=dev)
+        ctx.synth_packed_device(fslab.data_ptr(), fs, rl, nind, seed=SEED, s0=0); ctx.sync()
+        ctx.adopt_packed_device(fslab.data_ptr(), fs, rl, nind); ctx.set_rows(None)
+        ctx.set_option("grm_method", 1)
+        for _ in range(2):
+            fr = ctx.grm(want_snp=False)
+        ft = ctx.timings()
+        ctx.set_option("grm_method", 0)
+        fp64 = {"kernel": "grm_syrk_kernel (FP64 DMMA.8x8x4)", "kernel_ms": float(ft["grm_ms"]), "nsnp": fs,
+                "achieved": float(nind) * (nind + 1.0) * fr["nused"] / (ft["grm_ms"] * 1e-3) / 1e12, "unit": "TFLOP/s",
+                "grm_sm_mhz": float(ft["grm_sm_mhz"]), "grm_sms": int(ft["grm_sms"])}
+        del fslab
+    barrier()
+
     # ---- multi-GPU parity, before anything is timed: the sharded pass == the single-GPU pass on a small matrix
     parity = None
     if world > 1:
@@ -200,8 +223,10 @@ def run_b200(args):
         a0, a1 = parallel.shard_snps(pm, rank, world)
         ctx.adopt_packed_device(small.data_ptr() + a0 * prl, a1 - a0, prl, pn); ctx.set_rows(None)
         got = None
+        ctx.set_option("grm_method", 2)                          # the sharded pass on the integer tensor-core path (the bench's path) ...
         for _ in range(2):                                       # the second pass reuses the mapped buffers and the flag epochs
             got = ctx.grm(want_snp=False, want_xtx=True)
+        ctx.set_option("grm_method", 0)                          # ... against the single-GPU FP64 DMMA pass (1,000 rows: auto = DMMA)
         err = float(np.abs(got["XTX"] - want["XTX"]).max() / np.abs(want["XTX"]).max())
         mine = torch.from_numpy(got["XTX"].view(np.int64).copy()).to(dev)
         allx = [torch.empty_like(mine) for _ in range(world)]
@@ -209,7 +234,7 @@ def run_b200(args):
         same = all(bool(torch.equal(allx[0], t)) for t in allx)
         flag = torch.tensor([1.0 if (err <= 1e-12 and same and got["nused"] == want["nused"]) else 0.0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        parity = {"checked": True, "ok": bool(flag.item() == 1.0), "shape": "%d indiv x %d SNPs, 5%% missing, %d shards" % (pn, pm, world),
+        parity = {"checked": True, "ok": bool(flag.item() == 1.0), "shape": "%d indiv x %d SNPs, 5%% missing, %d shards, integer tensor-core path vs single-GPU FP64 DMMA" % (pn, pm, world),
                   "max_rel_err_vs_single_gpu": err, "bit_identical_across_ranks": same, "tolerance": 1e-12}
         one.close(); del small, mine, allx
         if not parity["ok"]:
@@ -272,7 +297,7 @@ def run_b200(args):
     units = total_used * float(nind) ** 2
     ms_per_step = ms / steps
     value = units / (ms_per_step * 1e-3)
-    keys = ("gather_ms", "stats_ms", "grm_ms", "exchange_wait_ms", "finalize_ms", "grm_sm_mhz", "grm_sms", "grm_cta_min_ms", "grm_cta_max_ms", "grm_span_ms")
+    keys = ("gather_ms", "stats_ms", "grm_ms", "exchange_wait_ms", "finalize_ms", "i8_gemm_ms", "i8_tera_ops", "i8_slices", "i8_segments", "grm_launches")
     mine = torch.tensor([[float(k[q]) for q in keys] for k in kern], dtype=torch.float64, device=dev)      # [steps][keys]
     if world > 1:
         allk = [torch.empty_like(mine) for _ in range(world)]
@@ -280,9 +305,13 @@ def run_b200(args):
         allk = torch.stack(allk).cpu().numpy()                  # [world][steps][keys]
     else:
         allk = mine.cpu().numpy()[None]
-    grm_ms = float(allk[0, :, 2].mean())                       # rank 0's kernel (the roofline line); all ranks below
+    grm_ms = float(allk[0, :, 2].mean())                       # rank 0: the whole GRM phase (prep, operand transform, integer GEMMs)
+    gemm_ms = float(allk[0, :, 5].mean())                      # rank 0: the integer GEMM launches alone (the roofline line); all ranks below
+    tops = float(allk[0, :, 6].mean())                         # 1e12 8-bit ops (multiply + add) those launches issued
+    method = int(kern[-1]["grm_method"])
     flops = float(nind) * (nind + 1.0) * own_used
-    achieved = flops / (grm_ms * 1e-3) / 1e12
+    fp64_equiv = flops / (grm_ms * 1e-3) / 1e12
+    achieved = tops / (gemm_ms * 1e-3) if gemm_ms > 0 else 0.0
     per_rank = {q: _stats(allk[:, :, j]) for j, q in enumerate(keys)}
     per_rank["grm_ms_by_rank_median"] = [float(np.median(allk[w, :, 2])) for w in range(world)]
     nonkernel_ms = ms_per_step - float(np.mean(allk[:, :, 2].max(axis=0)))
@@ -337,7 +366,7 @@ def run_b200(args):
 
     line = None
     if rank == 0:
-        # FP64 pipe peak: MEASURED_PEAKS.json carries no FP64 entry, so measure cuBLAS DGEMM here (same box, same run)
+        # FP64 pipe peak (for roofline_fp64): MEASURED_PEAKS.json carries no FP64 entry, so measure cuBLAS DGEMM here (same box, same run)
         n = 8192
         a = torch.randn(n, n, dtype=torch.float64, device=dev); b = torch.randn(n, n, dtype=torch.float64, device=dev)
         for _ in range(2):
@@ -349,16 +378,33 @@ def run_b200(args):
         dgemm = 2.0 * n ** 3 / (best * 1e-3) / 1e12
         del a, b
         dmma, dfma = ctx.microbench_fp64()
-        # the roofline denominator is the larger of the two measured FP64 tensor rates: cuBLAS DGEMM (an application-level ceiling,
-        # itself a DMMA.8x8x4 kernel) and the library's DMMA issue-rate probe (the stream of grm_syrk_kernel without the decode)
-        peak = max(dgemm, dmma)
-        # DRAM traffic of the dominant kernel: from the committed ncu capture of THIS launch shape, else null
+        peak64 = max(dgemm, dmma)
+        if fp64 is not None:
+            fp64.update({"peak": peak64, "frac": fp64["achieved"] / peak64, "frac_of_dgemm": fp64["achieved"] / dgemm, "peak_dgemm": dgemm,
+                         "peak_dmma_probe": dmma, "dfma_probe": dfma,
+                         "peak_source": "max of cuBLAS DGEMM 8192^3 best-of-5 and the library's DMMA issue-rate probe, both measured in this run on rank 0"})
+        # 8-bit integer tensor peak: MEASURED_PEAKS.json measures cuBLAS bf16; kind::i8 issues at twice the bf16 rate (4.5 vs 2.25 P nominal)
+        mp = {}
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        bf_s, bf_b = mp.get("bf16_tflops_sustained"), mp.get("bf16_tflops")
+        if bf_s:
+            peak8 = 2.0 * bf_s
+            psrc = ("2 x MEASURED_PEAKS.json bf16_tflops_sustained (%.1f; the kernel is timed inside a seconds-long step) -- 8-bit integer MMAs issue at twice "
+                    "the bf16 rate; 2 x the burst figure = %.1f, nominal dense 4500.  A fraction above 1 of the sustained figure is expected here: the "
+                    "operands are small non-negative integers (genotype bases 0..2, 7-bit digits), which toggle far fewer datapath bits than cuBLAS's random "
+                    "bf16 inputs, so the SM clock under the 1 kW cap stays higher (see clocks)" % (bf_s, 2.0 * (bf_b or 0.0)))
+        else:
+            peak8 = 2.0 * 1400.0
+            psrc = "2 x 1400 TFLOP/s bf16 sustained, of fallback (MEASURED_PEAKS.json absent)"
         traffic = None; traffic_src = None
-        tp = os.path.join(ROOT, "profiles", "grm_syrk_traffic.json")
-        if os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "grm_i8_traffic.json")
+        if os.path.exists(tp) and method == 2:
             try:
                 tj = json.load(open(tp))
-                if tj.get("nindiv") == nind and tj.get("nsnp_per_launch") == per:
+                if tj.get("nindiv") == nind and tj.get("slab_rows") == int(kern[-1]["i8_slab_rows"]):
                     traffic = tj.get("dram_bytes_per_launch"); traffic_src = tj.get("source")
             except Exception:
                 traffic = None
@@ -369,26 +415,34 @@ def run_b200(args):
                 cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as ex:      # the checker is optional for the product line
                 cb = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)[:200]}
-        par = "single GPU" if world == 1 else ("strong scaling: the step's %d SNPs split over %d GPUs; partial-GRM tiles pushed from the SYRK epilogue into the "
-                                               "owner's receive buffer over NVLink (peer memory, CUDA IPC), stream-ordered flag barrier, fixed-order reduce + "
+        par = "single GPU" if world == 1 else ("strong scaling: the %d SNPs split over %d GPUs; every rank's partial GRM goes tile by tile into the owners' "
+                                               "receive buffers over NVLink (peer memory, CUDA IPC), stream-ordered flag barrier, fixed-order reduce + "
                                                "all-gather of the tiles; no host collective inside the step" % (STEP_SNPS, world))
+        if method == 2:
+            roof = {"bound": "tensor", "kernel": "grm_i8_pair_kernel (tcgen05.mma.cta_group::2.kind::i8, s32 accumulators in TMEM)",
+                    "achieved": achieved, "peak": peak8, "unit": "TFLOP/s", "op": "8-bit integer multiply-add = 2 ops (TOP/s)",
+                    "frac": achieved / peak8, "frac_of_nominal_4500": achieved / 4500.0, "traffic": traffic, "traffic_source": traffic_src,
+                    "kernel_ms": gemm_ms, "launches_per_step": int(kern[-1]["grm_launches"]), "snp_rows_per_launch": int(kern[-1]["i8_slab_rows"]),
+                    "digits": int(kern[-1]["i8_slices"]), "bases": int(kern[-1]["i8_segments"]), "peak_source": psrc,
+                    "algorithmic": "tiles x 256 x 256 x SNP rows x digits x bases x 2 ops per launch (256 x 256 lower-triangle tiles incl. the diagonal ones; "
+                                   "the digits are the price of exactness: 7 bits of the FP64 per-SNP weight per pass), summed over the step's launches",
+                    "fp64_equivalent_tflops": fp64_equiv,
+                    "fp64_equivalent": "N(N+1)*M_used FP64 flops of the rank-M update / the whole GRM phase (prep + operand transform + integer GEMMs)"}
+        else:
+            roof = {"bound": "tensor", "kernel": "grm_syrk_kernel (FP64 DMMA.8x8x4)", "achieved": fp64_equiv, "peak": peak64, "unit": "TFLOP/s",
+                    "frac": fp64_equiv / peak64, "traffic": None, "kernel_ms": grm_ms}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config({"parallelism": par, "nsplit": kern[-1]["nsplit"], "nsnp_per_gpu_per_step": per}),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64 (per-SNP weights, scales and the accumulation are FP64; the sum over SNPs is exact u8 x u8 -> s32 tensor-core arithmetic)"
+                         if method == 2 else "f64", "data": "synthetic",
+                "config": workload_config({"parallelism": par, "nsnp_per_gpu_per_step": per}),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ems / esteps, "steps": esteps},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "tensor", "kernel": "grm_syrk_kernel (FP64 DMMA.8x8x4)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": grm_ms,
-                             "peak_source": "MEASURED_PEAKS.json has no FP64 entry: max of the two FP64 tensor rates measured in this run on rank 0 -- cuBLAS DGEMM "
-                                            "8192^3 best-of-5 %.2f TFLOP/s, DMMA issue-rate probe (8 warps/SM, 32 independent DMMA.8x8x4 per k-step) %.2f TFLOP/s; "
-                                            "DFMA (non-tensor FP64) probe %.1f TFLOP/s" % (dgemm, dmma, dfma),
-                             "peak_dgemm": dgemm, "peak_dmma_probe": dmma, "frac_of_dgemm": achieved / dgemm,
-                             "algorithmic": "N(N+1)*M_used flops per launch (lower triangle incl. diagonal, FMA=2), M_used = this rank's SNPs of the slab",
-                             "kernel_clock": "grm_sm_mhz = median over CTAs of clock64 cycles / globaltimer ns, measured by the kernel itself; grm_sms = "
-                                             "distinct SMs its CTAs ran on"},
+                "roofline": roof,
+                "roofline_fp64": fp64,
                 "cpu_baseline": cb,
-                "kernel_ms": {k: float(allk[0, :, j].mean()) for j, k in enumerate(keys[:5])},
+                "kernel_ms": {k: float(allk[0, :, j].mean()) for j, k in enumerate(keys[:6])},
                 "per_rank_per_step": per_rank,
                 "nonkernel_ms_per_step": nonkernel_ms,
                 "parity_checked": parity,
@@ -408,6 +462,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp64-probe", action="store_true", help="skip the FP64 DMMA kernel measurement (roofline_fp64)")
     ap.add_argument("--no-full-run", action="store_true", help="skip the complete 50,000 x 600,000 smartpca run (smartpca_e2e_s)")
     args = ap.parse_args()
     if args.impl == "reference":

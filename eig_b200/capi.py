@@ -41,7 +41,7 @@ class Timings(C.Structure):
                 ("grm_span_ms", C.c_float), ("grm_sms", C.c_int), ("chfsi_converged", C.c_int), ("chfsi_resid", C.c_float),
                 ("exchange_wait_ms", C.c_float), ("band_ms", C.c_float), ("chase_ms", C.c_float),
                 ("grm_method", C.c_int), ("i8_slices", C.c_int), ("i8_segments", C.c_int), ("i8_flag_blocks", C.c_int),
-                ("i8_tera_ops", C.c_float)]
+                ("i8_tera_ops", C.c_float), ("i8_slab_rows", C.c_int), ("i8_gemm_ms", C.c_float)]
 
 
 ALLGATHER_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)

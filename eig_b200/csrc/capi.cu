@@ -65,6 +65,7 @@ void eb_destroy(eb_ctx* c) {
   peer_release(c);                                           // close the IPC mappings of the peers' buffers
   for (auto& reg : c->peer) { for (void* p : reg.graveyard) cudaFree(p); reg.graveyard.clear(); }
   for (int i = 0; i < 12; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (cudaEvent_t e : c->i8_ev) cudaEventDestroy(e);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -302,6 +303,15 @@ static int grm_pass(eb_ctx* c, const eb_grm_opts* opts, int* c0, int* c1, int* n
   if ((rc = fetch_snp_outputs(c, c0, c1, nmiss, used, xmean, xfancy, nused_out))) return rc;
   cudaEventElapsedTime(&c->tm.stats_ms, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->tm.grm_ms, c->ev[2], c->ev[3]);
+  c->tm.i8_gemm_ms = 0.f;
+  if (c->tm.grm_method == 2) {
+    for (int i = 0; i < c->i8_nlaunch; i++) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c->i8_ev[2 * i], c->i8_ev[2 * i + 1]);
+      c->tm.i8_gemm_ms += ms;
+    }
+    c->tm.grm_launches = c->i8_nlaunch;
+  }
   if (c->tm.grm_method == 2 && c->i8_sync_h[2]) {
     set_error("grm (i8): %u pass synchronisations timed out (clusters not co-resident?)", c->i8_sync_h[2]);
     return EB_ERR_STATE;

@@ -165,6 +165,8 @@ struct eb_ctx {
   eb::DevBuf<double> i8_r;          // rank-one partial sums per SNP chunk, r[npad], sum a^2
   eb::DevBuf<long long> i8_prep;    // largest weight exponent, flagged blocks, used SNPs, exponent sum
   eb::DevBuf<int> i8_tiles;         // (nb, mb) tile order
+  std::vector<cudaEvent_t> i8_ev;   // start / stop of every integer GEMM launch of the last pass
+  int i8_nlaunch = 0;
   unsigned int i8_sync_h[4] = {0, 0, 0, 0};   // [2]: pass-synchronisation time-outs of the last pass (0 in a healthy run)
   int opt_grm_method = 0;           // 0 auto (integer path from opt_i8_min rows), 1 FP64 DMMA, 2 integer tensor cores
   int opt_i8_min = 4096;

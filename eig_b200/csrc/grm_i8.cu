@@ -823,20 +823,21 @@ int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push_mode) {
   nsl = std::max(1, std::min(nsl, 9));
   const int splitv = c->opt_i8_splitv ? 1 : 0;
   const int nseg_all = nflag > 0 ? 3 : 1;
-  c->tm.i8_slices = nsl; c->tm.i8_segments = nseg_all; c->tm.i8_flag_blocks = (int)nflag;
+  c->tm.i8_slices = nsl; c->tm.i8_segments = nseg_all; c->tm.i8_flag_blocks = (int)nflag; c->tm.i8_slab_rows = 0;
 
   // slab: as many SNP blocks as the operand budget allows (A: nseg matrices, B: nseg * nsl matrices of [rows][npad] bytes)
   size_t freeb = 0, totalb = 0;
   cudaMemGetInfo(&freeb, &totalb);
   const size_t have = c->i8_ops.n;
   const size_t per_row = (size_t)nseg_all * (1 + nsl) * (size_t)npad;
-  size_t budget = have + (size_t)((double)freeb * 0.55);
+  size_t budget = std::min(have + (size_t)((double)freeb * 0.4), (size_t)48 << 30);    // leave room for the eigensolver's copy of the matrix
   if (c->opt_i8_slab > 0) budget = std::min(budget, (size_t)c->opt_i8_slab * per_row);
   long long rows = (long long)(budget / per_row) / I8_BK * I8_BK;
   rows = std::min<long long>(rows, c->mpad);
   rows = std::min<long long>(rows, 1 << 20);
   if (rows < I8_BK) { set_error("grm (i8): not enough device memory for one 128-SNP operand block (%zu bytes per SNP row)", per_row); return EB_ERR_NOMEM; }
   if ((rc = c->i8_ops.ensure((size_t)rows * per_row))) return rc;
+  c->tm.i8_slab_rows = (int)rows;
   uint8_t* Aop = c->i8_ops.p;
   uint8_t* Bop = Aop + (size_t)nseg_all * rows * npad;
 
@@ -876,6 +877,7 @@ int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push_mode) {
   c->grm_grid = 0;                                       // no per-CTA self-measurement on this path
   bool first = true;
   double ops = 0.0;
+  c->i8_nlaunch = 0;
   if (!any_weight) {
     EB_CUDA(cudaMemsetAsync(c->partial.p, 0, plane * sizeof(double), c->stream));     // no used SNP at all
   } else {
@@ -889,6 +891,13 @@ int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push_mode) {
                                                      (int)rows, npad, nsl, Emax, nseg, splitv, Aop, Bop);
       EB_CHECK_LAUNCH(c);
       args.nkb = nkb; args.nseg = nseg; args.first = first ? 1 : 0; args.kbflag = c->i8_flag.p + kb0;
+      // events around every integer GEMM launch: the kernel-only time of the roofline line (eb_timings.i8_gemm_ms)
+      while (c->i8_ev.size() < 2 * (size_t)(c->i8_nlaunch + 1)) {
+        cudaEvent_t e;
+        EB_CUDA(cudaEventCreate(&e));
+        c->i8_ev.push_back(e);
+      }
+      EB_CUDA(cudaEventRecord(c->i8_ev[2 * c->i8_nlaunch], c->stream));
       if (pair) {
         args.sync_lag = c->opt_i8_sync;
         args.sync_ctr = reinterpret_cast<unsigned int*>(c->i8_prep.p + 4);
@@ -897,6 +906,8 @@ int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push_mode) {
       }
       else grm_i8_kernel<<<grid, I8_THREADS, I8_SMEM, c->stream>>>(mapA, mapB, args);
       EB_CHECK_LAUNCH(c);
+      EB_CUDA(cudaEventRecord(c->i8_ev[2 * c->i8_nlaunch + 1], c->stream));
+      c->i8_nlaunch++;
       first = false;
       ops += (double)tiles.size() * tile_macs * 2.0 * (double)I8_BK * nsl * ((double)nkb + 2.0 * nfl * (nseg == 3 ? 1 : 0));
     }

@@ -308,6 +308,8 @@ typedef struct {
   int i8_slices, i8_segments;   /* integer path: 7-bit weight digits; 1 = complete data (one basis), 3 = missing genotypes present */
   int i8_flag_blocks;           /* integer path: 128-SNP blocks that contain a missing genotype (they take the two extra bases) */
   float i8_tera_ops;            /* integer path: 1e12 8-bit multiply-adds x 2 issued by the last pass (all digits and bases) */
+  int i8_slab_rows;             /* integer path: SNP rows per GEMM launch (operand slab) of the last pass */
+  float i8_gemm_ms;             /* integer path: summed device time of the grm_i8 GEMM launches of the last pass (CUDA events) */
 } eb_timings;
 int eb_get_timings (eb_ctx *, eb_timings * t);
 /* FP64 DMMA / DFMA issue-rate microbenchmarks (TFLOP/s) used as roofline cross-checks */
