@@ -136,6 +136,10 @@ struct eb_ctx {
   eb::DevBuf<double> lambda_d, zvec_d;
   int64_t zvec_ld = 0;             // row pitch of zvec_d after the last solve (n, or n rounded up to even for the full basis)
   eb::DevBuf<double> eig2w, chfsiw;   // two-stage reduction / subspace-iteration workspaces (eig2_kernels.cu)
+  eb::DevBuf<double> eigQ2, eigT;     // kept reflectors for the eigenvector back-transformation: bulge chasing (n^2 / 2), stage-1 T factors
+  double* eig_q2 = nullptr;           // where the stage-2 reflectors of the last two_stage_tridiag(keep_q) are (eigQ2 or the dead GRM accumulator)
+  int eig_npanels = 0;
+  int opt_eig_vectors = 0;            // two-stage path, spectrum + vectors: 0 = back-transformation of the tridiagonal eigenvectors, 1 = subspace iteration
   std::vector<double> ritz;        // scaled Ritz values of the last subspace iteration
   double* dbg_band_h = nullptr;    // eb_debug_tridiag only
   int opt_eig_method = 0;          // 0 auto, 1 one-stage (dsytrd-style), 2 two-stage + subspace iteration
@@ -209,7 +213,8 @@ int launch_gemm(eb_ctx* c, bool a_km, bool b_kn, const double* A, int64_t lda, c
 // grm_kernel.cu (dense path)
 int grm_dense_finalize(eb_ctx* c);
 // eig2_kernels.cu
-int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, double* e, bool collective = false);
+int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, double* e, bool collective = false, bool keep_q = false);
+int two_stage_backtransform(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* Z, int64_t ldz);
 int chfsi_top(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* theta_h, double* vec_d, int* iters_out, int* matvecs_out,
               double lo0 = 0.0, bool collective = false);
 // fpca_kernels.cu

@@ -389,7 +389,13 @@ __device__ unsigned long long g_bc_prof[8];
 // part*16 .. part*16+15 of the current 64 x 64 off-diagonal block B and diagonal block D in REGISTERS (one L2 round trip
 // per step); shared memory holds the copies the cross-thread reductions need.  Per step: B <- H2 (B H1) fused into one
 // update (w = tau1 B v1 gives column 0 of B H1, hence H2, before B is touched), D <- H2 D H2.
-__global__ void __launch_bounds__(BC_THREADS, 2) bulge_chase_kernel(double* __restrict__ AB, int n, int* __restrict__ prog, int* __restrict__ err) {
+// Q2 != nullptr: every reflector is kept for the back-transformation of eigenvectors (q2_apply_kernel): sweep s owns n - 1 - s doubles at
+// q2_off(s, n), element t belongs to row s + 1 + t; reflector k of the sweep occupies elements 64 k .. 64 k + len - 1 with tau in place of
+// the implicit v[0] = 1.
+__host__ __device__ __forceinline__ size_t q2_off(long long s, long long n) { return (size_t)(s * (n - 1) - s * (s - 1) / 2); }
+
+__global__ void __launch_bounds__(BC_THREADS, 2) bulge_chase_kernel(double* __restrict__ AB, int n, int* __restrict__ prog, int* __restrict__ err,
+                                                                    double* __restrict__ Q2) {
 #ifdef EB_BC_PROFILE
   long long t_prev = clock64();
 #endif
@@ -463,6 +469,8 @@ __global__ void __launch_bounds__(BC_THREADS, 2) bulge_chase_kernel(double* __re
     __syncthreads();
     double tau = hs.tau;
     if (tid < la) __stcg(&AB[(size_t)s * LDAB + 1 + tid], tid == 0 ? hs.beta : 0.0);
+    double* q2s = Q2 ? Q2 + q2_off(s, n) : nullptr;
+    if (q2s && tid < la) __stcs(&q2s[tid], tid == 0 ? tau : v1[tid]);
     {
       double pr = 0.0;
 #pragma unroll
@@ -534,6 +542,7 @@ __global__ void __launch_bounds__(BC_THREADS, 2) bulge_chase_kernel(double* __re
       if (warp == 0) bc_make_reflector(xs, lb, v2, &hs, lane);
       __syncthreads();                                                       // (3)
       const double tau2 = hs.tau;
+      if (q2s && tid < lb) __stcs(&q2s[(r1 - s - 1) + tid], tid == 0 ? tau2 : v2[tid]);
       {
         // u_raw[c = i] over rows c0..c0+15, gamma = v2 . wv, p_raw[i] over columns c0..c0+15
         double ur = 0.0, gp = 0.0, pr = 0.0;
@@ -763,6 +772,145 @@ __global__ void __launch_bounds__(256) normalize_rows_kernel(double* __restrict_
   for (int i = threadIdx.x; i < n; i += 256) v[i] *= inv;
 }
 
+
+// =================================================================================================== eigenvector back-transformation
+// x = Q1 Q2 z for the leading eigenvectors z of the tridiagonal matrix: Q1 = product of the stage-1 block reflectors I - V T V^T (V kept
+// below the band in the panel's own dead columns of the working matrix, T in a side buffer), Q2 = product of the bulge-chasing reflectors.
+// For the 10-40 vectors smartpca prints this is O(n^2 nvec) work against the ~270 n^2 x 64 block mat-vecs of the subspace iteration.
+
+// A[r0 + gi][j + cc] = V[cc][r0 + gi] for gi > cc (strictly below the unit diagonal: outside the band, never read again by stage 1 / 2)
+__global__ void __launch_bounds__(256) save_v_kernel(double* __restrict__ A, int64_t lda, int n, int j, const double* __restrict__ VZ, int64_t ldv) {
+  __shared__ double t[64][65];
+  const int r0 = j + BW, i0 = blockIdx.x * 64;
+  for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
+    const int cc = idx >> 6, r = idx & 63, gi = i0 + r;
+    t[r][cc] = (r0 + gi < n) ? VZ[(size_t)cc * ldv + r0 + gi] : 0.0;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
+    const int r = idx >> 6, cc = idx & 63, gi = i0 + r;
+    if (r0 + gi < n && gi > cc) A[(size_t)(r0 + gi) * lda + j + cc] = t[r][cc];
+  }
+}
+
+// Z <- Q2 Z: sweeps in reverse order; the reflectors of one sweep act on disjoint 64-row blocks (one warp each), a grid barrier separates
+// the sweeps.  Z: [nvec][ldz].
+constexpr int Q2_THREADS = 512;
+__global__ void __launch_bounds__(Q2_THREADS, 1) q2_apply_kernel(const double* __restrict__ Q2, int n, int nvec, double* __restrict__ Z, int64_t ldz,
+                                                                  int* __restrict__ bar, int* __restrict__ err) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = Q2_THREADS / 32;
+  const int G = gridDim.x;
+  int bar_target = 0;
+  for (int s = n - 3; s >= 0; s--) {
+    const int L = n - 1 - s, nref = (L + 63) >> 6;
+    const double* q = Q2 + q2_off(s, n);
+    for (int k = blockIdx.x * nw + warp; k < nref; k += G * nw) {
+      const int len = min(64, L - 64 * k), row0 = s + 1 + 64 * k;
+      double v0 = lane < len ? __ldcs(&q[64 * k + lane]) : 0.0;
+      const double v1 = lane + 32 < len ? __ldcs(&q[64 * k + lane + 32]) : 0.0;
+      const double tau = __shfl_sync(0xffffffffu, v0, 0);
+      if (lane == 0) v0 = 1.0;
+      if (tau != 0.0) {
+        for (int j0 = 0; j0 < nvec; j0 += 8) {
+          double z0[8], z1[8], d[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const bool ok = j0 + j < nvec;
+            double* zr = Z + (size_t)(j0 + j) * ldz + row0;
+            z0[j] = (ok && lane < len) ? __ldcg(&zr[lane]) : 0.0;
+            z1[j] = (ok && lane + 32 < len) ? __ldcg(&zr[lane + 32]) : 0.0;
+            d[j] = v0 * z0[j] + v1 * z1[j];
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int j = 0; j < 8; j++) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            if (j0 + j < nvec) {
+              double* zr = Z + (size_t)(j0 + j) * ldz + row0;
+              const double f = tau * d[j];
+              if (lane < len) __stcg(&zr[lane], z0[j] - f * v0);
+              if (lane + 32 < len) __stcg(&zr[lane + 32], z1[j] - f * v1);
+            }
+          }
+        }
+      }
+    }
+    if (G > 1) grid_barrier(bar, bar_target += G, err);
+    else __syncthreads();
+  }
+}
+
+// stage-1 block reflector of the panel at column j: Gpart[chunk][v][c] = sum over the chunk's rows of V[i][c] Z[v][i]
+constexpr int Q1_ROWS = 256;       // rows per CTA
+constexpr int Q1_MAXV = 40;
+__device__ __forceinline__ double q1_v(const double* __restrict__ A, int64_t lda, int r0, int j, int i, int c) {
+  const int gi = i - r0;
+  return gi > c ? A[(size_t)i * lda + j + c] : (gi == c ? 1.0 : 0.0);
+}
+__global__ void __launch_bounds__(256) q1_dot_kernel(const double* __restrict__ A, int64_t lda, int n, int j, int nvec, const double* __restrict__ Z,
+                                                     int64_t ldz, double* __restrict__ Gpart) {
+  __shared__ double red[4][64];
+  const int r0 = j + BW, c = threadIdx.x & 63, part = threadIdx.x >> 6;
+  const int i0 = r0 + blockIdx.x * Q1_ROWS, i1 = min(n, i0 + Q1_ROWS);
+  double acc[Q1_MAXV];
+#pragma unroll
+  for (int v = 0; v < Q1_MAXV; v++) acc[v] = 0.0;
+  for (int i = i0 + part; i < i1; i += 4) {
+    const double vv = q1_v(A, lda, r0, j, i, c);
+#pragma unroll
+    for (int v = 0; v < Q1_MAXV; v++)
+      if (v < nvec) acc[v] += vv * Z[(size_t)v * ldz + i];
+  }
+  for (int v = 0; v < nvec; v++) {
+    double a = 0.0;
+#pragma unroll
+    for (int u = 0; u < Q1_MAXV; u++) if (u == v) a = acc[u];
+    red[part][c] = a;
+    __syncthreads();
+    if (part == 0) Gpart[((size_t)blockIdx.x * nvec + v) * 64 + c] = red[0][c] + red[1][c] + red[2][c] + red[3][c];
+    __syncthreads();
+  }
+}
+// Z[v][i] -= sum_c V[i][c] (T G_v)[c],  G_v = sum over chunks (fixed order)
+__global__ void __launch_bounds__(256) q1_update_kernel(const double* __restrict__ A, int64_t lda, int n, int j, int nvec, double* __restrict__ Z,
+                                                        int64_t ldz, const double* __restrict__ Gpart, int nchunk, const double* __restrict__ T) {
+  __shared__ double Gs[Q1_MAXV][64];
+  __shared__ double TG[Q1_MAXV][64];
+  double (*Vs)[65] = reinterpret_cast<double (*)[65]>(&Gs[0][0]);      // [32][65], reuses Gs once T G is formed
+  const int r0 = j + BW;
+  for (int idx = threadIdx.x; idx < nvec * 64; idx += 256) {
+    double a = 0.0;
+    for (int ch = 0; ch < nchunk; ch++) a += Gpart[(size_t)ch * nvec * 64 + idx];
+    Gs[idx >> 6][idx & 63] = a;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < nvec * 64; idx += 256) {
+    const int v = idx >> 6, cp = idx & 63;
+    double a = 0.0;
+    for (int cc = cp; cc < 64; cc++) a += T[cp * 64 + cc] * Gs[v][cc];         // T upper triangular, row-major
+    TG[v][cp] = a;
+  }
+  __syncthreads();
+  const int i0 = r0 + blockIdx.x * Q1_ROWS;
+  for (int b = 0; b < Q1_ROWS; b += 32) {
+    for (int idx = threadIdx.x; idx < 32 * 64; idx += 256) {
+      const int r = idx >> 6, cc = idx & 63, i = i0 + b + r;
+      Vs[r][cc] = i < n ? q1_v(A, lda, r0, j, i, cc) : 0.0;
+    }
+    __syncthreads();
+    const int r = threadIdx.x & 31, i = i0 + b + r;
+    for (int v = threadIdx.x >> 5; v < nvec; v += 8) {
+      double a = 0.0;
+#pragma unroll 8
+      for (int cc = 0; cc < 64; cc++) a += Vs[r][cc] * TG[v][cc];
+      if (i < n) Z[(size_t)v * ldz + i] -= a;
+    }
+    __syncthreads();
+  }
+}
+
 // =================================================================================================== host drivers
 static int coop_launch(eb_ctx* c, const void* fn, dim3 grid, dim3 block, void** args, size_t smem) {
   EB_CUDA(cudaLaunchCooperativeKernel(fn, grid, block, args, smem, c->stream));
@@ -866,9 +1014,20 @@ static int dist_gather_cols(eb_ctx* c, double* A, int64_t lda, int n, int row0, 
 
 // Stage 1 + stage 2: A (n x n, lda, lower triangle + complete diagonal tiles valid; destroyed) -> d, e (unscaled).
 // collective: all ranks of the communicator call with the SAME full symmetric matrix (both triangles valid); see above.
-int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, double* e, bool collective) {
+int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, double* e, bool collective, bool keep_q) {
   cudaStream_t st = c->stream;
   int rc;
+  // keep_q: the stage-1 block reflectors stay in the dead part of A (+ their T factors in c->eigT), the stage-2 reflectors go to c->eigQ2
+  // (or into the GRM's dead lower-tile accumulator when that is large enough): two_stage_backtransform() turns eigenvectors of the
+  // tridiagonal matrix into eigenvectors of A
+  double* q2 = nullptr;
+  c->eig_npanels = 0; c->eig_q2 = nullptr;
+  if (keep_q) {
+    const size_t need = q2_off(n - 2 > 0 ? n - 2 : 0, n) + 64;
+    if (c->partial.p && c->partial.n >= need) q2 = c->partial.p;
+    else { if ((rc = c->eigQ2.ensure(need))) return rc; q2 = c->eigQ2.p; }
+    if ((rc = c->eigT.ensure((size_t)(n / BW + 2) * 4096))) return rc;
+  }
   const bool dist = collective && c->has_comm && c->comm.world > 1;
   const int NW = dist ? c->comm.world : 1, me = dist ? c->comm.rank : 0;
   bool first_exchange = true;
@@ -936,6 +1095,12 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
     const size_t smem = use_global ? (size_t)(8192 + 512) * 8 : (size_t)rows_per * 512 + SH_EXTRA;
     void* args[] = {&pp};
     if ((rc = coop_launch(c, (const void*)panel_qr_kernel, dim3(G), dim3(256), args, smem))) return rc;
+    if (keep_q) {
+      save_v_kernel<<<(np + 63) / 64, 256, 0, st>>>(A, lda, n, j, w.VZ, ldv);
+      EB_CHECK_LAUNCH(c);
+      EB_CUDA(cudaMemcpyAsync(c->eigT.p + (size_t)c->eig_npanels * 4096, w.T, sizeof(double) * 4096, cudaMemcpyDeviceToDevice, st));
+      c->eig_npanels++;
+    }
     mark(2);
     // ---- W = A22 V
     int ksplit = 1;
@@ -1013,7 +1178,7 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
     const int useful = n / (2 * BW) + 4;
     const int grid = std::max(1, std::min(std::min(per_sm * c->num_sms, n - 2), useful));
     double* ab = w.AB; int nn = n; int* prog = w.prog; int* err = w.err;
-    void* args[] = {&ab, &nn, &prog, &err};
+    void* args[] = {&ab, &nn, &prog, &err, &q2};
     if ((rc = coop_launch(c, (const void*)bulge_chase_kernel, dim3(grid), dim3(BC_THREADS), args, BC_SMEM))) return rc;
   }
 #ifdef EB_BC_PROFILE
@@ -1034,6 +1199,49 @@ int two_stage_tridiag(eb_ctx* c, double* A, int64_t lda, int n, double* d, doubl
   EB_CUDA(cudaMemcpyAsync(&herr, w.err, sizeof(int), cudaMemcpyDeviceToHost, st));
   EB_CUDA(cudaStreamSynchronize(st));
   if (herr) { set_error("two_stage_tridiag: a device-side wait timed out (code %d: 1 = bulge-chase predecessor, 3 = panel grid barrier)", herr); return EB_ERR_NUMERIC; }
+  c->eig_q2 = q2;
+  return 0;
+}
+
+// Z [nvec][ldz]: eigenvectors of the tridiagonal matrix -> eigenvectors of the matrix two_stage_tridiag(keep_q) reduced (A is its
+// working copy with the stage-1 reflectors in place).  Replicated on every rank of a collective solve (O(n^2 nvec) work).
+int two_stage_backtransform(eb_ctx* c, const double* A, int64_t lda, int n, int nvec, double* Z, int64_t ldz) {
+  cudaStream_t st = c->stream;
+  int rc;
+  if (!c->eig_q2 || nvec > Q1_MAXV) { set_error("two_stage_backtransform: reflectors were not kept (or more than %d vectors)", Q1_MAXV); return EB_ERR_STATE; }
+  if (n > 2) {
+    int* bar = reinterpret_cast<int*>(c->eig2w.p);            // the stage-1 workspace is dead: [0] barrier counter, [1] error flag
+    EB_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(int), st));
+    int per_sm = 0;
+    EB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, q2_apply_kernel, Q2_THREADS, 0));
+    const int want = ((n + 63) / 64 + Q2_THREADS / 32 - 1) / (Q2_THREADS / 32);       // one warp per reflector of the longest sweep
+    int grid = std::max(1, std::min(want, std::max(1, per_sm) * c->num_sms));
+    const double* q2 = c->eig_q2; int nn = n, nv = nvec; int64_t ld = ldz; int* err = bar + 1;
+    void* args[] = {&q2, &nn, &nv, &Z, &ld, &bar, &err};
+    if ((rc = coop_launch(c, (const void*)q2_apply_kernel, dim3(grid), dim3(Q2_THREADS), args, 0))) return rc;
+  }
+  if (getenv("EB_EIG_PROFILE")) {
+    static double t_prev = 0;
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[eig profile] vectors: Q2 applied at cpu clock %.1f ms (delta to previous print)\n", ((double)clock() / CLOCKS_PER_SEC - t_prev) * 1e3);
+    t_prev = (double)clock() / CLOCKS_PER_SEC;
+  }
+  const int G_max = (n + Q1_ROWS - 1) / Q1_ROWS + 1;
+  if ((rc = c->eigW.ensure((size_t)G_max * Q1_MAXV * 64))) return rc;
+  for (int p = c->eig_npanels - 1; p >= 0; p--) {
+    const int j = p * BW, r0 = j + BW, np = n - r0;
+    const int nchunk = (np + Q1_ROWS - 1) / Q1_ROWS;
+    q1_dot_kernel<<<nchunk, 256, 0, st>>>(A, lda, n, j, nvec, Z, ldz, c->eigW.p);
+    EB_CHECK_LAUNCH(c);
+    q1_update_kernel<<<nchunk, 256, 0, st>>>(A, lda, n, j, nvec, Z, ldz, c->eigW.p, nchunk, c->eigT.p + (size_t)p * 4096);
+    EB_CHECK_LAUNCH(c);
+  }
+  int herr = 0;
+  if (n > 2) {
+    EB_CUDA(cudaMemcpyAsync(&herr, reinterpret_cast<int*>(c->eig2w.p) + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    EB_CUDA(cudaStreamSynchronize(st));
+    if (herr) { set_error("two_stage_backtransform: grid barrier timed out"); return EB_ERR_NUMERIC; }
+  }
   return 0;
 }
 

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <vector>
+#include <time.h>
 #include "common.cuh"
 
 namespace eb {
@@ -700,12 +701,11 @@ __global__ void __launch_bounds__(256) normalize_rows_full_kernel(double* __rest
 
 // eigenvectors 0..nvec-1 of the tridiagonal (d, e; lam descending on the device and the host) and their back-transformation
 // through the reflectors kept in the rows of A.  Result: c->zvec_d, [nvec][ldz] with ldz = n rounded up to even.
-static int full_basis(eb_ctx* c, double* A, int64_t lda, int n, int nvec, const double* d, const double* e, const double* tau,
-                      const std::vector<double>& lam_h, double tn, int64_t* ldz_out) {
+// eigenvectors 0..nvec-1 of the tridiagonal (d, e; lam descending, host copy given) -> c->zvec_d [nvec][ldz]: batched inverse iteration
+// (one thread per vector), dstein-style sequential treatment of numerically coincident groups
+static int tri_vectors(eb_ctx* c, int n, int nvec, const double* d, const double* e, const double* lam_h, double tn, int64_t ldz) {
   cudaStream_t st = c->stream;
   int rc;
-  const int64_t ldz = ((int64_t)n + 1) & ~1ll;
-  *ldz_out = ldz;
   if ((rc = c->zvec_d.ensure((size_t)nvec * ldz))) return rc;
   EB_CUDA(cudaMemsetAsync(c->zvec_d.p, 0, sizeof(double) * (size_t)nvec * ldz, st));
   // shifts: dstein's separation of near-coincident eigenvalues; groups that need re-orthogonalisation
@@ -730,7 +730,7 @@ static int full_basis(eb_ctx* c, double* A, int64_t lda, int n, int nvec, const 
     }
     if (nvec - cs > 1) { starts.push_back(cs); lens.push_back(nvec - cs); }
   }
-  DevBuf<double> sh_d, wk, Vp, Gp, T, W, W2;
+  DevBuf<double> sh_d, wk;
   DevBuf<uint8_t> piv;
   DevBuf<int> cl;
   const int batch = (int)std::min<int64_t>(nvec, std::max<int64_t>(256, (int64_t)(3ll << 30) / (5 * 8 * (int64_t)n)));   // <= 3 GiB of work arrays
@@ -758,7 +758,41 @@ static int full_basis(eb_ctx* c, double* A, int64_t lda, int n, int nvec, const 
     EB_CHECK_LAUNCH(c);
     EB_CUDA(cudaStreamSynchronize(st));
   }
-  wk.release(); piv.release();
+  return 0;
+}
+
+// modified Gram-Schmidt over the rows of Z (twice), unit 2-norm: the leading vectors of a gap-free spectrum come out of independent
+// inverse iterations orthogonal to ~eps / gap only
+__global__ void __launch_bounds__(1024) mgs_rows_kernel(double* __restrict__ Z, int64_t ldz, int n, int nvec) {
+  __shared__ double red[32];
+  for (int v = 0; v < nvec; v++) {
+    double* z = Z + (size_t)v * ldz;
+    for (int pass = 0; pass < 2; pass++)
+      for (int u = 0; u < v; u++) {
+        const double* zu = Z + (size_t)u * ldz;
+        double sacc = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sacc += zu[i] * z[i];
+        sacc = block_sum(sacc, red);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) z[i] -= sacc * zu[i];
+        __syncthreads();
+      }
+    double q = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) q += z[i] * z[i];
+    q = block_sum(q, red);
+    const double inv = 1.0 / sqrt(q);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) z[i] *= inv;
+    __syncthreads();
+  }
+}
+
+static int full_basis(eb_ctx* c, double* A, int64_t lda, int n, int nvec, const double* d, const double* e, const double* tau,
+                      const std::vector<double>& lam_h, double tn, int64_t* ldz_out) {
+  cudaStream_t st = c->stream;
+  int rc;
+  const int64_t ldz = ((int64_t)n + 1) & ~1ll;
+  *ldz_out = ldz;
+  if ((rc = tri_vectors(c, n, nvec, d, e, lam_h.data(), tn, ldz))) return rc;
+  DevBuf<double> Vp, Gp, T, W, W2;
   // back-transformation: z <- H_0 H_1 ... H_{n-3} z, reflectors grouped 64 at a time, last group first
   const int nrefl = std::max(0, n - 2);
   if (nrefl > 0) {
@@ -877,11 +911,13 @@ static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, do
     const size_t wn = (size_t)n * 4 + 64;
     if ((rc = c->eigw.ensure(wn))) return rc;
     double *d = c->eigw.p, *e = d + n, *e2 = e + n, *bounds = e2 + n;
+    // spectrum AND vectors: keep the reflectors of both stages and back-transform the eigenvectors of the tridiagonal matrix
+    const bool backtr = nvec > 0 && nvec <= 40 && c->opt_eig_vectors == 0;
     EB_CUDA(cudaEventRecord(c->ev[5], st));
     dim3 grid((n + 255) / 256, n);
     copy_matrix_kernel<<<grid, 256, 0, st>>>(A_d, lda_in, c->eigA.p, lda, n);
     EB_CHECK_LAUNCH(c);
-    if ((rc = two_stage_tridiag(c, c->eigA.p, lda, n, d, e, collective && n >= c->opt_dist_min))) return rc;
+    if ((rc = two_stage_tridiag(c, c->eigA.p, lda, n, d, e, collective && n >= c->opt_dist_min, backtr))) return rc;
     EB_CUDA(cudaEventRecord(c->ev[6], st));
     if ((rc = tridiag_spectrum(c, n, d, e, e2, bounds, scale, collective && n >= c->opt_dist_min))) return rc;
     EB_CUDA(cudaEventRecord(c->ev[7], st));
@@ -892,6 +928,41 @@ static int eig_two_stage(eb_ctx* c, const double* A_d, int64_t lda_in, int n, do
     cudaEventElapsedTime(&c->tm.band_ms, c->ev[5], c->ev[10]);
     cudaEventElapsedTime(&c->tm.chase_ms, c->ev[10], c->ev[6]);
     if (scale > 0.0) lo0 = lambda_h[n - 1] / scale;
+    if (backtr) {
+      double bnd[4];
+      EB_CUDA(cudaMemcpyAsync(bnd, bounds, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+      EB_CUDA(cudaStreamSynchronize(st));
+      EB_CUDA(cudaEventRecord(c->ev[8], st));
+      const int64_t ldz = ((int64_t)n + 1) & ~1ll;
+      c->zvec_ld = ldz;
+      const bool prof = getenv("EB_EIG_PROFILE") != nullptr;
+      auto lap = [&](const char* what, double& t0) {
+        if (!prof) return;
+        cudaStreamSynchronize(st);
+        const double t1 = (double)clock() / CLOCKS_PER_SEC;
+        fprintf(stderr, "[eig profile] vectors: %s %.1f ms\n", what, (t1 - t0) * 1e3);
+        t0 = t1;
+      };
+      double tp = (double)clock() / CLOCKS_PER_SEC;
+      if ((rc = tri_vectors(c, n, nvec, d, e, lambda_h, bnd[2], ldz))) return rc;
+      lap("inverse iteration on T", tp);
+      mgs_rows_kernel<<<1, 1024, 0, st>>>(c->zvec_d.p, ldz, n, nvec);
+      EB_CHECK_LAUNCH(c);
+      lap("Gram-Schmidt", tp);
+      if ((rc = two_stage_backtransform(c, c->eigA.p, lda, n, nvec, c->zvec_d.p, ldz))) return rc;
+      lap("Q1 Q2 z", tp);
+      normalize_rows_full_kernel<<<nvec, 256, 0, st>>>(c->zvec_d.p, ldz, n);
+      EB_CHECK_LAUNCH(c);
+      sign_fix_kernel<<<nvec, 256, 0, st>>>(c->zvec_d.p, ldz, n);
+      EB_CHECK_LAUNCH(c);
+      EB_CUDA(cudaEventRecord(c->ev[9], st));
+      if (evecs_h)
+        EB_CUDA(cudaMemcpy2DAsync(evecs_h, sizeof(double) * n, c->zvec_d.p, sizeof(double) * ldz, sizeof(double) * n, nvec, cudaMemcpyDeviceToHost, st));
+      EB_CUDA(cudaStreamSynchronize(st));
+      cudaEventElapsedTime(&c->tm.vectors_ms, c->ev[8], c->ev[9]);
+      c->ritz.assign(lambda_h, lambda_h + nvec);
+      return 0;
+    }
   }
   if (nvec > 0) {
     if ((rc = c->zvec_d.ensure((size_t)nvec * n))) return rc;

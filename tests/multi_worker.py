@@ -127,11 +127,19 @@ def main():
     ctx.upload_packed(Pb[u0:u1], nb); ctx.set_rows(None); ctx.grm(want_snp=False)
     la, va = single.eig(5)
     ctx.set_option("dist_min", 2048)          # default 8192: force the row-distributed band reduction / subspace iteration at this n
+    ctx.set_option("eig_vectors", 1)          # leading vectors by the (row-distributed) subspace iteration
     lb, vb = ctx.eig(5)
     tm = ctx.timings()
     assert tm["eig_method"] == 2 and tm["chfsi_matvecs"] > 0
     assert np.abs(la - lb).max() <= 1e-9 * la[0]
     assert np.abs(np.abs(np.einsum("ij,ij->i", va, vb)) - 1).max() <= 1e-9
+    ctx.set_option("eig_vectors", 0)          # default: back-transformation through the reflectors of the row-distributed band reduction
+    lc, vc = ctx.eig(5)
+    tm = ctx.timings()
+    assert tm["eig_method"] == 2 and tm["chfsi_matvecs"] == 0
+    assert np.abs(la - lc).max() <= 1e-9 * la[0]
+    assert np.abs(np.abs(np.einsum("ij,ij->i", va, vc)) - 1).max() <= 1e-9
+    vb = vc
     hv = torch.from_numpy(vb.view(np.int64).reshape(-1).copy())
     if backend == "nccl":
         hvd = hv.to(dev); hall = [torch.empty_like(hvd) for _ in range(world)]

@@ -30,11 +30,15 @@ def _eval_check(lam, ref):
     assert np.abs(lam[~big] - ref[~big]).max(initial=0.0) <= EVAL_RTOL * scale
 
 
-@pytest.fixture()
-def ctx2(ctx):
+@pytest.fixture(params=["backtransform", "subspace"])
+def ctx2(ctx, request):
+    """two-stage path; leading vectors (when the spectrum is computed too) by back-transformation of the tridiagonal eigenvectors through
+    the kept reflectors of both stages (default) or by the subspace iteration on the original matrix"""
     ctx.set_option("eig_method", 2)
+    ctx.set_option("eig_vectors", 0 if request.param == "backtransform" else 1)
     yield ctx
     ctx.set_option("eig_method", 0)
+    ctx.set_option("eig_vectors", 0)
 
 
 @pytest.mark.parametrize("n", [259, 320, 449, 1000, 1537])
@@ -200,11 +204,13 @@ def test_subspace_iteration_reports_how_it_converged(ctx):
     ctx.upload_packed(P, nind); ctx.set_rows(None)
     r = ctx.grm(want_snp=False, want_xtx=True)
     ctx.set_option("eig_method", 2)
+    ctx.set_option("eig_vectors", 1)          # the subspace iteration (the default with a spectrum is the back-transformation)
     try:
         lam, vec = ctx.eig(10)
         tm = ctx.timings()
     finally:
         ctx.set_option("eig_method", 0)
+        ctx.set_option("eig_vectors", 0)
     assert tm["eig_method"] == 2 and tm["chfsi_matvecs"] > 0
     A = r["XTX"]
     res = np.linalg.norm(A @ vec.T - vec.T * lam[:10], axis=0) / np.abs(lam).max()
