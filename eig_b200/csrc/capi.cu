@@ -660,8 +660,11 @@ int eb_pca_full(eb_ctx* c, const eb_pca_opts* o, int* xindex_io, int nrows, doub
     // Large n: the outlier passes only need the leading vectors (smartpca.c:1250); the full spectrum (.eval, Tracy-Widom)
     // is computed once, on the pass that turns out to be the last.  Small n: one-stage solver, everything each pass.
     const bool two = eig_uses_two_stage(c, n, nv);
+    // a pass that cannot be followed by another one (no outlier iterations asked for, or all of them used up) takes spectrum and
+    // vectors from ONE two-stage solve (vectors by back-transformation through the kept reflectors)
+    const bool last_for_sure = iter == numoutiter;
     t0 = now_s();
-    if ((rc = eb_eig(c, nv, two ? nullptr : lambda, ev.data()))) return rc;
+    if ((rc = eb_eig(c, nv, (two && !last_for_sure) ? nullptr : lambda, ev.data()))) return rc;
     res->secs_eig += now_s() - t0;
     res->niter = iter; res->y = y; res->nused = nused; res->nrows_final = n;
     const int keep = std::min(o->numeigs, n);
@@ -683,7 +686,7 @@ int eb_pca_full(eb_ctx* c, const eb_pca_opts* o, int* xindex_io, int nrows, doub
         if (all[2 * r] != mine[0] || all[2 * r + 1] != mine[1]) { set_error("eb_pca_full: ranks disagree on the outlier list (pass %d)", iter); return EB_ERR_STATE; }
     }
     if (nbad == 0) {
-      if (two) {
+      if (two && !last_for_sure) {
         t0 = now_s();
         if ((rc = eb_eig(c, 0, lambda, nullptr))) return rc;
         res->secs_eig += now_s() - t0;
