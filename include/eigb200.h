@@ -191,8 +191,17 @@ void eigvals (double *mat, double *evals, int n);
 
 /* eigensolver selection: key "eig_method" = 0 auto | 1 one-stage | 2 two-stage + subspace iteration;
  * "two_stage_min" = n at which auto switches to 2; "dist_min" = n from which a COLLECTIVE eb_eig (communicator set, GRM from a
- * sharded eb_grm) splits the band reduction and the subspace iteration over the ranks (default 8192).  Returns EB_ERR_ARG for an
- * unknown key. */
+ * sharded eb_grm) splits the band reduction and the subspace iteration over the ranks (default 8192);
+ * "eig_vectors" = 0 (default): a two-stage solve that returns spectrum AND vectors back-transforms the eigenvectors of the
+ * tridiagonal matrix through the kept reflectors of both stages | 1: subspace iteration on the original matrix.
+ * GRM kernel selection (eb_grm, eb_pca_full; domult_increment_lookup, smartpca.c:3426-3495):
+ * "grm_method" = 0 auto (integer path from "i8_min" rows, default 4096) | 1 FP64 DMMA (grm_syrk_kernel) | 2 exact integer tensor
+ * cores (grm_i8_pair_kernel: tcgen05.mma kind::i8, s32 accumulators in TMEM, FP64 weights as 7-bit digits, FP64 accumulation);
+ * "i8_slices" = 0 auto (>= 52 bits below the typical per-SNP weight: 8 digits on ordinary data) | 1..9 digits;
+ * "i8_slab" = cap on the SNP rows per operand slab (0: what memory allows); "i8_pair" = 1 CTA pairs (default) | 0 single CTAs;
+ * "i8_sync" = passes a cluster may run ahead of the slowest (default 0, -1 = free running); "i8_splitv" = 1: the validity basis
+ * in an accumulator of its own instead of a signed operand.  All ranks of a communicator must use the same "grm_method".
+ * Returns EB_ERR_ARG for an unknown key. */
 int eb_set_option (eb_ctx *, const char *key, int value);
 
 /* testing aid: two-stage tridiagonalisation alone.  d[n], e[n] of the similar tridiagonal (unscaled); band (may be
