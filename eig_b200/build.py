@@ -20,9 +20,7 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
+def _compile(verbose):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs = []
@@ -40,7 +38,25 @@ def build(force=False, verbose=False):
         ok &= p.returncode == 0
     if not ok:
         raise RuntimeError("nvcc failed")
-    subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"], check=True)
+    # link to a temporary name, then rename: a process that dlopens the library never sees a half-written file
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    subprocess.run([NVCC, "-shared", "-o", tmp] + objs + ["-lcudart"], check=True)
+    os.replace(tmp, LIB)
+
+
+def build(force=False, verbose=False):
+    """Build under an exclusive file lock: the ranks of a torchrun launch may all find the library stale at the same time (a source
+    edited after the last build); one of them builds, the others wait and then find it fresh."""
+    if not force and not needs_build():
+        return LIB
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            if force or needs_build():
+                _compile(verbose)
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
     return LIB
 
 
