@@ -576,6 +576,8 @@ int eb_set_option(eb_ctx* c, const char* key, int value) {
   if (!strcmp(key, "dist_min")) { c->opt_dist_min = value; return 0; }
   if (!strcmp(key, "eig_vectors")) { c->opt_eig_vectors = value; return 0; }
   if (!strcmp(key, "grm_method")) { c->opt_grm_method = value; return 0; }
+  if (!strcmp(key, "pg_method")) { c->opt_pg_method = value; return 0; }
+  if (!strcmp(key, "pg_i8_min")) { c->opt_pg_i8_min = value; return 0; }
   if (!strcmp(key, "i8_min")) { c->opt_i8_min = value; return 0; }
   if (!strcmp(key, "i8_slices")) { c->opt_i8_slices = value; return 0; }
   if (!strcmp(key, "i8_slab")) { c->opt_i8_slab = value; return 0; }

@@ -180,6 +180,12 @@ struct eb_ctx {
   int opt_i8_sync = 0;              // pair kernel: passes a cluster may run ahead of the slowest one (-1: no synchronisation)
   int opt_i8_splitv = 0;            // 1 = validity basis in its own accumulator with a negative scale instead of a signed operand
 
+  // packed x skinny products on the integer tensor cores (pg_i8.cu)
+  eb::DevBuf<uint8_t> pgi_digits;   // 7-bit digit rows of the skinny operand: [1 or 2][columns x 8][K]
+  eb::DevBuf<double> pgi_scale;     // per-column maxima / scales
+  int opt_pg_method = 0;            // 0 auto (integer path from pg_i8_min rows and K), 1 FP64 DMMA, 2 integer tensor cores
+  int opt_pg_i8_min = 2048;
+
   eb_timings tm = {};
   cudaEvent_t ev[12] = {};
 };
@@ -199,6 +205,9 @@ int launch_synth(eb_ctx* c, uint8_t* dst, int64_t nsnp, int64_t pitch, int numin
 int grm_accumulate(eb_ctx* c, bool finalize_local = true, bool push = false);   // work+table -> split-K planes [-> xtx] | -> owners' receive buffers
 int grm_nsplit_for(const eb_ctx* c, bool sharded);
 int grm_trace(eb_ctx* c);        // recompute trace_d / y from xtx
+// pg_i8.cu
+int pg_i8_launch(eb_ctx* c, int mode, const uint8_t* work, int64_t wpitch, int npad, const double* table, const double* In_t, int64_t ld_in,
+                 double* Out_t, int64_t ld_out, int ncols, double oscale);
 // grm_i8.cu
 bool grm_use_i8(const eb_ctx* c);
 int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push);

@@ -238,6 +238,13 @@ static int launch_packed_gemm(eb_ctx* c, const double* table, const double* In_t
                               int ncols, double oscale, const PackedView* view = nullptr) {
   const PackedView dflt = {c->work.p, c->wpitch, c->npad};
   const PackedView pv = view ? *view : dflt;
+  // integer tensor-core version with in-kernel decode (pg_i8.cu): same contract, exact digit products
+  {
+    const bool fits = (pv.npad % 128) == 0 && (pv.wpitch % 16) == 0 && (c->mpad % 128) == 0;
+    const bool big = pv.npad >= c->opt_pg_i8_min && c->mpad >= c->opt_pg_i8_min;
+    if (fits && (c->opt_pg_method == 2 || (c->opt_pg_method == 0 && big)))
+      return pg_i8_launch(c, MODE == MODE_XA ? 0 : 1, pv.work, pv.wpitch, pv.npad, table, In_t, ld_in, Out_t, ld_out, ncols, oscale);
+  }
   const int64_t rows = MODE == MODE_XTB ? pv.npad : c->mpad;
   const int64_t Klen = MODE == MODE_XTB ? c->mpad : pv.npad;
   const int nk = (int)(Klen / PG_KT);
