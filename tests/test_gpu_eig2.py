@@ -222,3 +222,24 @@ def test_subspace_iteration_reports_how_it_converged(ctx):
     # either way the eigenvalues agree with a dense solve to the north_star bar
     w = np.linalg.eigvalsh(A)[::-1]
     assert np.abs(lam - w).max() <= 1e-9 * w[0]
+
+
+def test_pca_full_single_pass_takes_spectrum_and_vectors_from_one_solve(ctx):
+    """numoutlieriter 0: the only pass is certainly the last, so eb_pca_full asks the two-stage solver for spectrum AND vectors at once
+    (vectors by back-transformation, no subspace iteration); same result as the run that may remove outliers but finds none."""
+    nsnp, nind = 4000, 1700
+    P = synth.pack(synth.genotypes(13, nsnp, nind, missing=0.02, npops=5, delta=0.3))
+    ctx.upload_packed(P, nind)
+    ctx.set_option("eig_method", 2)
+    try:
+        a = ctx.pca_full(numeigs=6, numoutliter=0)
+        ta = ctx.timings()
+        b = ctx.pca_full(numeigs=6, numoutliter=3, outlthresh=50.0)
+        tb = ctx.timings()
+    finally:
+        ctx.set_option("eig_method", 0)
+    assert ta["eig_method"] == 2 and ta["chfsi_matvecs"] == 0 and a["niter"] == 1
+    assert b["niter"] == 1 and len(b["removed_index"]) == 0
+    assert np.abs(a["lambda_"] - b["lambda_"]).max() <= 1e-12 * a["lambda_"][0]
+    for i in range(5):
+        assert abs(abs(float(a["evecs"][i] @ b["evecs"][i])) - 1.0) <= 1e-9
