@@ -29,13 +29,15 @@ constexpr int PGI_BK = 128;               // K elements per stage
 constexpr int PGI_TILE_A = 128 * 128;     // one byte operand tile
 constexpr int PGI_PACKED = 128 * 32;
 constexpr int PGI_MAXC = 32;              // output columns per launch (N = 8 x columns <= 256)
-constexpr int PGI_THREADS = 192;
+constexpr int PGI_DECW = 4;               // decode / epilogue warps
+constexpr int PGI_THREADS = 64 + 32 * PGI_DECW;
 enum { PGI_XA = 0, PGI_XTB = 1 };
 
 struct PgiArgs {
   int ncp;                  // padded columns of this launch (even), N = ncp * 8
   int ncols;                // real columns
   int nk, nsplit;           // K stages in total, K splits (grid.y)
+  int nraw;                 // depth of the TMA ring (digit rows + packed sub-tile)
   int64_t rows;             // valid output rows
   int64_t ld_out, plane_stride;
   double oscale;
@@ -55,6 +57,9 @@ __device__ __forceinline__ uint32_t pgi_idesc(int a_mn_major, int n) {
   return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// Two rings: the RAW ring (digit rows + packed sub-tile, filled by TMA, `nraw` stages deep) and the OPERAND ring (the two decoded byte
+// tiles, 2 stages).  A raw stage is free again when the decode warps have read its packed sub-tile AND the MMAs have read its digit
+// rows (PGI_DECW + 1 arrivals); an operand stage when the MMAs that read it have completed (tcgen05.commit).
 template <int MODE>
 __global__ void __launch_bounds__(PGI_THREADS, 1)
 pg_i8_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapD, const __grid_constant__ PgiArgs args) {
@@ -63,17 +68,22 @@ pg_i8_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
   const int N = args.ncp * PGI_ND;
   const int nB = MODE == PGI_XTB ? 2 : 1;                 // digit matrices per stage
   const int d_bytes = nB * N * 128;
-  const int stage_bytes = 2 * PGI_TILE_A + d_bytes + PGI_PACKED;            // A_v | A_h | digits | packed (all 1024-aligned: N*128 is)
-  const int nstages = MODE == PGI_XTB ? 2 : 3;
-  uint64_t* full_tma = reinterpret_cast<uint64_t*>(smem + nstages * stage_bytes);
-  uint64_t* full_dec = full_tma + 4;
-  uint64_t* empty = full_dec + 4;
-  uint64_t* accbar = empty + 4;
+  const int raw_bytes = d_bytes + PGI_PACKED;             // digits | packed   (N * 128 is a multiple of 2048: everything stays 1024-aligned)
+  const int nraw = args.nraw;
+  constexpr int NOP = 2;
+  uint8_t* ops = smem;                                    // NOP x (A_v | A_h)
+  uint8_t* raw = smem + NOP * 2 * PGI_TILE_A;
+  uint64_t* raw_full = reinterpret_cast<uint64_t*>(raw + nraw * raw_bytes);
+  uint64_t* raw_empty = raw_full + 8;
+  uint64_t* op_full = raw_empty + 8;
+  uint64_t* op_empty = op_full + NOP;
+  uint64_t* accbar = op_empty + NOP;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accbar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < nstages; s++) { i8_mbar_init(full_tma + s, 1); i8_mbar_init(full_dec + s, 4); i8_mbar_init(empty + s, 1); }
+    for (int s = 0; s < nraw; s++) { i8_mbar_init(raw_full + s, 1); i8_mbar_init(raw_empty + s, PGI_DECW + 1); }
+    for (int s = 0; s < NOP; s++) { i8_mbar_init(op_full + s, PGI_DECW); i8_mbar_init(op_empty + s, 1); }
     i8_mbar_init(accbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -94,30 +104,30 @@ pg_i8_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t rs = 0, rph = 0;
       for (int kb = kb0; kb < kb1; kb++) {
-        i8_mbar_wait(empty + stage, phase ^ 1);
-        uint8_t* sb = smem + stage * stage_bytes;
-        i8_mbar_expect_tx(full_tma + stage, (uint32_t)(d_bytes + PGI_PACKED));
+        i8_mbar_wait(raw_empty + rs, rph ^ 1);
+        uint8_t* sb = raw + rs * raw_bytes;
+        i8_mbar_expect_tx(raw_full + rs, (uint32_t)raw_bytes);
         // packed sub-tile: 128 SNP rows x 32 bytes (128 individuals)
-        if (MODE == PGI_XA) pgi_tma_2d(sb + 2 * PGI_TILE_A + d_bytes, &mapW, kb * 32, tile * 128, full_tma + stage);
-        else pgi_tma_2d(sb + 2 * PGI_TILE_A + d_bytes, &mapW, tile * 32, kb * 128, full_tma + stage);
-        for (int b = 0; b < nB; b++) pgi_tma_2d(sb + 2 * PGI_TILE_A + b * N * 128, &mapD, kb * 128, b * N, full_tma + stage);
-        if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
+        if (MODE == PGI_XA) pgi_tma_2d(sb + d_bytes, &mapW, kb * 32, tile * 128, raw_full + rs);
+        else pgi_tma_2d(sb + d_bytes, &mapW, tile * 32, kb * 128, raw_full + rs);
+        for (int b = 0; b < nB; b++) pgi_tma_2d(sb + b * N * 128, &mapD, kb * 128, b * N, raw_full + rs);
+        if (++rs == (uint32_t)nraw) { rs = 0; rph ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0, acc = 0;
+      uint32_t rs = 0, rph = 0, os = 0, oph = 0, acc = 0;
       const uint32_t idesc = pgi_idesc(MODE == PGI_XTB ? 1 : 0, N);
       for (int kb = kb0; kb < kb1; kb++) {
-        i8_mbar_wait(full_tma + stage, phase);
-        i8_mbar_wait(full_dec + stage, phase);
+        i8_mbar_wait(raw_full + rs, rph);
+        i8_mbar_wait(op_full + os, oph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = i8_smem_u32(smem + stage * stage_bytes);
-        const uint32_t sd = sa + 2 * PGI_TILE_A;
+        const uint32_t sa = i8_smem_u32(ops + os * 2 * PGI_TILE_A);
+        const uint32_t sd = i8_smem_u32(raw + rs * raw_bytes);
 #pragma unroll
         for (int j = 0; j < PGI_BK / 32; j++) {
           if (MODE == PGI_XA) {
@@ -132,23 +142,26 @@ pg_i8_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
           }
           acc = 1;
         }
-        i8_commit(empty + stage);
-        if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
+        i8_commit(op_empty + os);
+        i8_commit(raw_empty + rs);
+        if (++rs == (uint32_t)nraw) { rs = 0; rph ^= 1; }
+        if (++os == NOP) { os = 0; oph ^= 1; }
       }
       i8_commit(accbar);
     }
     __syncwarp();
   } else {
     // ===================================================================== decode warps, then epilogue
-    const int dt = threadIdx.x - 64;                 // 0..127
-    uint32_t stage = 0, phase = 0;
+    const int dt = threadIdx.x - 64;                 // 0 .. 32 PGI_DECW - 1
+    uint32_t rs = 0, rph = 0, os = 0, oph = 0;
     for (int kb = kb0; kb < kb1; kb++) {
-      i8_mbar_wait(full_tma + stage, phase);
-      uint8_t* sb = smem + stage * stage_bytes;
-      const uint32_t* pk = reinterpret_cast<const uint32_t*>(sb + 2 * PGI_TILE_A + d_bytes);
+      i8_mbar_wait(raw_full + rs, rph);
+      i8_mbar_wait(op_empty + os, oph ^ 1);
+      uint8_t* sb = ops + os * 2 * PGI_TILE_A;
+      const uint32_t* pk = reinterpret_cast<const uint32_t*>(raw + rs * raw_bytes + d_bytes);
 #pragma unroll
-      for (int it = 0; it < 8; it++) {
-        const int w = it * 128 + dt;                // word index: row r = w >> 3 (SNP), j = w & 7 (16 individuals)
+      for (int it = 0; it < 1024 / (32 * PGI_DECW); it++) {
+        const int w = it * (32 * PGI_DECW) + dt;    // word index: row r = w >> 3 (SNP), j = w & 7 (16 individuals)
         const int r = w >> 3, j = w & 7;
         const uint32_t x = pk[w];
         uint32_t ov[4], oh[4];
@@ -165,8 +178,9 @@ pg_i8_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core's reads
       __syncwarp();
-      if (lane == 0) i8_mbar_arrive(full_dec + stage);
-      if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
+      if (lane == 0) { i8_mbar_arrive(op_full + os); i8_mbar_arrive(raw_empty + rs); }
+      if (++rs == (uint32_t)nraw) { rs = 0; rph ^= 1; }
+      if (++os == NOP) { os = 0; oph ^= 1; }
     }
     // ---- epilogue: this thread owns output row (tile * 128 + m)
     const int q = warp & 3, m = q * 32 + lane;
@@ -180,7 +194,8 @@ pg_i8_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
       a_s = t0; b_s = 0.5 * (t2 - t0);
     }
     double* outp = args.out + (size_t)ks * args.plane_stride + row;
-    for (int c0 = 0; c0 < N; c0 += 32) {              // 32 accumulator columns = 4 output columns x 8 digits
+    // two warps share a TMEM lane quarter: they take alternate 32-column chunks
+    for (int c0 = 32 * ((warp - 2) >> 2); c0 < N; c0 += 32 * (PGI_DECW / 4)) {      // 32 accumulator columns = 4 output columns x 8 digits
       uint32_t v[32], h[32];
       i8_tmem_ld32(taddr + c0, v);
       if (MODE == PGI_XA) i8_tmem_ld32(taddr + 256 + c0, h);
@@ -363,8 +378,11 @@ static int pg_i8_run(eb_ctx* c, const uint8_t* work, int64_t wpitch, int npad, c
       if ((rc = c->pg_part.ensure((size_t)nsplit * a.plane_stride))) return rc;
       a.out = c->pg_part.p;
     }
-    const int nstages = MODE == PGI_XTB ? 2 : 3;
-    const size_t smem = (size_t)nstages * (2 * PGI_TILE_A + nB * N * 128 + PGI_PACKED) + 1024 + 256;
+    const size_t raw_bytes = (size_t)nB * N * 128 + PGI_PACKED;
+    const size_t fixed = (size_t)2 * 2 * PGI_TILE_A + 1024 + 512;
+    a.nraw = (int)std::max<size_t>(2, std::min<size_t>(6, (227 * 1024 - fixed) / raw_bytes));
+    const size_t smem = fixed + (size_t)a.nraw * raw_bytes;
+    if (smem > 227 * 1024) { set_error("pg_i8: stage layout does not fit shared memory (N %d)", N); return EB_ERR_STATE; }
     EB_CUDA(cudaFuncSetAttribute(pg_i8_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pg_i8_kernel<MODE><<<dim3(gx, nsplit), PGI_THREADS, smem, c->stream>>>(mapW, mapD, a);
     EB_CHECK_LAUNCH(c);
