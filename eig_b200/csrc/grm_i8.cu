@@ -3,19 +3,19 @@
 //
 // The FP64 pipe of sm_100a ends at ~37 TFLOP/s (DMMA.8x8x4); the integer tensor pipe is ~100x wider.  The GRM admits an exact integer
 // formulation because a column of the normalised genotype matrix only takes three values: x_is = v_is (a_s + b_s k_is) with the raw
-// genotype k in {0,1,2}, the validity bit v and two per-SNP FP64 numbers a_s = -mean * scale, b_s = scale.  With the three NON-NEGATIVE
-// integer bases  h = k v,  hbar = (2 - k) v,  v  one has, for every pair of individuals,
-//        x_is x_js = w2_s h_is h_js + w3_s hbar_is hbar_js - w1_s v_is v_js,
-//        w2 = b^2 + ab/2 = scale^2 (1 - mean/2) >= 0,   w3 = -ab/2 = scale^2 mean/2 >= 0,   w1 = -(a^2 + 2ab) = scale^2 mean (2 - mean) >= 0,
-// i.e. three diagonally weighted integer SYRKs.  Every weight is cut into NSL 7-bit digits of a common fixed-point scale
-// (w = sum_k m_k 2^(E - 7(k+1)), m_k in [0,127]); digit k of the weights multiplies one operand (m_k * basis <= 254 fits a byte), the
-// other operand is the bare basis, and  C_k = sum_s basis_is (m_k,s basis_js)  is an u8 x u8 -> s32 tensor-core product that is EXACT.
-// XTX = sum_k 2^(E-7(k+1)) C_k is then accumulated in FP64 by the epilogue.  With NSL = 8 the weights carry 56 bits below the largest
-// one -- more than the 53 of the FP64 products the DMMA path rounds -- and the sum over SNPs has NO rounding error at all, so the
+// genotype k in {0,1,2}, the validity bit v and two per-SNP FP64 numbers a_s = -mean * scale, b_s = scale.  With the two integer bases
+// h = k v in {0,1,2} and v in {0,1} one has, for every pair of individuals,
+//        x_is x_js = h_is T1_s[k_js] + v_is T2_s[k_js],     T1[k] = ab + b^2 k,   T2[k] = a^2 + ab k   (0 for a missing genotype),
+// i.e. two integer-times-table products per SNP (each is unsymmetric, their sum is the symmetric GRM; only its lower triangle is
+// computed).  Every table entry is cut into NSL signed 7-bit digits of one fixed-point scale (T = sum_k m_k 2^(E - 7(k+1)), |m_k| <= 127):
+// digit k of T[code] is ONE byte of the weighted operand, the other operand is the bare basis, and
+// C_k = sum_s h_is m_k(T1_s[k_js]) + v_is m_k(T2_s[k_js]) is a u8 x s8 -> s32 tensor-core product that is EXACT.
+// XTX = sum_k 2^(E-7(k+1)) C_k is then accumulated in FP64 by the epilogue.  With NSL = 8 the table entries carry 56 bits below the
+// largest one -- more than the 53 of the FP64 products the DMMA path rounds -- and the sum over SNPs has NO rounding error at all, so the
 // result is closer to the exact GRM than either FP64 implementation (the tests compare all three).
 // SNPs without a missing genotype (class F) need one basis only:  x_i x_j = b^2 k_i k_j + ab (k_i + k_j) + a^2, the last two terms
 // being rank one (an FP64 mat-vec over the packed matrix, added by the finalize kernel); 128-SNP blocks that contain only such SNPs
-// are skipped in the hbar / v segments, so complete data costs NSL integer passes and data with missing genotypes 3 NSL.
+// are skipped in the v segment, so complete data costs NSL integer passes and data with missing genotypes 2 NSL.
 //
 // Kernels:
 //   i8_prep_kernel       per SNP: class, the three weights, the largest exponent, block flags, rank-one coefficients
@@ -63,20 +63,16 @@ __device__ __forceinline__ constexpr uint32_t i8_idesc(int a_signed, int b_signe
 
 // ------------------------------------------------------------------------------------------------------------ the GEMM
 // Work items: (tile, group).  A tile is 256 GRM rows (N side, block nb) x 128 GRM columns (M side, block mb) of the lower triangle.
-// A group is one weight digit k (splitv: one digit of {h, hbar} or of {v}); its segments accumulate into one TMEM buffer over all the
+// A group is one digit k; its (one or two) segments accumulate into one TMEM buffer over all the
 // SNP blocks of the slab, then the epilogue adds scale[k] * C to the FP64 tile.  All three roles walk the same item sequence.
 struct I8Walk {
   int gps, ngroups;
   __device__ __forceinline__ I8Walk(const I8Args& a) {
-    gps = (a.splitv && a.nseg == 3) ? 2 : 1;
-    ngroups = a.nsl * gps;
+    gps = 1;
+    ngroups = a.nsl;
   }
   __device__ __forceinline__ void group(const I8Args& a, int g, int& k, int& seg0, int& seg1, bool& neg) const {
-    k = g / gps;
-    const int part = g - k * gps;
-    if (gps == 1) { seg0 = 0; seg1 = a.nseg; neg = false; }
-    else if (part == 0) { seg0 = 0; seg1 = 2; neg = false; }
-    else { seg0 = 2; seg1 = 3; neg = true; }
+    k = g; seg0 = 0; seg1 = a.nseg; neg = false;
   }
 };
 
@@ -148,8 +144,7 @@ grm_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
           const uint32_t tacc = tmem_base + buf * I8_TN;
           uint32_t acc = 0;
           for (int seg = seg0; seg < seg1; seg++) {
-            // the validity basis of the merged form is stored as -1 (s8) so that its non-negative weight digits subtract
-            const uint32_t idesc = i8_idesc((seg == 2 && !args.splitv) ? 1 : 0, 0);
+            const uint32_t idesc = i8_idesc(0, 1);                   // A: unsigned basis, B: signed digits
             for (int kb = 0; kb < args.nkb; kb++) {
               if (seg > 0 && !args.kbflag[kb]) continue;
               i8_mbar_wait(full + stage, phase);
@@ -374,7 +369,7 @@ grm_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           const uint32_t tacc = tmem_base + buf * 256;
           uint32_t acc = 0;
           for (int seg = seg0; seg < seg1; seg++) {
-            const uint32_t idesc = i8p_idesc((seg == 2 && !args.splitv) ? 1 : 0, 0);
+            const uint32_t idesc = i8p_idesc(0, 1);                  // A: unsigned basis, B: signed digits
             for (int kb = 0; kb < args.nkb; kb++) {
               if (seg > 0 && !args.kbflag[kb]) continue;
               i8_mbar_wait(full + stage, phase);
@@ -454,18 +449,24 @@ grm_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 // ------------------------------------------------------------------------------------------------------------ preparation
 // prep[0] = largest exponent of a weight (frexp convention: w < 2^E), prep[1] = blocks with a missing genotype, prep[2] = used SNPs,
 // prep[3] = sum of the exponents of w2 over the used SNPs (for the digit count)
-__device__ __forceinline__ void i8_weights(const double* __restrict__ table, const int* __restrict__ nmiss, const uint8_t* __restrict__ used,
-                                           int64_t s, int64_t nsnp, bool& use, bool& classF, double& a, double& b, double& w2, double& w3, double& w1) {
+// Per-SNP 3-entry tables of the weighted operand (entry = genotype code 0, 1, 2; missing -> 0):
+//   T1[k] = ab + b^2 k  pairs with the genotype basis h,   T2[k] = a^2 + ab k  pairs with the validity basis v,
+//   x_i x_j = h_i T1[k_j] + v_i T2[k_j]   for every pair of individuals (zero as soon as one of them is missing).
+// SNPs without a missing genotype (class F): T1[k] = b^2 k only, the rest is rank one (coef = ab, asq = a^2).
+__device__ __forceinline__ void i8_tables(const double* __restrict__ table, const int* __restrict__ nmiss, const uint8_t* __restrict__ used,
+                                          int64_t s, int64_t nsnp, bool& use, bool& classF, double& a, double& b, double (&T1)[3], double (&T2)[3]) {
   use = s < nsnp && used[s];
-  a = b = w2 = w3 = w1 = 0.0;
+  a = b = 0.0;
+  T1[0] = T1[1] = T1[2] = T2[0] = T2[1] = T2[2] = 0.0;
   classF = true;
   if (!use) return;
   const double t0 = table[4 * s], t2 = table[4 * s + 2];
   a = t0; b = 0.5 * (t2 - t0);
   classF = nmiss[s] == 0;
-  if (classF) { w2 = b * b; return; }
-  const double hab = 0.5 * a * b;
-  w2 = fmax(b * b + hab, 0.0); w3 = fmax(-hab, 0.0); w1 = fmax(-(a * a + 4.0 * hab), 0.0);
+  const double bb = b * b, ab = a * b;
+  if (classF) { T1[1] = bb; T1[2] = 2.0 * bb; return; }
+  T1[0] = ab; T1[1] = ab + bb; T1[2] = ab + 2.0 * bb;
+  T2[0] = a * a; T2[1] = a * a + ab; T2[2] = a * a + 2.0 * ab;
 }
 
 __global__ void __launch_bounds__(256) i8_prep_kernel(const double* __restrict__ table, const int* __restrict__ nmiss, const uint8_t* __restrict__ used,
@@ -473,12 +474,13 @@ __global__ void __launch_bounds__(256) i8_prep_kernel(const double* __restrict__
                                                       double* __restrict__ asq, long long* __restrict__ prep) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= mpad) return;
-  bool use, classF; double a, b, w2, w3, w1;
-  i8_weights(table, nmiss, used, s, nsnp, use, classF, a, b, w2, w3, w1);
+  bool use, classF; double a, b, T1[3], T2[3];
+  i8_tables(table, nmiss, used, s, nsnp, use, classF, a, b, T1, T2);
   coef[s] = (use && classF) ? a * b : 0.0;
   asq[s] = (use && classF) ? a * a : 0.0;
   if (!use) return;
-  const double wmax = fmax(w2, fmax(w3, w1));
+  const double w2 = b * b;
+  const double wmax = fmax(fmax(fabs(T1[0]), fmax(fabs(T1[1]), fabs(T1[2]))), fmax(fabs(T2[0]), fmax(fabs(T2[1]), fabs(T2[2]))));
   int e = 0, e2 = 0;
   frexp(wmax, &e); frexp(w2, &e2);
   if (wmax > 0.0) atomicMax(reinterpret_cast<int*>(prep), e + 4096);     // biased: exponents may be negative
@@ -542,35 +544,39 @@ __global__ void __launch_bounds__(256) i8_rank1_reduce_kernel(const double* __re
   }
 }
 
-// Packed rows of one slab -> byte operands.  A[seg][row][npad]: the bare basis (h | hbar | v, the latter as -1 unless splitv);
-// B[seg * nsl + k][row][npad]: digit k of the segment's weight times the basis.  One block per SNP; one thread per 32-bit packed word
+// Packed rows of one slab -> byte operands.  A[seg][row][npad]: the bare basis (h | v);
+// B[seg * nsl + k][row][npad]: digit k (signed) of the segment's table entry T1 / T2 for the genotype.  One block per SNP; one thread per 32-bit packed word
 // (16 individuals): the four 2-bit codes of a byte become the selector of one PRMT over the 4-entry table of the output matrix.
 __global__ void __launch_bounds__(256) i8_transform_kernel(const uint8_t* __restrict__ work, int64_t wpitch, const double* __restrict__ table,
                                                            const int* __restrict__ nmiss, const uint8_t* __restrict__ used, const uint8_t* __restrict__ kbflag,
-                                                           int64_t nsnp, int64_t s_first, int ks_alloc, int npad, int nsl, int E, int nseg, int splitv,
+                                                           int64_t nsnp, int64_t s_first, int ks_alloc, int npad, int nsl, int E, int nseg,
                                                            uint8_t* __restrict__ A, uint8_t* __restrict__ B) {
-  __shared__ uint32_t lut[3][1 + I8_MAXSL];
+  __shared__ uint32_t lut[2][1 + I8_MAXSL];
   const int row = blockIdx.x;
   const int64_t s = s_first + row;
   const bool flagged = kbflag[row / I8_BK] != 0;
-  const int segs = (nseg == 3 && flagged) ? 3 : 1;
-  if (threadIdx.x < 3 * (1 + nsl)) {
+  const int segs = (nseg == 2 && flagged) ? 2 : 1;
+  if (threadIdx.x < 2 * (1 + nsl)) {
     const int seg = threadIdx.x / (1 + nsl), j = threadIdx.x - seg * (1 + nsl);
-    bool use, classF; double a, b, w2, w3, w1;
-    i8_weights(table, nmiss, used, s, nsnp, use, classF, a, b, w2, w3, w1);
-    const double w = seg == 0 ? w2 : (seg == 1 ? w3 : w1);
-    // basis bytes for the codes 0, 1, 2, 3 (3 = missing -> 0)
-    const uint32_t basis = seg == 0 ? 0x00020100u : (seg == 1 ? 0x00000102u : 0x00010101u);
+    bool use, classF; double a, b, T1[3], T2[3];
+    i8_tables(table, nmiss, used, s, nsnp, use, classF, a, b, T1, T2);
     uint32_t word;
     if (j == 0) {
-      word = (seg == 2 && !splitv) ? 0x00FFFFFFu : basis;
+      word = seg == 0 ? 0x00020100u : 0x00010101u;                   // bare basis for the codes 0, 1, 2, 3: h | v
     } else {
+      // digit k (7 bits, most significant first, with the sign of the value) of the three table entries: one byte each
       const int k = j - 1;
-      unsigned long long qv = __double2ull_rn(ldexp(w, 7 * nsl - E));
-      const unsigned long long qmax = (nsl * 7 >= 64) ? ~0ull : ((1ull << (7 * nsl)) - 1ull);
-      if (qv > qmax) qv = qmax;
-      const uint32_t mk = (uint32_t)((qv >> (7 * (nsl - 1 - k))) & 127ull);
-      word = basis * mk;                                             // every byte <= 254: no carries
+      word = 0;
+#pragma unroll
+      for (int cd = 0; cd < 3; cd++) {
+        const double t = seg == 0 ? T1[cd] : T2[cd];
+        unsigned long long qv = __double2ull_rn(ldexp(fabs(t), 7 * nsl - E));
+        const unsigned long long qmax = (nsl * 7 >= 64) ? ~0ull : ((1ull << (7 * nsl)) - 1ull);
+        if (qv > qmax) qv = qmax;
+        int mk = (int)((qv >> (7 * (nsl - 1 - k))) & 127ull);
+        if (t < 0.0) mk = -mk;
+        word |= ((uint32_t)(mk & 0xFF)) << (8 * cd);
+      }
     }
     lut[seg][j] = word;
   }
@@ -761,8 +767,7 @@ int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push_mode) {
     nsl = std::max(7, std::min(nsl, 9));
   }
   nsl = std::max(1, std::min(nsl, 9));
-  const int splitv = c->opt_i8_splitv ? 1 : 0;
-  const int nseg_all = nflag > 0 ? 3 : 1;
+  const int nseg_all = nflag > 0 ? 2 : 1;
   c->tm.i8_slices = nsl; c->tm.i8_segments = nseg_all; c->tm.i8_flag_blocks = (int)nflag; c->tm.i8_slab_rows = 0;
 
   // slab: as many SNP blocks as the operand budget allows (A: nseg matrices, B: nseg * nsl matrices of [rows][npad] bytes)
@@ -795,7 +800,7 @@ int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push_mode) {
 
   I8Args args;
   memset(&args, 0, sizeof(args));
-  args.npad = npad; args.ntiles = (int)tiles.size(); args.nsl = nsl; args.splitv = splitv;
+  args.npad = npad; args.ntiles = (int)tiles.size(); args.nsl = nsl; args.splitv = 0;
   for (int k = 0; k < nsl; k++) args.scale[k] = ldexp(1.0, Emax - 7 * (k + 1));
   args.tiles = reinterpret_cast<const int2*>(c->i8_tiles.p);
   args.out = c->partial.p;
@@ -826,9 +831,9 @@ int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push_mode) {
       const int kb0 = (int)(s0 / I8_BK), nkb = ks / I8_BK;
       int nfl = 0;
       for (int kb = 0; kb < nkb; kb++) nfl += flag_h[kb0 + kb] ? 1 : 0;
-      const int nseg = nfl > 0 ? 3 : 1;
+      const int nseg = nfl > 0 ? 2 : 1;
       i8_transform_kernel<<<ks, 256, 0, c->stream>>>(c->work.p, c->wpitch, c->table_d.p, c->nmiss_d.p, c->used_d.p, c->i8_flag.p + kb0, c->nsnp, s0,
-                                                     (int)rows, npad, nsl, Emax, nseg, splitv, Aop, Bop);
+                                                     (int)rows, npad, nsl, Emax, nseg, Aop, Bop);
       EB_CHECK_LAUNCH(c);
       args.nkb = nkb; args.nseg = nseg; args.first = first ? 1 : 0; args.kbflag = c->i8_flag.p + kb0;
       // events around every integer GEMM launch: the kernel-only time of the roofline line (eb_timings.i8_gemm_ms)
@@ -849,7 +854,7 @@ int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push_mode) {
       EB_CUDA(cudaEventRecord(c->i8_ev[2 * c->i8_nlaunch + 1], c->stream));
       c->i8_nlaunch++;
       first = false;
-      ops += (double)tiles.size() * tile_macs * 2.0 * (double)I8_BK * nsl * ((double)nkb + 2.0 * nfl * (nseg == 3 ? 1 : 0));
+      ops += (double)tiles.size() * tile_macs * 2.0 * (double)I8_BK * nsl * ((double)nkb + (double)nfl * (nseg == 2 ? 1 : 0));
     }
   }
   c->tm.i8_tera_ops = (float)(ops * 1e-12);

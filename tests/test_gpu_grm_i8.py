@@ -66,7 +66,7 @@ def test_i8_grm_matches_oracle_and_dmma(ctx, nsnp, nind, miss, alt, fancy, rows,
     finally:
         ctx.set_option("i8_splitv", 0); ctx.set_option("i8_slab", 0)
     assert t["grm_method"] == 2 and 7 <= t["i8_slices"] <= 9
-    assert t["i8_segments"] == (3 if miss > 0 else 1)
+    assert t["i8_segments"] == (2 if miss > 0 else 1)
     o = _oracle_grm(P, nind, xindex=xi, fancynorm=fancy, altnormstyle=alt)
     for k in ("c0", "c1", "nmiss", "used"):
         assert np.array_equal(r[k], o[k]), k
