@@ -208,6 +208,9 @@ int grm_trace(eb_ctx* c);        // recompute trace_d / y from xtx
 // pg_i8.cu
 int pg_i8_launch(eb_ctx* c, int mode, const uint8_t* work, int64_t wpitch, int npad, const double* table, const double* In_t, int64_t ld_in,
                  double* Out_t, int64_t ld_out, int ncols, double oscale);
+int pg_i8_slice_wide(eb_ctx* c, const double* In_t, int64_t ld_in, int64_t kvalid, int64_t kpad, int ncols, uint8_t* digits, double* colscale);
+int pg_i8_rows_wide(eb_ctx* c, const uint8_t* work, int64_t wpitch, int npad, const double* table, const uint8_t* digits, const double* colscale,
+                    int ncols, int64_t s0, int nb, double* out, int64_t ld_r);
 // grm_i8.cu
 bool grm_use_i8(const eb_ctx* c);
 int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push);

@@ -1008,13 +1008,38 @@ int shrink_run(eb_ctx* c, int k, int newshrink, double* coords, double* lambda_o
     EB_CHECK_LAUNCH(c);
   }
   // ---- SNP blocks: loadings of every leave-one-out vector and the per-sample sums
+  // Integer tensor-core path (pg_i8.cu): the k leave-one-out matrices are cut into 7-bit digit rows ONCE, then every SNP block is one
+  // launch per eigenvector with the packed block decoded inside the kernel; FP64 path: decode the block to FP64, DMMA GEMM.
+  const int ncp32 = (n + 31) / 32 * 32;
+  const size_t dig_bytes = (size_t)ncp32 * 8 * npad;
+  bool wide_i8 = (c->opt_pg_method == 2 || (c->opt_pg_method == 0 && n >= c->opt_pg_i8_min && mpad >= c->opt_pg_i8_min)) && (npad % 128) == 0 &&
+                 (nb_max % 128) == 0;
+  DevBuf<uint8_t> dig_all;
+  DevBuf<double> csc_all;
+  if (wide_i8) {
+    size_t freeb = 0, totalb = 0;
+    cudaMemGetInfo(&freeb, &totalb);
+    if ((size_t)k * dig_bytes > freeb / 2) wide_i8 = false;        // not enough room for the digit rows of all k matrices: FP64 path
+  }
+  if (wide_i8) {
+    if ((rc = dig_all.ensure((size_t)k * dig_bytes)) || (rc = csc_all.ensure((size_t)k * ncp32))) return rc;
+    for (int i = 0; i < k; i++)
+      if ((rc = pg_i8_slice_wide(c, En.p + (size_t)i * n * npad, npad, n, npad, n, dig_all.p + (size_t)i * dig_bytes, csc_all.p + (size_t)i * ncp32))) return rc;
+  }
   EB_CUDA(cudaMemsetAsync(acc.p, 0, sizeof(double) * (size_t)nz * k * (k + 2) * npad, c->stream));
   for (int64_t s0 = 0; s0 < mpad; s0 += nb_max) {
     const int nb = (int)std::min<int64_t>(nb_max, mpad - s0);
-    shr_decode_kernel<<<dim3((npad + 255) / 256, nb), 256, 0, c->stream>>>(c->work.p, c->wpitch, mtab.p, s0, npad, D.p);
-    EB_CHECK_LAUNCH(c);
-    for (int i = 0; i < k; i++)
-      if ((rc = launch_gemm(c, false, false, D.p, npad, En.p + (size_t)i * n * npad, npad, Ft.p + (size_t)i * nb * npad, npad, nb, n, n))) return rc;
+    if (wide_i8) {
+      for (int i = 0; i < k; i++)
+        if ((rc = pg_i8_rows_wide(c, c->work.p, c->wpitch, npad, mtab.p, dig_all.p + (size_t)i * dig_bytes, csc_all.p + (size_t)i * ncp32, n, s0, nb,
+                                  Ft.p + (size_t)i * nb * npad, npad)))
+          return rc;
+    } else {
+      shr_decode_kernel<<<dim3((npad + 255) / 256, nb), 256, 0, c->stream>>>(c->work.p, c->wpitch, mtab.p, s0, npad, D.p);
+      EB_CHECK_LAUNCH(c);
+      for (int i = 0; i < k; i++)
+        if ((rc = launch_gemm(c, false, false, D.p, npad, En.p + (size_t)i * n * npad, npad, Ft.p + (size_t)i * nb * npad, npad, nb, n, n))) return rc;
+    }
     const dim3 grid((n + 127) / 128, k, nz);
     if (newshrink)
       shr_reduce_kernel<true><<<grid, 128, 0, c->stream>>>(Ft.p, nb, npad, n, k, c->work.p, c->wpitch, ftab.p, c->used_d.p, FF.p, mpad, s0, acc.p);

@@ -38,8 +38,11 @@ struct PgiArgs {
   int ncols;                // real columns
   int nk, nsplit;           // K stages in total, K splits (grid.y)
   int nraw;                 // depth of the TMA ring (digit rows + packed sub-tile)
-  int64_t rows;             // valid output rows
-  int64_t ld_out, plane_stride;
+  int tile0;                // first row tile of this launch (blockIdx.x counts from it)
+  int64_t rows;             // valid output rows (global row index < rows)
+  int64_t out_row0;         // global row that maps to output row 0
+  int64_t ld_l, ld_r;       // output element (row, column l) at out[(row - out_row0) * ld_r + l * ld_l]
+  int64_t plane_stride;
   double oscale;
   const double* table;      // [mpad][4]
   const double* colscale;   // [ncp]: 2^(e_l)
@@ -98,7 +101,7 @@ pg_i8_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  const int tile = blockIdx.x, ks = blockIdx.y;
+  const int tile = args.tile0 + blockIdx.x, ks = blockIdx.y, zg = blockIdx.z;      // zg: group of ncp output columns (digit rows zg * N ..)
   const int kb0 = (int)(((long long)args.nk * ks) / args.nsplit), kb1 = (int)(((long long)args.nk * (ks + 1)) / args.nsplit);
 
   if (warp == 0) {
@@ -112,7 +115,7 @@ pg_i8_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
         // packed sub-tile: 128 SNP rows x 32 bytes (128 individuals)
         if (MODE == PGI_XA) pgi_tma_2d(sb + d_bytes, &mapW, kb * 32, tile * 128, raw_full + rs);
         else pgi_tma_2d(sb + d_bytes, &mapW, tile * 32, kb * 128, raw_full + rs);
-        for (int b = 0; b < nB; b++) pgi_tma_2d(sb + b * N * 128, &mapD, kb * 128, b * N, raw_full + rs);
+        for (int b = 0; b < nB; b++) pgi_tma_2d(sb + b * N * 128, &mapD, kb * 128, (b * (int)gridDim.z + zg) * N, raw_full + rs);
         if (++rs == (uint32_t)nraw) { rs = 0; rph ^= 1; }
       }
     }
@@ -193,7 +196,7 @@ pg_i8_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
       const double t0 = args.table[4 * row], t2 = args.table[4 * row + 2];
       a_s = t0; b_s = 0.5 * (t2 - t0);
     }
-    double* outp = args.out + (size_t)ks * args.plane_stride + row;
+    double* outp = args.out + (size_t)ks * args.plane_stride + (size_t)(row - args.out_row0) * args.ld_r;
     // two warps share a TMEM lane quarter: they take alternate 32-column chunks
     for (int c0 = 32 * ((warp - 2) >> 2); c0 < N; c0 += 32 * (PGI_DECW / 4)) {      // 32 accumulator columns = 4 output columns x 8 digits
       uint32_t v[32], h[32];
@@ -201,7 +204,7 @@ pg_i8_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
       if (MODE == PGI_XA) i8_tmem_ld32(taddr + 256 + c0, h);
 #pragma unroll
       for (int cc = 0; cc < 4; cc++) {
-        const int l = (c0 >> 3) + cc;
+        const int l = zg * args.ncp + (c0 >> 3) + cc;
         if (l >= args.ncols) break;
         const double sc = args.colscale[l];
         double sv = 0.0, sh = 0.0, f = 1.0 / 128.0;
@@ -212,7 +215,7 @@ pg_i8_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
           f *= 1.0 / 128.0;
         }
         const double y = (MODE == PGI_XA ? (a_s * sv + b_s * sh) : sv) * sc * args.oscale;
-        if (row < args.rows) outp[(size_t)l * args.ld_out] = y;
+        if (row < args.rows) outp[(size_t)l * args.ld_l] = y;
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -229,7 +232,7 @@ pg_i8_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ C
 // colmax[b][l] = max_k |w_b(k) In[l][k]|, w = 1 (XA) or a_k, b_k (XTB; the two share one scale per column: max over both)
 template <int MODE>
 __global__ void __launch_bounds__(256) pgi_colmax_kernel(const double* __restrict__ In, int64_t ld_in, int64_t klen, const double* __restrict__ table,
-                                                         unsigned long long* __restrict__ colmax) {
+                                                         unsigned long long* __restrict__ colmax) {      // klen: VALID K entries
   __shared__ double red[256];
   const int l = blockIdx.y;
   double mx = 0.0;
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(256) pgi_colmax_kernel(const double* __restric
 }
 // colscale[l] = 2^(e_l), e_l from frexp of the column maximum (value < 2^e)
 __global__ void pgi_colscale_kernel(const unsigned long long* __restrict__ colmax, int ncp, double* __restrict__ colscale) {
-  const int l = threadIdx.x;
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= ncp) return;
   const double mx = __longlong_as_double((long long)colmax[l]);
   int e = 0;
@@ -363,14 +366,15 @@ static int pg_i8_run(eb_ctx* c, const uint8_t* work, int64_t wpitch, int npad, c
     const unsigned gk = (unsigned)std::min<int64_t>((klen + 255) / 256, 4 * c->num_sms);
     pgi_colmax_kernel<MODE><<<dim3(gk, take), 256, 0, c->stream>>>(in, ld_in, klen, table, colmax);
     EB_CHECK_LAUNCH(c);
-    pgi_colscale_kernel<<<1, PGI_MAXC, 0, c->stream>>>(colmax, ncp, colscale);
+    pgi_colscale_kernel<<<(ncp + 63) / 64, 64, 0, c->stream>>>(colmax, ncp, colscale);
     EB_CHECK_LAUNCH(c);
     pgi_slice_kernel<MODE><<<dim3((unsigned)((klen / 16 + 255) / 256), ncp), 256, 0, c->stream>>>(in, ld_in, klen, klen, take, ncp, table, colscale,
                                                                                                   reinterpret_cast<int8_t*>(c->pgi_digits.p));
     EB_CHECK_LAUNCH(c);
     if ((rc = pgi_make_map(&mapD, c->pgi_digits.p, (int64_t)nB * N, klen, 128, N, true))) return rc;
     PgiArgs a;
-    a.ncp = ncp; a.ncols = take; a.nk = nk; a.nsplit = nsplit; a.rows = rows; a.ld_out = ld_out; a.oscale = oscale; a.table = table;
+    a.ncp = ncp; a.ncols = take; a.nk = nk; a.nsplit = nsplit; a.rows = rows; a.oscale = oscale; a.table = table;
+    a.tile0 = 0; a.out_row0 = 0; a.ld_l = ld_out; a.ld_r = 1;
     a.colscale = colscale;
     a.plane_stride = 0; a.out = out;
     if (nsplit > 1) {
@@ -392,6 +396,54 @@ static int pg_i8_run(eb_ctx* c, const uint8_t* work, int64_t wpitch, int npad, c
     }
     done += take;
   }
+  return 0;
+}
+
+// ---- rows = SNPs against a WIDE dense operand (shrinkmode: F_i = D Enew_i^T, one m x m matrix per eigenvector, smartpca.c:4340-4347):
+// the digits of all columns are cut once (pg_i8_slice_wide), then every SNP block is one launch whose grid.z walks the column groups.
+// digits: [ncp32 * 8][kpad] bytes, colscale: [ncp32], ncp32 = columns rounded up to a multiple of 32
+int pg_i8_slice_wide(eb_ctx* c, const double* In_t, int64_t ld_in, int64_t kvalid, int64_t kpad, int ncols, uint8_t* digits, double* colscale) {
+  int rc;
+  const int ncp = (ncols + PGI_MAXC - 1) / PGI_MAXC * PGI_MAXC;
+  if ((rc = c->pgi_scale.ensure((size_t)ncp + 8))) return rc;
+  unsigned long long* colmax = reinterpret_cast<unsigned long long*>(c->pgi_scale.p);
+  EB_CUDA(cudaMemsetAsync(colmax, 0, sizeof(unsigned long long) * ncp, c->stream));
+  const unsigned gk = (unsigned)std::min<int64_t>((kvalid + 255) / 256, 8);
+  for (int l0 = 0; l0 < ncols; l0 += 32768) {
+    const int nl = std::min(32768, ncols - l0);
+    pgi_colmax_kernel<PGI_XA><<<dim3(gk, nl), 256, 0, c->stream>>>(In_t + (size_t)l0 * ld_in, ld_in, kvalid, nullptr, colmax + l0);
+    EB_CHECK_LAUNCH(c);
+  }
+  pgi_colscale_kernel<<<(ncp + 63) / 64, 64, 0, c->stream>>>(colmax, ncp, colscale);
+  EB_CHECK_LAUNCH(c);
+  for (int l0 = 0; l0 < ncp; l0 += 32768) {
+    const int nl = std::min(32768, ncp - l0);
+    pgi_slice_kernel<PGI_XA><<<dim3((unsigned)((kpad / 16 + 255) / 256), nl), 256, 0, c->stream>>>(
+        In_t + (size_t)l0 * ld_in, ld_in, kvalid, kpad, std::max(0, std::min(nl, ncols - l0)), nl, nullptr, colscale + l0,
+        reinterpret_cast<int8_t*>(digits) + (size_t)l0 * PGI_ND * kpad);
+    EB_CHECK_LAUNCH(c);
+  }
+  return 0;
+}
+// out[(s - s0) * ld_r + a] = sum_t x_st In[a][t] for the SNP rows [s0, s0 + nb) (multiples of 128) and all `ncols` columns
+int pg_i8_rows_wide(eb_ctx* c, const uint8_t* work, int64_t wpitch, int npad, const double* table, const uint8_t* digits, const double* colscale,
+                    int ncols, int64_t s0, int nb, double* out, int64_t ld_r) {
+  int rc;
+  const int ncg = (ncols + PGI_MAXC - 1) / PGI_MAXC;
+  const int N = PGI_MAXC * PGI_ND;
+  CUtensorMap mapW, mapD;
+  if ((rc = pgi_make_map(&mapW, work, c->mpad, wpitch, 32, 128, false))) return rc;
+  if ((rc = pgi_make_map(&mapD, digits, (int64_t)ncg * N, npad, 128, N, true))) return rc;
+  PgiArgs a;
+  a.ncp = PGI_MAXC; a.ncols = ncols; a.nk = npad / PGI_BK; a.nsplit = 1; a.rows = s0 + nb; a.oscale = 1.0; a.table = table;
+  a.colscale = colscale; a.tile0 = (int)(s0 / 128); a.out_row0 = s0; a.ld_l = 1; a.ld_r = ld_r; a.plane_stride = 0; a.out = out;
+  const size_t raw_bytes = (size_t)N * 128 + PGI_PACKED;
+  const size_t fixed = (size_t)2 * 2 * PGI_TILE_A + 1024 + 512;
+  a.nraw = (int)std::max<size_t>(2, std::min<size_t>(6, (227 * 1024 - fixed) / raw_bytes));
+  const size_t smem = fixed + (size_t)a.nraw * raw_bytes;
+  EB_CUDA(cudaFuncSetAttribute(pg_i8_kernel<PGI_XA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pg_i8_kernel<PGI_XA><<<dim3((unsigned)(nb / 128), 1, (unsigned)ncg), PGI_THREADS, smem, c->stream>>>(mapW, mapD, a);
+  EB_CHECK_LAUNCH(c);
   return 0;
 }
 
