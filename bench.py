@@ -421,7 +421,10 @@ def run_b200(args):
         if method == 2:
             roof = {"bound": "tensor", "kernel": "grm_i8_pair_kernel (tcgen05.mma.cta_group::2.kind::i8, s32 accumulators in TMEM)",
                     "achieved": achieved, "peak": peak8, "unit": "TFLOP/s", "op": "8-bit integer multiply-add = 2 ops (TOP/s)",
-                    "frac": achieved / peak8, "frac_of_nominal_4500": achieved / 4500.0, "traffic": traffic, "traffic_source": traffic_src,
+                    "frac": achieved / peak8, "frac_of_nominal_4500": achieved / 4500.0,
+                    "frac_of_2x_bf16_burst": (achieved / (2.0 * bf_b)) if bf_b else None,
+                    "frac_of_nominal_at_measured_clock": (achieved / (4500.0 * clocks["sm_mhz"] / clocks["sm_max_mhz"]))
+                    if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") else None, "traffic": traffic, "traffic_source": traffic_src,
                     "kernel_ms": gemm_ms, "launches_per_step": int(kern[-1]["grm_launches"]), "snp_rows_per_launch": int(kern[-1]["i8_slab_rows"]),
                     "digits": int(kern[-1]["i8_slices"]), "bases": int(kern[-1]["i8_segments"]), "peak_source": psrc,
                     "algorithmic": "tiles x 256 x 256 x SNP rows x digits x bases x 2 ops per launch (256 x 256 lower-triangle tiles incl. the diagonal ones; "

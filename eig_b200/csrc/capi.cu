@@ -581,7 +581,6 @@ int eb_set_option(eb_ctx* c, const char* key, int value) {
   if (!strcmp(key, "i8_min")) { c->opt_i8_min = value; return 0; }
   if (!strcmp(key, "i8_slices")) { c->opt_i8_slices = value; return 0; }
   if (!strcmp(key, "i8_slab")) { c->opt_i8_slab = value; return 0; }
-  if (!strcmp(key, "i8_splitv")) { c->opt_i8_splitv = value; return 0; }
   if (!strcmp(key, "i8_pair")) { c->opt_i8_pair = value; return 0; }
   if (!strcmp(key, "i8_sync")) { c->opt_i8_sync = value; return 0; }
   set_error("eb_set_option: unknown key '%s'", key);

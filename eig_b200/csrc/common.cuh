@@ -178,7 +178,6 @@ struct eb_ctx {
   int opt_i8_slab = 0;              // 0 = as many SNPs per slab as memory allows, else the cap (tests: several slabs)
   int opt_i8_pair = 1;              // 1 = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles), 0 = one CTA per 128 x 256 tile
   int opt_i8_sync = 0;              // pair kernel: passes a cluster may run ahead of the slowest one (-1: no synchronisation)
-  int opt_i8_splitv = 0;            // 1 = validity basis in its own accumulator with a negative scale instead of a signed operand
 
   // packed x skinny products on the integer tensor cores (pg_i8.cu)
   eb::DevBuf<uint8_t> pgi_digits;   // 7-bit digit rows of the skinny operand: [1 or 2][columns x 8][K]

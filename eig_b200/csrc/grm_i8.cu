@@ -46,7 +46,7 @@ constexpr int I8_THREADS = 192;                  // warp 0 TMA, warp 1 MMA + TME
 constexpr int I8_MAXSL = 10;
 
 struct I8Args {
-  int npad, ntiles, nkb, nsl, nseg, splitv, first;
+  int npad, ntiles, nkb, nsl, nseg, first;
   double scale[I8_MAXSL];                        // 2^(E - 7 (k + 1))
   int sync_lag;                                  // pair kernel: -1 = free-running clusters, else passes a cluster may run ahead of the slowest
   unsigned int* sync_ctr;                        // pair kernel: arrivals at pass boundaries (zeroed before the launch), [2] = time-outs of the whole pass
@@ -800,7 +800,7 @@ int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push_mode) {
 
   I8Args args;
   memset(&args, 0, sizeof(args));
-  args.npad = npad; args.ntiles = (int)tiles.size(); args.nsl = nsl; args.splitv = 0;
+  args.npad = npad; args.ntiles = (int)tiles.size(); args.nsl = nsl;
   for (int k = 0; k < nsl; k++) args.scale[k] = ldexp(1.0, Emax - 7 * (k + 1));
   args.tiles = reinterpret_cast<const int2*>(c->i8_tiles.p);
   args.out = c->partial.p;

@@ -199,8 +199,7 @@ void eigvals (double *mat, double *evals, int n);
  * cores (grm_i8_pair_kernel: tcgen05.mma kind::i8, s32 accumulators in TMEM, FP64 weights as 7-bit digits, FP64 accumulation);
  * "i8_slices" = 0 auto (>= 52 bits below the typical per-SNP weight: 8 digits on ordinary data) | 1..9 digits;
  * "i8_slab" = cap on the SNP rows per operand slab (0: what memory allows); "i8_pair" = 1 CTA pairs (default) | 0 single CTAs;
- * "i8_sync" = passes a cluster may run ahead of the slowest (default 0, -1 = free running); "i8_splitv" = 1: the validity basis
- * in an accumulator of its own instead of a signed operand.  All ranks of a communicator must use the same "grm_method".
+ * "i8_sync" = passes a cluster may run ahead of the slowest (default 0, -1 = free running).  All ranks of a communicator must use the same "grm_method".
  * Packed x skinny products (fastmode, loadings / projections, lsqproj, shrinkmode's mat-vecs; kjg_fpca.c:104-178):
  * "pg_method" = 0 auto (integer tensor cores from "pg_i8_min" rows and SNPs, default 2048) | 1 FP64 DMMA (packed_gemm_kernel) |
  * 2 integer tensor cores with in-kernel decode (pg_i8_kernel).

@@ -33,20 +33,18 @@ def _both(ctx, **kw):
 
 
 CASES = [
-    # nsnp, nind, missing, altnorm, fancynorm, rows, splitv, slab
-    (7, 5, 0.0, 0, 1, None, 0, 0),
-    (300, 101, 0.10, 1, 1, None, 0, 0),
-    (300, 101, 0.10, 1, 1, None, 1, 0),
-    (1000, 333, 0.30, 0, 1, "subset", 0, 256),
-    (513, 128, 0.0, 1, 0, None, 0, 0),
-    (2049, 700, 0.05, 1, 1, "subset", 0, 512),
-    (2049, 700, 0.05, 1, 1, "subset", 1, 512),
-    (1500, 1100, 0.0, 1, 1, None, 0, 384),
+    # nsnp, nind, missing, altnorm, fancynorm, rows, slab
+    (7, 5, 0.0, 0, 1, None, 0),
+    (300, 101, 0.10, 1, 1, None, 0),
+    (1000, 333, 0.30, 0, 1, "subset", 256),
+    (513, 128, 0.0, 1, 0, None, 0),
+    (2049, 700, 0.05, 1, 1, "subset", 512),
+    (1500, 1100, 0.0, 1, 1, None, 384),
 ]
 
 
-@pytest.mark.parametrize("nsnp,nind,miss,alt,fancy,rows,splitv,slab", CASES)
-def test_i8_grm_matches_oracle_and_dmma(ctx, nsnp, nind, miss, alt, fancy, rows, splitv, slab):
+@pytest.mark.parametrize("nsnp,nind,miss,alt,fancy,rows,slab", CASES)
+def test_i8_grm_matches_oracle_and_dmma(ctx, nsnp, nind, miss, alt, fancy, rows, slab):
     g = synth.genotypes(11, nsnp, nind, missing=miss, npops=3, delta=0.2)
     g[0, :] = -1            # an all-missing SNP
     g[1, :] = 2             # a monomorphic SNP
@@ -59,12 +57,11 @@ def test_i8_grm_matches_oracle_and_dmma(ctx, nsnp, nind, miss, alt, fancy, rows,
         xi = np.sort(rs.choice(nind, size=nind - nind // 5, replace=False)).astype(np.int32)
     ctx.upload_packed(P, nind)
     ctx.set_rows(xi)
-    ctx.set_option("i8_splitv", splitv)
     ctx.set_option("i8_slab", slab)
     try:
         d, r, t = _both(ctx, fancynorm=fancy, altnormstyle=alt)
     finally:
-        ctx.set_option("i8_splitv", 0); ctx.set_option("i8_slab", 0)
+        ctx.set_option("i8_slab", 0)
     assert t["grm_method"] == 2 and 7 <= t["i8_slices"] <= 9
     assert t["i8_segments"] == (2 if miss > 0 else 1)
     o = _oracle_grm(P, nind, xindex=xi, fancynorm=fancy, altnormstyle=alt)
