@@ -348,6 +348,8 @@ static int pg_i8_run(eb_ctx* c, const uint8_t* work, int64_t wpitch, int npad, c
   const unsigned gx = (unsigned)((rows + 127) / 128);
   int nsplit = (int)std::min<int64_t>(std::min<int64_t>(16, std::max(1, nk / 16)), (8LL * c->num_sms + gx - 1) / gx);
   nsplit = std::max(1, nsplit);
+  // s32 accumulators: at most 2 x 127 + 127 per K element, so a split must stay below 2^31 / 381 = 5.6 M elements (whole-genome SNP counts)
+  nsplit = std::max(nsplit, (int)((klen + (4ll << 20) - 1) / (4ll << 20)));
   CUtensorMap mapW, mapD;
   if ((rc = pgi_make_map(&mapW, work, c->mpad, wpitch, 32, 128, false))) return rc;
   const int nB = MODE == PGI_XTB ? 2 : 1;
