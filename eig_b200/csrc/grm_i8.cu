@@ -18,12 +18,14 @@
 // are skipped in the v segment, so complete data costs NSL integer passes and data with missing genotypes 2 NSL.
 //
 // Kernels:
-//   i8_prep_kernel       per SNP: class, the three weights, the largest exponent, block flags, rank-one coefficients
+//   i8_prep_kernel       per SNP: class, the two 3-entry tables, the largest exponent, block flags, rank-one coefficients
 //   i8_rank1_kernel      r_i = sum_{s in F} a_s b_s k_is  (packed matrix read once, FP64, fixed summation order)
 //   i8_transform_kernel  packed 2-bit rows -> byte operands [matrix][SNP][individual] (MN-major for the MMA, PRMT as a 4-entry LUT)
 //   grm_i8_kernel        persistent, warp-specialised: TMA producer (128B-swizzled 3-D tensor maps) -> 4-stage mbarrier ring ->
 //                        one thread issuing tcgen05.mma.kind::i8 (M 128 x N 256 x K 32, both operands MN-major) into a
 //                        double-buffered TMEM accumulator -> 4 epilogue warps (tcgen05.ld, s32 -> f64, scaled FP64 add into the tile)
+//   grm_i8_pair_kernel   the same on CTA pairs (cluster of 2, tcgen05.mma.cta_group::2, 256 x 256 tiles, 6 stages) with a pass-level
+//                        synchronisation of the clusters that keeps their shared operand columns in L2 -- the default
 //   grm_i8_finalize_kernel / grm_i8_push_kernel   rank-one terms, mirror (symit2) | tiles to their owners' receive buffers (sharded)
 #include <math.h>
 #include <string.h>
