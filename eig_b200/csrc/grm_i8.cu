@@ -500,28 +500,30 @@ __global__ void __launch_bounds__(256) i8_count_flags_kernel(const uint8_t* __re
 // pad rows read code 3 and are masked by the finalize kernel).  One thread = one 32-bit word = 16 individuals.
 constexpr int I8_R1_CHUNK = 1024;
 __global__ void __launch_bounds__(128) i8_rank1_kernel(const uint8_t* __restrict__ work, int64_t wpitch, int64_t mpad, const double* __restrict__ coef,
-                                                       double* __restrict__ rpart, int npad) {
+                                                       double* __restrict__ rpart, int npad, int nchunks) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= (int)(wpitch >> 2)) return;
-  const int64_t s0 = (int64_t)blockIdx.y * I8_R1_CHUNK, s1 = min(s0 + (int64_t)I8_R1_CHUNK, mpad);
-  double acc[16];
+  for (int chunk = blockIdx.y; chunk < nchunks; chunk += gridDim.y) {      // grid.y is capped at 65,535: very long SNP axes wrap around
+    const int64_t s0 = (int64_t)chunk * I8_R1_CHUNK, s1 = min(s0 + (int64_t)I8_R1_CHUNK, mpad);
+    double acc[16];
 #pragma unroll
-  for (int i = 0; i < 16; i++) acc[i] = 0.0;
-  for (int64_t s = s0; s < s1; s++) {
-    const double cf = coef[s];
-    if (cf == 0.0) continue;                                           // warp-uniform
-    const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(work + s * wpitch) + w);
-    const double c2 = cf + cf;
+    for (int i = 0; i < 16; i++) acc[i] = 0.0;
+    for (int64_t s = s0; s < s1; s++) {
+      const double cf = coef[s];
+      if (cf == 0.0) continue;                                           // warp-uniform
+      const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(work + s * wpitch) + w);
+      const double c2 = cf + cf;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-      const uint32_t code = (x >> (((i >> 2) << 3) + ((3 - (i & 3)) << 1))) & 3u;
-      acc[i] += (code & 1u) ? cf : 0.0;
-      acc[i] += (code & 2u) ? c2 : 0.0;
+      for (int i = 0; i < 16; i++) {
+        const uint32_t code = (x >> (((i >> 2) << 3) + ((3 - (i & 3)) << 1))) & 3u;
+        acc[i] += (code & 1u) ? cf : 0.0;
+        acc[i] += (code & 2u) ? c2 : 0.0;
+      }
     }
-  }
-  double* out = rpart + (size_t)blockIdx.y * npad + (size_t)w * 16;
+    double* out = rpart + (size_t)chunk * npad + (size_t)w * 16;
 #pragma unroll
-  for (int i = 0; i < 16; i++) out[i] = acc[i];
+    for (int i = 0; i < 16; i++) out[i] = acc[i];
+  }
 }
 // r[i] = sum over chunks (fixed order); r[npad] = sum_s asq[s] (fixed-order tree of block 0)
 __global__ void __launch_bounds__(256) i8_rank1_reduce_kernel(const double* __restrict__ rpart, int nchunks, int npad, const double* __restrict__ asq,
@@ -751,8 +753,8 @@ int grm_accumulate_i8(eb_ctx* c, bool finalize_local, bool push_mode) {
   EB_CUDA(cudaMemcpyAsync(flag_h.data(), c->i8_flag.p, (size_t)nkb_all, cudaMemcpyDeviceToHost, c->stream));
   // the rank-one terms of the SNPs without missing genotypes run while the host decides the geometry
   {
-    dim3 grid((unsigned)(((c->wpitch >> 2) + 127) / 128), (unsigned)nchunks);
-    i8_rank1_kernel<<<grid, 128, 0, c->stream>>>(c->work.p, c->wpitch, c->mpad, coef, rpart, npad);
+    dim3 grid((unsigned)(((c->wpitch >> 2) + 127) / 128), (unsigned)std::min(nchunks, 65535));
+    i8_rank1_kernel<<<grid, 128, 0, c->stream>>>(c->work.p, c->wpitch, c->mpad, coef, rpart, npad, nchunks);
     EB_CHECK_LAUNCH(c);
     i8_rank1_reduce_kernel<<<(npad + 255) / 256, 256, 0, c->stream>>>(rpart, nchunks, npad, asq, c->mpad, rvec);
     EB_CHECK_LAUNCH(c);
