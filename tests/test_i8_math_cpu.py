@@ -92,3 +92,32 @@ def test_integer_formulation_matches_the_port():
     X += r[:, None] + r[None, :] + cc
     assert np.array_equal(X, X.T) or np.abs(X - X.T).max() <= 1e-13 * np.abs(X).max()
     assert np.abs(X - o["XTX"]).max() <= 1e-13 * np.abs(o["XTX"]).max()
+
+
+def test_skinny_operand_digits_and_the_packed_product():
+    """pg_i8.cu: out[s][l] = a_s sum_q 2^(e_l-7(q+1)) (V D^T)[s][(l,q)] + b_s sum_q ... (H D^T)[s][(l,q)] with D = signed 7-bit digits of
+    the FP64 operand on one power-of-two scale per column; integer sums in Python ints."""
+    rs = np.random.RandomState(5)
+    nsnp, nind, L = 40, 37, 3
+    g = synth.genotypes(8, nsnp, nind, missing=0.2)
+    a = rs.randn(nsnp); b = rs.rand(nsnp) + 0.2
+    B = rs.randn(nind, L) * 10.0 ** rs.uniform(-4, 4, size=(1, L))
+    X = np.where(g >= 0, a[:, None] + b[:, None] * g, 0.0)
+    want = X @ B
+    got = np.zeros((nsnp, L))
+    for l in range(L):
+        e = int(np.frexp(np.abs(B[:, l]).max())[1])
+        dig = [_digits(float(B[i, l]) / 2.0 ** e, 0) for i in range(nind)]         # |value| < 1 on the column's scale
+        for s in range(nsnp):
+            cv = [0] * NSL; ch = [0] * NSL
+            for i in range(nind):
+                if g[s, i] < 0:
+                    continue
+                for q in range(NSL):
+                    cv[q] += dig[i][q]
+                    ch[q] += int(g[s, i]) * dig[i][q]
+            sv = sum(cv[q] * 2.0 ** (-7 * (q + 1)) for q in range(NSL))
+            sh = sum(ch[q] * 2.0 ** (-7 * (q + 1)) for q in range(NSL))
+            got[s, l] = (a[s] * sv + b[s] * sh) * 2.0 ** e
+    scale = np.abs(want).max(axis=0, keepdims=True)
+    assert (np.abs(got - want) / scale).max() <= 1e-13
